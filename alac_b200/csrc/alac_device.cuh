@@ -1,0 +1,399 @@
+// alac_device.cuh -- device-side ALAC primitives shared by the encode and decode kernels.
+//
+// Everything here is exact integer arithmetic; the semantics follow the reference's host
+// primitives (file:line relative to /root/reference):
+//   predictor      codec/dp_enc.c:77-388 (pc_block), codec/dp_dec.c:55-381 (unpc_block)
+//   Golomb coder   codec/ag_enc.c:249-367 (dyn_comp), codec/ag_dec.c:272-362 (dyn_decomp)
+// but are re-shaped for one-chain-per-lane streaming: each primitive consumes / produces ONE
+// sample per call so predictor, entropy coder and (un)mixing fuse into a single pass with no
+// intermediate arrays.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace alacb {
+
+// ---- constants (codec/aglib.h:36-55, codec/dplib.h:40-45) ----------------------------------
+constexpr uint32_t kQbShift = 9;
+constexpr uint32_t kQb = 1u << kQbShift;
+constexpr uint32_t kPb0 = 40, kMb0 = 10, kKb0 = 14;
+constexpr uint32_t kMaxPrefix = 9;
+constexpr uint32_t kRunRawBits = 16;
+constexpr uint32_t kMeanClamp = 0xffffu;
+constexpr uint32_t kDenShift = 9;
+constexpr int kMaxRes = 4;
+constexpr int kMixBits = 2;
+
+enum : uint32_t { ID_SCE = 0, ID_CPE = 1, ID_CCE = 2, ID_LFE = 3, ID_DSE = 4, ID_PCE = 5, ID_FIL = 6, ID_END = 7 };
+
+// ---- tiny helpers ---------------------------------------------------------------------------
+__device__ __forceinline__ int32_t sext_bits(int32_t v, uint32_t chanshift)
+{
+    // "(x << chanshift) >> chanshift", codec/dp_enc.c:232
+    return (int32_t)((uint32_t)v << chanshift) >> chanshift;
+}
+__device__ __forceinline__ int32_t sext16(int32_t v) { return (int32_t)(int16_t)v; }
+__device__ __forceinline__ int32_t sign3(int32_t v) { return min(max(v, -1), 1); }
+__device__ __forceinline__ uint32_t bswap32(uint32_t v) { return __byte_perm(v, 0, 0x0123); }
+
+// ---- PCM sample access (packed little-endian) ------------------------------------------------
+// full-width, right-aligned, sign-extended sample; codec/matrix_enc.cu:72-99,120-159,186-282,330-391
+template <int DEPTH>
+__device__ __forceinline__ int32_t load_sample(const uint8_t *p)
+{
+    if (DEPTH == 16) {
+        return (int32_t)__ldg(reinterpret_cast<const int16_t *>(p));
+    } else if (DEPTH == 32) {
+        return __ldg(reinterpret_cast<const int32_t *>(p));
+    } else {
+        uint32_t w = (uint32_t)__ldg(p) | ((uint32_t)__ldg(p + 1) << 8) | ((uint32_t)__ldg(p + 2) << 16);
+        return DEPTH == 20 ? ((int32_t)(w << 8) >> 12) : ((int32_t)(w << 8) >> 8);
+    }
+}
+// raw container bits of one sample, as the escape path writes them (codec/ALACEncoder.cu:761-803)
+template <int DEPTH>
+__device__ __forceinline__ uint32_t load_raw_bits(const uint8_t *p)
+{
+    if (DEPTH == 16) return (uint32_t)__ldg(reinterpret_cast<const uint16_t *>(p));
+    if (DEPTH == 32) return (uint32_t)__ldg(reinterpret_cast<const int32_t *>(p));
+    uint32_t w = (uint32_t)__ldg(p) | ((uint32_t)__ldg(p + 1) << 8) | ((uint32_t)__ldg(p + 2) << 16);
+    return DEPTH == 20 ? (w >> 4) : w;
+}
+template <int DEPTH> struct DepthTraits {
+    static constexpr uint32_t kBytes = DEPTH == 16 ? 2 : DEPTH == 32 ? 4 : 3;
+    static constexpr uint32_t kShift = DEPTH == 32 ? 16 : DEPTH == 24 ? 8 : 0;   // codec/ALACEncoder.cu:327-332
+};
+template <int DEPTH>
+__device__ __forceinline__ void store_sample(uint8_t *p, int32_t v)
+{
+    // codec/ALACDecoder.cu:193-495 output packing
+    if (DEPTH == 16) {
+        *reinterpret_cast<int16_t *>(p) = (int16_t)v;
+    } else if (DEPTH == 32) {
+        *reinterpret_cast<int32_t *>(p) = v;
+    } else {
+        if (DEPTH == 20) v = (int32_t)((uint32_t)v << 4);
+        p[0] = (uint8_t)v; p[1] = (uint8_t)(v >> 8); p[2] = (uint8_t)(v >> 16);
+    }
+}
+
+// ---- sign-LMS predictor step -------------------------------------------------------------------
+// hist[0] = newest previous sample ... hist[TAPS-1], hist[TAPS] = "top" (codec/dp_enc.c:202-214).
+// Coefficients are carried as int32 holding int16 values; every update re-wraps to int16
+// exactly like the reference's int16_t registers.
+template <int TAPS>
+__device__ __forceinline__ void lms_adapt(int32_t (&a)[TAPS], const int32_t (&b)[TAPS], int32_t err)
+{
+    // codec/dp_enc.c:236-329.  Branch-free ladder: the walk goes from the last tap to the first and
+    // stops when the running error crosses zero; "live" masks the taps after the stop.
+    // For err < 0 the reference shifts the non-positive product (-|b|) >> 9, i.e. rounds toward
+    // -inf: -ceil(|b|/512) == -((|b| + 511) >> 9)  (dp_enc.c:288).
+    const int32_t sg = err > 0 ? 1 : -1;
+    const uint32_t rnd = err > 0 ? 0u : 511u;
+    int32_t left = abs(err);
+    bool live = (err != 0);
+#pragma unroll
+    for (int k = TAPS - 1; k >= 0; k--) {
+        const int32_t s = sign3(b[k]) * sg;
+        a[k] = live ? sext16(a[k] - s) : a[k];
+        const int32_t q = (int32_t)(((uint32_t)abs(b[k]) + rnd) >> kDenShift);
+        left -= (TAPS - k) * q;
+        live = live && (left > 0);
+    }
+}
+
+// encode: returns the residual of x given the history, adapts coefficients, shifts the history in
+template <int TAPS>
+__device__ __forceinline__ int32_t predict_enc_step(int32_t x, int32_t (&hist)[TAPS + 1], int32_t (&a)[TAPS], uint32_t chanshift)
+{
+    const int32_t top = hist[TAPS];
+    int32_t b[TAPS];
+    int32_t acc = 1 << (kDenShift - 1);
+#pragma unroll
+    for (int k = 0; k < TAPS; k++) {
+        b[k] = top - hist[k];
+        acc -= a[k] * b[k];
+    }
+    const int32_t err = sext_bits(x - top - (acc >> kDenShift), chanshift);     // dp_enc.c:228-233
+    lms_adapt<TAPS>(a, b, err);
+#pragma unroll
+    for (int k = TAPS; k > 0; k--) hist[k] = hist[k - 1];
+    hist[0] = x;
+    return err;
+}
+
+// decode: returns the reconstructed sample for residual err (codec/dp_dec.c:206-282)
+template <int TAPS>
+__device__ __forceinline__ int32_t predict_dec_step(int32_t err, int32_t (&hist)[TAPS + 1], int32_t (&a)[TAPS], uint32_t chanshift)
+{
+    const int32_t top = hist[TAPS];
+    int32_t b[TAPS];
+    int32_t acc = 1 << (kDenShift - 1);
+#pragma unroll
+    for (int k = 0; k < TAPS; k++) {
+        b[k] = top - hist[k];
+        acc -= a[k] * b[k];
+    }
+    const int32_t x = sext_bits(err + top + (acc >> kDenShift), chanshift);
+    lms_adapt<TAPS>(a, b, err);
+#pragma unroll
+    for (int k = TAPS; k > 0; k--) hist[k] = hist[k - 1];
+    hist[0] = x;
+    return x;
+}
+
+// ---- adaptive Golomb: streaming encoder state ------------------------------------------------------
+// dyn_comp consumes a block; here the same state machine is advanced one residual at a time.
+struct AgEnc {
+    uint32_t mb;        // running mean, codec/ag_enc.c:273
+    uint32_t zmode;     // 1 right after a zero run
+    uint32_t in_run;    // counting zeros (codec/ag_enc.c:328-350)
+    uint32_t nz;        // zeros counted so far
+    uint32_t c;         // samples consumed
+    uint32_t count;     // block length
+    uint32_t bits;      // bits produced
+    __device__ __forceinline__ void start(uint32_t n)
+    {
+        mb = kMb0; zmode = 0; in_run = 0; nz = 0; c = 0; count = n; bits = 0;
+    }
+};
+
+// MSB-first bit sink: 32-bit words, word w holds stream bits [32w, 32w+32) with bit 32w in the MSB
+struct BitSink {
+    uint32_t *dst;      // next word to write
+    uint32_t *end;      // capacity guard
+    uint64_t acc;
+    uint32_t nacc;
+    __device__ __forceinline__ void start(uint32_t *p, uint32_t cap_words) { dst = p; end = p + cap_words; acc = 0; nacc = 0; }
+    __device__ __forceinline__ void put(uint32_t value, uint32_t len)   // len 1..32, value < 2^len
+    {
+        acc = (acc << len) | value;
+        nacc += len;
+        if (nacc >= 32) {
+            nacc -= 32;
+            if (dst < end) *dst = (uint32_t)(acc >> nacc);
+            dst++;
+        }
+    }
+    __device__ __forceinline__ void finish()
+    {
+        if (nacc) {
+            if (dst < end) *dst = (uint32_t)(acc << (32 - nacc));
+            dst++;
+        }
+    }
+};
+struct NoSink {
+    __device__ __forceinline__ void put(uint32_t, uint32_t) {}
+};
+
+// exact n / (2^k - 1) for n < 9 * (2^k - 1): floor(2^32 / m) + 1, k = 0..15 (k = 0 unused)
+__constant__ uint32_t c_div_magic[16] = {
+    0u, 0u /* m = 1 handled apart */, 1431655766u, 613566757u, 286331154u, 138547333u, 68174085u, 33818641u,
+    16843010u, 8405025u, 4198405u, 2098178u, 1048833u, 524353u, 262161u, 131077u
+};
+
+// codec/ag_enc.c:115-148 dyn_code for a zero-run length
+template <bool EMIT, class Sink>
+__device__ __forceinline__ void ag_flush_run(AgEnc &s, Sink &sink, uint32_t zmode_after)
+{
+    const uint32_t k = (uint32_t)__clz((int)s.mb) - 24u + ((s.mb + 16u) >> 6);   // ag_enc.c:352
+    const uint32_t mz = ((1u << k) - 1u) & ((1u << kKb0) - 1u);
+    const uint32_t n = s.nz;
+    const uint32_t div = n / mz;
+    uint32_t len, value;
+    if (div < kMaxPrefix) {
+        const uint32_t mod = n - div * mz;
+        const uint32_t de = (mod == 0);
+        len = div + k + 1 - de;
+        value = (((1u << div) - 1u) << (len - div)) + mod + 1 - de;
+        if (len > kMaxPrefix + kRunRawBits) { len = kMaxPrefix + kRunRawBits; value = (((1u << kMaxPrefix) - 1u) << kRunRawBits) + n; }
+    } else {
+        len = kMaxPrefix + kRunRawBits;
+        value = (((1u << kMaxPrefix) - 1u) << kRunRawBits) + n;
+    }
+    s.bits += len;
+    if (EMIT) sink.put(value, len);
+    s.mb = 0;
+    s.zmode = zmode_after;
+    s.in_run = 0;
+}
+
+// one residual through dyn_comp's loop body (codec/ag_enc.c:277-361); encoder-side pb/kb/mb0 are
+// always 40/14/10 (codec/ALACEncoder.cu:365,435,515)
+template <bool EMIT, class Sink>
+__device__ __forceinline__ void ag_put(AgEnc &s, int32_t del, uint32_t bit_size, Sink &sink)
+{
+    if (s.in_run) {
+        if (del == 0) {
+            s.nz++;
+            s.c++;
+            if (s.nz >= 65535u) ag_flush_run<EMIT>(s, sink, 0u);
+            else if (s.c == s.count) ag_flush_run<EMIT>(s, sink, 1u);
+            return;
+        }
+        ag_flush_run<EMIT>(s, sink, 1u);
+    }
+    const uint32_t mb = s.mb;
+    uint32_t k = 31u - (uint32_t)__clz((int)((mb >> kQbShift) + 3u));
+    k = min(k, kKb0);
+    const uint32_t m = (1u << k) - 1u;
+    const uint32_t n = (uint32_t)((del << 1) ^ (del >> 31)) - s.zmode;           // ag_enc.c:287
+
+    // codec/ag_enc.c:151-184 dyn_code_32bit (numBits can never exceed 25 when div < 9, k <= 14)
+    if (n < kMaxPrefix * m) {
+        const uint32_t div = (k == 1) ? n : __umulhi(n, c_div_magic[k]);
+        const uint32_t mod = n - div * m;
+        const uint32_t de = (mod == 0);
+        const uint32_t len = div + k + 1 - de;
+        s.bits += len;
+        if (EMIT) sink.put((((1u << div) - 1u) << (len - div)) + mod + 1 - de, len);
+    } else {
+        s.bits += kMaxPrefix + bit_size;
+        if (EMIT) {
+            sink.put((1u << kMaxPrefix) - 1u, kMaxPrefix);
+            sink.put(bit_size == 32 ? n : (n & ((1u << bit_size) - 1u)), bit_size);
+        }
+    }
+    s.c++;
+    uint32_t nmb = kPb0 * (n + s.zmode) + mb - ((kPb0 * mb) >> kQbShift);       // ag_enc.c:314
+    if (n > kMeanClamp) nmb = kMeanClamp;
+    s.mb = nmb;
+    s.zmode = 0;
+    if (((nmb << 2) < kQb) && (s.c < s.count)) {                                  // ag_enc.c:324
+        s.in_run = 1;
+        s.nz = 0;
+    }
+}
+
+// ---- MSB-first bit reader over global memory (decoder) --------------------------------------------------
+// Reads 32-bit aligned words (byte-swapped) and keeps a 64-bit window; positions are in bits from
+// the packet's first byte.  Words past the packet's last byte read as zero.
+struct BitReader {
+    const uint32_t *base;   // 4-byte aligned address at or before the packet
+    uint32_t bias;          // bit offset of the packet's first bit inside base[0]
+    uint32_t last_word;     // index of the last word holding packet bytes
+    uint32_t wi;            // index of w0
+    uint32_t w0, w1;
+    uint32_t pos;           // current bit position (packet relative)
+    bool valid;             // false for an empty packet: every read gives zero
+
+    __device__ __forceinline__ uint32_t word(uint32_t i) const { return (valid && i <= last_word) ? bswap32(__ldg(base + i)) : 0u; }
+    __device__ __forceinline__ void start(const uint8_t *packet, uint32_t nbytes)
+    {
+        const uintptr_t addr = reinterpret_cast<uintptr_t>(packet);
+        base = reinterpret_cast<const uint32_t *>(addr & ~(uintptr_t)3);
+        bias = (uint32_t)(addr & 3u) * 8u;
+        valid = nbytes != 0;
+        last_word = valid ? (bias + nbytes * 8u - 1u) >> 5 : 0u;
+        pos = 0;
+        wi = 0;
+        w0 = word(0);
+        w1 = word(1);
+    }
+    __device__ __forceinline__ uint32_t peek32_at(uint32_t p)
+    {
+        const uint32_t abs_bit = bias + p;
+        const uint32_t i = abs_bit >> 5;
+        if (i != wi) {
+            if (i == wi + 1) { w0 = w1; w1 = word(i + 1); }
+            else { w0 = word(i); w1 = word(i + 1); }
+            wi = i;
+        }
+        return __funnelshift_l(w1, w0, abs_bit & 31u);
+    }
+    __device__ __forceinline__ uint32_t peek32() { return peek32_at(pos); }
+    __device__ __forceinline__ uint32_t get(uint32_t nbits)   // 0..32
+    {
+        if (nbits == 0) return 0;
+        const uint32_t v = peek32() >> (32u - nbits);
+        pos += nbits;
+        return v;
+    }
+};
+
+// codec/ag_dec.c:220-270 dyn_get_32bit
+__device__ __forceinline__ uint32_t ag_get_sample(BitReader &br, uint32_t m, uint32_t k, uint32_t maxbits)
+{
+    const uint32_t window = br.peek32();
+    const uint32_t pre = (uint32_t)__clz((int)~window);
+    uint32_t result;
+    if (pre >= kMaxPrefix) {
+        br.pos += kMaxPrefix;
+        result = br.get(maxbits);
+    } else {
+        result = pre;
+        br.pos += pre + 1;
+        if (k != 1) {
+            const uint32_t v = (window << (pre + 1)) >> (32u - k);
+            br.pos += k - 1;
+            result = pre * m;
+            if (v >= 2) { result += v - 1; br.pos += 1; }
+        }
+    }
+    return result;
+}
+
+// codec/ag_dec.c:171-217 dyn_get
+__device__ __forceinline__ uint32_t ag_get_run(BitReader &br, uint32_t m, uint32_t k)
+{
+    const uint32_t window = br.peek32();
+    const uint32_t pre = (uint32_t)__clz((int)~window);
+    uint32_t result;
+    if (pre >= kMaxPrefix) {
+        result = (window << kMaxPrefix) >> (32u - kRunRawBits);
+        br.pos += kMaxPrefix + kRunRawBits;
+    } else {
+        const uint32_t v = (window << (pre + 1)) >> (32u - k);
+        br.pos += pre + 1 + k;
+        result = pre * m + v - 1;
+        if (v < 2) { result -= (v - 1); br.pos -= 1; }
+    }
+    return result;
+}
+
+// streaming dyn_decomp (codec/ag_dec.c:272-362): next() yields one residual per call
+struct AgDec {
+    uint32_t mb, zmode, pending_zeros, c, count;
+    uint32_t pb, kb, wb, max_size;
+    uint32_t start_rel;     // first bit's byte-floor, for the reference's "bitPos < maxPos" test
+    int32_t status;
+    __device__ __forceinline__ void start(const BitReader &br, uint32_t n, uint32_t mb0, uint32_t pb_, uint32_t kb_, uint32_t max_size_)
+    {
+        mb = mb0; zmode = 0; pending_zeros = 0; c = 0; count = n;
+        pb = pb_; kb = kb_; wb = (1u << kb_) - 1u; max_size = max_size_;
+        start_rel = br.pos & ~7u;
+        status = 0;
+    }
+    // cap_bits = packet bytes * 8
+    __device__ __forceinline__ int32_t next(BitReader &br, uint32_t cap_bits)
+    {
+        if (pending_zeros) { pending_zeros--; c++; return 0; }
+        if (status) { c++; return 0; }
+        if (!((br.pos - start_rel) < cap_bits)) { status = -50; c++; return 0; }      // ag_dec.c:302
+        uint32_t k = 31u - (uint32_t)__clz((int)((mb >> kQbShift) + 3u));
+        k = min(k, kb);
+        const uint32_t m = (1u << k) - 1u;
+        const uint32_t n = ag_get_sample(br, m, k, max_size);
+        const uint32_t nd = n + zmode;
+        const int32_t mult = (-(int32_t)(nd & 1u)) | 1;
+        const int32_t del = (int32_t)(((nd + 1u) >> 1) * (uint32_t)mult);              // ag_dec.c:313-319
+        c++;
+        mb = pb * (n + zmode) + mb - ((pb * mb) >> kQbShift);
+        if (n > kMeanClamp) mb = kMeanClamp;
+        zmode = 0;
+        if (((mb << 2) < kQb) && (c < count)) {                                          // ag_dec.c:334
+            zmode = 1;
+            k = (uint32_t)__clz((int)mb) - 24u + ((mb + 16u) >> 6);
+            const uint32_t mz = ((1u << k) - 1u) & wb;
+            const uint32_t run = ag_get_run(br, mz, k);
+            if (!(c + run <= count)) { status = -50; }                                   // ag_dec.c:341
+            else pending_zeros = run;
+            if (run >= 65535u) zmode = 0;
+            mb = 0;
+        }
+        return del;
+    }
+};
+
+}  // namespace alacb

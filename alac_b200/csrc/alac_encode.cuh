@@ -1,0 +1,601 @@
+// alac_encode.cuh -- encode kernels.
+//
+//   enc_search_kernel   one lane per (segment, channel): the whole serial chain of
+//                       EncodeStereo / EncodeMono (codec/ALACEncoder.cu:290-558, :812-963) --
+//                       mixRes search, numU/numV search, escape estimate, final predictor +
+//                       Golomb pass -- fused sample by sample; U and V of a pair sit on adjacent
+//                       lanes and exchange bit counts by shuffle.  Emits each channel's Golomb
+//                       stream into a private scratch slab and one ElemRec per element.
+//   enc_size_kernel     packet byte sizes from the element records.
+//   enc_assemble_kernel one warp per packet: gathers header / shift bytes / Golomb streams /
+//                       escape samples into the packet at its scanned offset (32-bit stores).
+#pragma once
+#include "alac_device.cuh"
+
+namespace alacb {
+
+// per (packet, element) result of the search kernel
+struct ElemRec {
+    uint32_t bits_u, bits_v;      // final-pass Golomb bits per channel
+    uint32_t elem_bits;           // total element size in bits incl. tag + instance
+    uint8_t escape;               // 0 compressed, 1 escape by estimate, 2 escape by post-check
+    uint8_t mix_res, num_u, num_v;
+    int16_t coef_u[8], coef_v[8]; // coefficients as written in the header (before the final pass)
+};
+
+struct EncLayout {
+    uint32_t channels;
+    uint32_t frame_size;
+    uint32_t fast_mode;
+    uint32_t elems_per_packet;
+    uint32_t chains_per_packet;
+    // per element (packet order): tag, first channel, per-type instance tag, first chain index
+    uint8_t elem_tag[8], elem_chan[8], elem_inst[8], elem_chain[8];
+};
+
+struct EncArgs {
+    const uint8_t *pcm;           // device, interleaved
+    const uint64_t *pkt_frame;    // per packet: first sample-frame (index into pcm)
+    const uint32_t *pkt_samples;  // per packet: sample-frames in it
+    const uint32_t *seg_first;    // per segment: first packet
+    const uint32_t *seg_count;    // per segment: packets in it
+    const uint32_t *seg_stream;   // per segment: stream index | 0x80000000 if first | 0x40000000 if last of stream
+    uint32_t seg_base;            // chunk: first segment handled by this launch
+    uint32_t num_segments;        // chunk: segments handled by this launch
+    uint32_t pkt_base;            // chunk: first packet (recs / scratch are chunk-relative)
+    EncLayout lay;
+    ElemRec *recs;                // [packet][elem]
+    uint32_t *scratch;            // [packet][chain][cap_words]
+    uint32_t cap_words;
+    int16_t *state;               // optional [stream][8][2][2][8]
+};
+
+// ---- sample sources -------------------------------------------------------------------------------
+// One lane's view of its channel after the reference's mix/copy stage (codec/matrix_enc.cu,
+// codec/ALACEncoder.cu:1144-1382): get(j) is u[j] (U lane) or v[j] (V lane); samples at or
+// beyond `valid` read as zero (deterministic-padding rule).
+template <int DEPTH, bool STEREO>
+struct MixSrc {
+    const uint8_t *base;    // sample-frame 0 of the packet, first channel of the element
+    uint32_t stride;        // bytes per sample-frame
+    uint32_t valid;
+    int32_t mix_res;
+    bool is_v;
+    __device__ __forceinline__ int32_t get(uint32_t j) const
+    {
+        if (j >= valid) return 0;
+        const uint8_t *p = base + (size_t)j * stride;
+        constexpr uint32_t sh = DepthTraits<DEPTH>::kShift;
+        if (!STEREO) {
+            return load_sample<DEPTH>(p) >> sh;
+        } else {
+            const int32_t l = load_sample<DEPTH>(p) >> sh;
+            const int32_t r = load_sample<DEPTH>(p + DepthTraits<DEPTH>::kBytes) >> sh;
+            if (mix_res != 0) {
+                return is_v ? (l - r) : ((mix_res * l + ((1 << kMixBits) - mix_res) * r) >> kMixBits);
+            }
+            return is_v ? r : l;
+        }
+    }
+};
+
+// pc_block(in, res, num, coefs, TAPS) streamed: sink(j, residual) is called for j = 0..max(num,TAPS+1)-1
+// exactly as the reference writes pc1[j] (warm-up entries 1..TAPS are written regardless of num,
+// codec/dp_enc.c:108-112).
+template <int TAPS, class Src, class Sink>
+__device__ __forceinline__ void predict_pass(const Src &src, uint32_t num, int32_t (&a)[TAPS], uint32_t chanshift, Sink &sink)
+{
+    int32_t hist[TAPS + 1];
+    int32_t prev = src.get(0);
+    sink(0u, prev);
+    hist[TAPS] = prev;
+#pragma unroll
+    for (int j = 1; j <= TAPS; j++) {
+        const int32_t x = src.get((uint32_t)j);
+        sink((uint32_t)j, sext_bits(x - prev, chanshift));
+        hist[TAPS - j] = x;
+        prev = x;
+    }
+    for (uint32_t j = TAPS + 1; j < num; j++) {
+        const int32_t x = src.get(j);
+        const int32_t err = predict_enc_step<TAPS>(x, hist, a, chanshift);
+        sink(j, err);
+    }
+}
+
+struct NullSink {
+    __device__ __forceinline__ void operator()(uint32_t, int32_t) const {}
+};
+
+// Golomb bit-costing sink; optionally keeps the residuals (the stage-B "stale tail")
+struct CostSink {
+    AgEnc ag;
+    uint32_t bit_size;
+    int32_t *keep;      // may be null
+    __device__ __forceinline__ void operator()(uint32_t j, int32_t err)
+    {
+        if (j < ag.count) {
+            NoSink ns;
+            ag_put<false>(ag, err, bit_size, ns);
+            if (keep) keep[j] = err;
+        }
+    }
+};
+
+struct EmitSink {
+    AgEnc ag;
+    BitSink bits;
+    uint32_t bit_size;
+    __device__ __forceinline__ void operator()(uint32_t j, int32_t err)
+    {
+        if (j < ag.count) ag_put<true>(ag, err, bit_size, bits);
+    }
+};
+
+__device__ __forceinline__ void init_coefs_row(int32_t *a, int n)
+{
+    // codec/dp_enc.c:49-60 with denshift 9
+    for (int k = 0; k < n; k++) a[k] = 0;
+    a[0] = (38 * 512) >> 4;
+    a[1] = (-29 * 512) >> 4;
+    a[2] = (-2 * 512) >> 4;
+}
+
+template <int DEPTH, bool STEREO>
+__global__ void __launch_bounds__(128)
+enc_search_kernel(EncArgs A, uint32_t elems_of_kind, uint32_t kind_elem0 /* bitmask of element slots of this kind */)
+{
+    constexpr uint32_t kLanesPerJob = STEREO ? 2 : 1;
+    const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t job = tid / kLanesPerJob;
+    const bool is_v = STEREO && (tid & 1u);
+    const uint32_t total_jobs = A.num_segments * elems_of_kind;
+    // lanes of a pair are both in or both out, so the shuffles below stay converged per pair
+    if (job >= total_jobs) return;
+    const uint32_t pair_mask = STEREO ? (3u << ((threadIdx.x & 31u) & ~1u)) : 0u;
+
+    const uint32_t seg = A.seg_base + job / elems_of_kind;
+    uint32_t which = job % elems_of_kind;
+    // slot = index of the which-th element of this kind inside the packet
+    uint32_t slot = 0;
+    for (uint32_t s = 0, m = kind_elem0; s < 8; s++, m >>= 1) {
+        if (m & 1u) { if (which == 0) { slot = s; break; } which--; }
+    }
+    const uint32_t chan = A.lay.elem_chan[slot];
+    const uint32_t chain = A.lay.elem_chain[slot] + (is_v ? 1u : 0u);
+    constexpr uint32_t bps = DepthTraits<DEPTH>::kBytes;
+    constexpr uint32_t shift = DepthTraits<DEPTH>::kShift;
+    const uint32_t stride = A.lay.channels * bps;
+    const uint32_t chan_bits = DEPTH - shift + (STEREO ? 1u : 0u);                 // :334 / :857
+    const uint32_t chanshift = 32u - chan_bits;
+
+    // coefficient rows 3 (4 taps) and 7 (8 taps) of this channel (codec/ALACEncoder.h:89-90)
+    int32_t c4[4], c8[8];
+    const uint32_t seg_info = A.seg_stream[seg];
+    const uint32_t stream = seg_info & 0x3fffffffu;
+    int16_t *st = A.state ? A.state + ((size_t)stream * 8 + chan) * 32 + (is_v ? 16 : 0) : nullptr;
+    if (st && (seg_info & 0x80000000u)) {
+        for (int k = 0; k < 4; k++) c4[k] = st[k];
+        for (int k = 0; k < 8; k++) c8[k] = st[8 + k];
+    } else {
+        init_coefs_row(c4, 4);
+        init_coefs_row(c8, 8);
+    }
+
+    const uint32_t p0 = A.seg_first[seg];
+    const uint32_t pn = A.seg_count[seg];
+    for (uint32_t pi = 0; pi < pn; pi++) {
+        const uint32_t pkt = p0 + pi;
+        const uint32_t n = A.pkt_samples[pkt];
+        const uint8_t *base = A.pcm + (A.pkt_frame[pkt] * A.lay.channels + chan) * bps;
+        uint32_t *slab = A.scratch + ((size_t)(pkt - A.pkt_base) * A.lay.chains_per_packet + chain) * A.cap_words;
+        const uint32_t partial = (n != A.lay.frame_size);
+
+        MixSrc<DEPTH, STEREO> src;
+        src.base = base; src.stride = stride; src.is_v = is_v; src.mix_res = 0; src.valid = n;
+
+        uint32_t best_res = 0;
+        uint32_t num_mine = 8;           // taps chosen for this lane's channel
+        uint32_t metric_mine = 0;
+        int do_escape = 0;
+
+        const bool fast = STEREO && A.lay.fast_mode;   // EncodeMono has no fast variant
+        if (!fast) {
+            if (STEREO) {
+                // stage A: mixRes search, first n/8 samples, chained on row 7 (:353-379)
+                const uint32_t na = n / 8;
+                uint32_t min_bits = 1u << 31;
+                for (int r = 0; r <= kMaxRes; r++) {
+                    src.mix_res = r;
+                    src.valid = na;
+                    CostSink cs;
+                    cs.ag.start(na);
+                    cs.bit_size = chan_bits;
+                    cs.keep = (r == kMaxRes) ? reinterpret_cast<int32_t *>(slab) : nullptr;
+                    predict_pass<8>(src, na, c8, chanshift, cs);
+                    const uint32_t both = cs.ag.bits + __shfl_xor_sync(pair_mask, cs.ag.bits, 1);
+                    if (both < min_bits) { min_bits = both; best_res = (uint32_t)r; }
+                }
+                src.mix_res = (int32_t)best_res;
+                src.valid = n;
+            }
+            // stage B: taps search (:418-452 stereo, :881-905 mono)
+            uint32_t best_metric = 1u << 31;
+            num_mine = 4;
+            const uint32_t nb = n / 32, nc = n / 8;
+#pragma unroll 1
+            for (uint32_t taps = 4; taps <= 8; taps += 4) {
+                CostSink cs;
+                cs.ag.start(nc);
+                cs.bit_size = chan_bits;
+                cs.keep = nullptr;
+                NullSink null_sink;
+                if (taps == 4) {
+                    for (int pass = 0; pass < 7; pass++) predict_pass<4>(src, nb, c4, chanshift, null_sink);
+                    predict_pass<4>(src, STEREO ? nb : nc, c4, chanshift, cs);
+                } else {
+                    for (int pass = 0; pass < 7; pass++) predict_pass<8>(src, nb, c8, chanshift, null_sink);
+                    predict_pass<8>(src, STEREO ? nb : nc, c8, chanshift, cs);
+                }
+                if (STEREO) {
+                    // residuals [max(n/32, taps+1), n/8) are what the mixRes=4 trial left behind (F4)
+                    const int32_t *stale = reinterpret_cast<const int32_t *>(slab);
+                    NoSink ns;
+                    for (uint32_t j = max(nb, taps + 1); j < nc; j++) ag_put<false>(cs.ag, stale[j], chan_bits, ns);
+                }
+                const uint32_t metric = cs.ag.bits * 8 + 16 * taps;
+                if (metric < best_metric) { best_metric = metric; num_mine = taps; }
+            }
+            metric_mine = best_metric;
+            // escape estimate (:455-461 stereo, :909-915 mono)
+            if (STEREO) {
+                const uint32_t other = __shfl_xor_sync(pair_mask, metric_mine, 1);
+                uint32_t min_bits = metric_mine + other + 64 + (partial ? 32u : 0u);
+                if (shift) min_bits += n * shift * 2;
+                const uint32_t escape_bits = n * DEPTH * 2 + (partial ? 32u : 0u) + 16;
+                do_escape = (min_bits >= escape_bits);
+            } else {
+                uint32_t min_bits = metric_mine + 32 + (partial ? 32u : 0u);
+                if (shift) min_bits += n * shift;
+                const uint32_t escape_bits = n * DEPTH + (partial ? 32u : 0u) + 16;
+                do_escape = (min_bits >= escape_bits);
+            }
+        }
+
+        // header coefficients are the post-search, pre-final-pass values (:479-485)
+        ElemRec *rec = A.recs + (size_t)(pkt - A.pkt_base) * A.lay.elems_per_packet + slot;
+        {
+            int16_t *hc = is_v ? rec->coef_v : rec->coef_u;
+            if (num_mine == 4) { for (int k = 0; k < 4; k++) hc[k] = (int16_t)c4[k]; for (int k = 4; k < 8; k++) hc[k] = 0; }
+            else { for (int k = 0; k < 8; k++) hc[k] = (int16_t)c8[k]; }
+        }
+
+        uint32_t my_bits = 0;
+        if (!do_escape) {
+            // stage C: final predictor + Golomb pass over the whole frame (:507-531, :941-945)
+            EmitSink es;
+            es.ag.start(n);
+            es.bit_size = chan_bits;
+            es.bits.start(slab, A.cap_words);
+            if (num_mine == 4) predict_pass<4>(src, n, c4, chanshift, es);
+            else predict_pass<8>(src, n, c8, chanshift, es);
+            es.bits.finish();
+            my_bits = es.ag.bits;
+        }
+
+        // sizes, post-check (:537-543, :952-958; fast mode :703-725)
+        uint32_t other_bits = 0, other_num = 0;
+        if (STEREO) {
+            other_bits = __shfl_xor_sync(pair_mask, my_bits, 1);
+            other_num = __shfl_xor_sync(pair_mask, num_mine, 1);
+        }
+        const uint32_t escape_bits = n * DEPTH * kLanesPerJob + (partial ? 32u : 0u) + 16;
+        uint32_t body_bits;     // element bits after tag+instance when compressed
+        if (STEREO) body_bits = 12 + 4 + (partial ? 32u : 0u) + 16 + (16 + 16 * num_mine) + (16 + 16 * other_num) + n * shift * 2 + my_bits + other_bits;
+        else        body_bits = 12 + 4 + (partial ? 32u : 0u) + 16 + (16 + 16 * num_mine) + n * shift + my_bits;
+        if (!do_escape) {
+            if (fast) {
+                uint32_t min_bits = (my_bits + num_mine * 16) + (other_bits + other_num * 16) + 64 + (partial ? 32u : 0u);
+                if (shift) min_bits += n * shift * 2;
+                if (min_bits >= escape_bits) do_escape = 2;
+            }
+            if (!do_escape && body_bits >= escape_bits) do_escape = 2;
+        }
+        if (!is_v) {
+            rec->escape = (uint8_t)do_escape;
+            rec->mix_res = (uint8_t)best_res;
+            rec->bits_u = my_bits;
+            rec->bits_v = other_bits;
+            rec->num_u = (uint8_t)num_mine;
+            rec->num_v = (uint8_t)other_num;
+            rec->elem_bits = 7 + (do_escape ? (12 + 4 + (partial ? 32u : 0u) + n * DEPTH * kLanesPerJob) : body_bits);
+        }
+    }
+
+    if (st && (seg_info & 0x40000000u)) {
+        for (int k = 0; k < 4; k++) st[k] = (int16_t)c4[k];
+        for (int k = 4; k < 8; k++) st[k] = 0;
+        for (int k = 0; k < 8; k++) st[8 + k] = (int16_t)c8[k];
+    }
+}
+
+// ---- packet sizes ------------------------------------------------------------------------------------
+__global__ void enc_size_kernel(const ElemRec *recs, uint32_t elems_per_packet, uint32_t num_packets,
+                                uint32_t *sizes, unsigned long long *escapes)
+{
+    const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= num_packets) return;
+    uint32_t bits = 3;      // ID_END, codec/ALACEncoder.cu:1036
+    uint32_t esc = 0;
+    for (uint32_t e = 0; e < elems_per_packet; e++) {
+        const ElemRec &r = recs[(size_t)p * elems_per_packet + e];
+        bits += r.elem_bits;
+        esc += r.escape ? 1u : 0u;
+    }
+    sizes[p] = (bits + 7) >> 3;     // byte-align, :1039
+    if (esc) atomicAdd(escapes, (unsigned long long)esc);
+}
+
+// ---- exclusive scan (single block, sequential tiles) -------------------------------------------------------
+// offsets[i] = sum_{j<i} sizes[j]; offsets[n] = total.  One 1024-thread block walks the array in tiles.
+__global__ void __launch_bounds__(1024) scan_u32_to_u64_kernel(const uint32_t *in, uint64_t *out, uint64_t n, uint32_t *max_out, int chain_base)
+{
+    __shared__ uint64_t warp_sums[32];
+    __shared__ uint64_t carry_s;
+    __shared__ uint32_t warp_max[32];
+    const uint32_t lane = threadIdx.x & 31u, wid = threadIdx.x >> 5;
+    // chain_base: continue from out[0], which the previous chunk's scan left as its grand total
+    if (threadIdx.x == 0) carry_s = chain_base ? out[0] : 0;
+    __syncthreads();
+    uint32_t my_max = 0;
+    for (uint64_t tile = 0; tile < n; tile += 1024) {
+        const uint64_t i = tile + threadIdx.x;
+        const uint32_t v = i < n ? in[i] : 0u;
+        my_max = max(my_max, v);
+        uint64_t x = v;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint64_t y = __shfl_up_sync(0xffffffffu, x, d);
+            if (lane >= (uint32_t)d) x += y;
+        }
+        if (lane == 31) warp_sums[wid] = x;
+        __syncthreads();
+        if (wid == 0) {
+            uint64_t s = warp_sums[lane];
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const uint64_t y = __shfl_up_sync(0xffffffffu, s, d);
+                if (lane >= (uint32_t)d) s += y;
+            }
+            warp_sums[lane] = s;
+        }
+        __syncthreads();
+        const uint64_t carry = carry_s;
+        const uint64_t incl = x + (wid ? warp_sums[wid - 1] : 0) + carry;
+        if (i < n) out[i] = incl - v;
+        __syncthreads();
+        if (threadIdx.x == 1023) carry_s = incl;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) out[n] = carry_s;
+    if (max_out) {
+        for (int d = 16; d; d >>= 1) my_max = max(my_max, __shfl_xor_sync(0xffffffffu, my_max, d));
+        if (lane == 0) warp_max[wid] = my_max;
+        __syncthreads();
+        if (wid == 0) {
+            uint32_t m = warp_max[lane];
+            for (int d = 16; d; d >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, d));
+            if (lane == 0) atomicMax(max_out, m);
+        }
+    }
+}
+
+// ---- packet assembly --------------------------------------------------------------------------------------
+enum : uint32_t { REG_WORDS = 0, REG_SHIFT = 1, REG_RAW = 2 };
+struct Region {
+    uint32_t dst;       // first bit inside the packet
+    uint32_t nbits;
+    uint32_t kind;
+    uint32_t elem;      // element slot (REG_SHIFT / REG_RAW)
+    const uint32_t *words;   // REG_WORDS: MSB-first words (shared or global)
+};
+
+__device__ __forceinline__ uint32_t bits_from_words(const uint32_t *w, uint32_t off, uint32_t nb)
+{
+    // nb 1..32 bits starting at bit `off` of an MSB-first word array (reads w[i] and, if needed, w[i+1])
+    const uint32_t i = off >> 5, sh = off & 31u;
+    const uint32_t hi = w[i];
+    const uint32_t lo = (sh + nb > 32u) ? w[i + 1] : 0u;
+    return __funnelshift_l(lo, hi, sh) >> (32u - nb);
+}
+
+// fixed-width entry arrays (shift region, escape samples): bits [off, off+nb) of the
+// concatenation of W-bit entries
+template <class EntryFn>
+__device__ __forceinline__ uint32_t bits_from_entries(uint32_t W, uint32_t off, uint32_t nb, EntryFn entry)
+{
+    uint32_t i = off / W;
+    const uint32_t bo = off - i * W;
+    uint64_t acc = 0;
+    uint32_t filled = 0;
+    while (filled < bo + nb) {
+        acc = (W == 32 ? (acc << 32) : (acc << W)) | (uint64_t)entry(i++);
+        filled += W;
+    }
+    const uint64_t v = acc >> (filled - bo - nb);
+    return nb == 32 ? (uint32_t)v : ((uint32_t)v & ((1u << nb) - 1u));
+}
+
+struct AsmArgs {
+    const uint8_t *pcm;
+    const uint64_t *pkt_frame;
+    const uint32_t *pkt_samples;
+    const ElemRec *recs;
+    const uint32_t *scratch;
+    uint32_t cap_words;
+    const uint32_t *sizes;
+    const uint64_t *offsets;
+    uint8_t *out;
+    uint32_t pkt_base;            // chunk: first packet; recs / scratch are chunk-relative
+    uint32_t num_packets;         // chunk: packets handled by this launch
+    EncLayout lay;
+};
+
+constexpr int kAsmWarps = 4;
+constexpr int kHdrWords = 13;       // 7 + 16 + 32 + 16 + 2*(16+128) = 359 bits
+constexpr int kMaxRegions = 8 * 4 + 1;
+
+template <int DEPTH>
+__global__ void __launch_bounds__(kAsmWarps * 32) enc_assemble_kernel(AsmArgs A)
+{
+    __shared__ uint32_t s_hdr[kAsmWarps][8][kHdrWords];
+    __shared__ Region s_reg[kAsmWarps][kMaxRegions];
+    __shared__ uint32_t s_nreg[kAsmWarps];
+    __shared__ uint32_t s_end_word[kAsmWarps];
+
+    const uint32_t lane = threadIdx.x & 31u, wid = threadIdx.x >> 5;
+    const uint32_t rel = blockIdx.x * kAsmWarps + wid;      // chunk-relative packet
+    if (rel >= A.num_packets) return;
+    const uint32_t pkt = A.pkt_base + rel;
+    constexpr uint32_t bps = DepthTraits<DEPTH>::kBytes;
+    constexpr uint32_t shift = DepthTraits<DEPTH>::kShift;
+    const uint32_t n = A.pkt_samples[pkt];
+    const uint32_t partial = (n != A.lay.frame_size);
+    const uint32_t E = A.lay.elems_per_packet;
+    const uint32_t stride = A.lay.channels * bps;
+    const uint8_t *frame_base = A.pcm + A.pkt_frame[pkt] * A.lay.channels * bps;
+
+    // lanes 0..E-1 build their element's header words
+    if (lane < E) {
+        const ElemRec &r = A.recs[(size_t)rel * E + lane];
+        uint32_t *h = s_hdr[wid][lane];
+        BitSink bs;
+        bs.start(h, kHdrWords);
+        const uint32_t tag = A.lay.elem_tag[lane];
+        const bool stereo = (tag == ID_CPE);
+        bs.put(tag, 3);
+        bs.put(A.lay.elem_inst[lane], 4);
+        bs.put(0, 12);
+        if (r.escape) {
+            bs.put((partial << 3) | 1u, 4);                                       // :761-765
+            if (partial) bs.put(n, 32);
+        } else {
+            bs.put((partial << 3) | ((shift / 8) << 1), 4);                       // :466-471
+            if (partial) bs.put(n, 32);
+            bs.put(stereo ? (uint32_t)kMixBits : 0u, 8);
+            bs.put(stereo ? (uint32_t)r.mix_res : 0u, 8);
+            bs.put((0u << 4) | kDenShift, 8);                                     // :477-485
+            bs.put((4u << 5) | r.num_u, 8);
+            for (uint32_t i = 0; i < r.num_u; i++) bs.put((uint16_t)r.coef_u[i], 16);
+            if (stereo) {
+                bs.put((0u << 4) | kDenShift, 8);
+                bs.put((4u << 5) | r.num_v, 8);
+                for (uint32_t i = 0; i < r.num_v; i++) bs.put((uint16_t)r.coef_v[i], 16);
+            }
+        }
+        bs.finish();
+    }
+    __syncwarp();
+    // lane 0 lays out the regions
+    if (lane == 0) {
+        uint32_t nr = 0, at = 0;
+        Region *R = s_reg[wid];
+        for (uint32_t e = 0; e < E; e++) {
+            const ElemRec &r = A.recs[(size_t)rel * E + e];
+            const bool stereo = (A.lay.elem_tag[e] == ID_CPE);
+            const uint32_t nch = stereo ? 2u : 1u;
+            uint32_t hb;
+            if (r.escape) hb = 7 + 16 + (partial ? 32u : 0u);
+            else hb = 7 + 16 + (partial ? 32u : 0u) + 16 + (16 + 16 * r.num_u) + (stereo ? (16 + 16 * r.num_v) : 0u);
+            R[nr++] = Region{at, hb, REG_WORDS, e, s_hdr[wid][e]};
+            at += hb;
+            if (r.escape) {
+                if (n) { R[nr++] = Region{at, n * nch * DEPTH, REG_RAW, e, nullptr}; at += n * nch * DEPTH; }
+            } else {
+                if (shift && n) { R[nr++] = Region{at, n * nch * shift, REG_SHIFT, e, nullptr}; at += n * nch * shift; }
+                const uint32_t *su = A.scratch + ((size_t)rel * A.lay.chains_per_packet + A.lay.elem_chain[e]) * A.cap_words;
+                if (r.bits_u) { R[nr++] = Region{at, r.bits_u, REG_WORDS, e, su}; at += r.bits_u; }
+                if (stereo && r.bits_v) { R[nr++] = Region{at, r.bits_v, REG_WORDS, e, su + A.cap_words}; at += r.bits_v; }
+            }
+        }
+        // ID_END (3 bits of ones); padding bits stay zero
+        s_end_word[wid] = 0xE0000000u;
+        R[nr++] = Region{at, 3, REG_WORDS, 0, &s_end_word[wid]};
+        s_nreg[wid] = nr;
+    }
+    __syncwarp();
+
+    const uint32_t nreg = s_nreg[wid];
+    const Region *R = s_reg[wid];
+    const uint32_t size = A.sizes[pkt];
+    uint8_t *dst = A.out + A.offsets[pkt];
+    // output is written as 4-byte words aligned in the OUTPUT buffer; a = bytes before the first aligned word
+    const uint32_t mis = (uint32_t)(reinterpret_cast<uintptr_t>(dst) & 3u);
+    const uint32_t lead_bytes = mis ? (4u - mis) : 0u;     // bytes of the packet before the first aligned word
+    // word g (g >= 0) covers packet bytes [lead + 4g, lead + 4g + 4); g = -1 is the leading partial word
+    const uint32_t words_total = size > lead_bytes ? (size - lead_bytes + 3) / 4 : 0u;
+    uint32_t cursor = 0;
+    // gather the bits [bit0, bit0 + 8*nbytes) of the packet into an MSB-first word
+    auto gather = [&](uint32_t byte0, uint32_t nbytes) -> uint32_t {
+        const uint32_t bit0 = byte0 * 8u, bit1 = bit0 + nbytes * 8u;
+        uint32_t word = 0;
+        while (cursor < nreg && R[cursor].dst + R[cursor].nbits <= bit0) cursor++;
+        for (uint32_t ri = cursor; ri < nreg && R[ri].dst < bit1; ri++) {
+            const Region &r = R[ri];
+            const uint32_t lo = max(bit0, r.dst), hi = min(bit1, r.dst + r.nbits);
+            const uint32_t off = lo - r.dst, nb = hi - lo;
+            uint32_t v;
+            if (r.kind == REG_WORDS) {
+                v = bits_from_words(r.words, off, nb);
+            } else {
+                const bool stereo = (A.lay.elem_tag[r.elem] == ID_CPE);
+                const uint8_t *eb = frame_base + (size_t)A.lay.elem_chan[r.elem] * bps;
+                if (r.kind == REG_SHIFT) {
+                    // :488-500 stereo (loL << s) | loR in 2s bits; :934-938 mono lo in s bits
+                    constexpr uint32_t sh = shift ? shift : 8u;
+                    constexpr uint32_t mask = (1u << sh) - 1u;
+                    if (stereo) {
+                        v = bits_from_entries(2 * sh, off, nb, [&](uint32_t i) -> uint32_t {
+                            if (i >= n) return 0u;
+                            const uint8_t *p = eb + (size_t)i * stride;
+                            const uint32_t l = load_raw_bits<DEPTH>(p) & mask, rr = load_raw_bits<DEPTH>(p + bps) & mask;
+                            return (l << sh) | rr;
+                        });
+                    } else {
+                        v = bits_from_entries(sh, off, nb, [&](uint32_t i) -> uint32_t {
+                            if (i >= n) return 0u;
+                            return load_raw_bits<DEPTH>(eb + (size_t)i * stride) & mask;
+                        });
+                    }
+                } else {
+                    const uint32_t nch = stereo ? 2u : 1u;
+                    v = bits_from_entries(DEPTH, off, nb, [&](uint32_t i) -> uint32_t {
+                        if (i >= n * nch) return 0u;
+                        const uint32_t s = stereo ? (i >> 1) : i, c = stereo ? (i & 1u) : 0u;
+                        return load_raw_bits<DEPTH>(eb + (size_t)s * stride + c * bps);
+                    });
+                }
+            }
+            word |= v << (bit0 + 32u - hi);     // word holds packet bits [bit0, bit0+32) MSB-first
+        }
+        return word;
+    };
+    // bytes before the first 4-byte-aligned output address: lane 0, byte stores
+    if (lane == 0 && lead_bytes) {
+        const uint32_t nb = min(lead_bytes, size);
+        const uint32_t word = gather(0, nb);
+        for (uint32_t b = 0; b < nb; b++) dst[b] = (uint8_t)(word >> (24 - 8 * b));
+    }
+    for (uint32_t g = lane; g < words_total; g += 32) {
+        const uint32_t byte0 = lead_bytes + 4u * g;
+        const uint32_t nbytes = min(4u, size - byte0);
+        const uint32_t word = gather(byte0, nbytes);
+        if (nbytes == 4) {
+            *reinterpret_cast<uint32_t *>(dst + byte0) = bswap32(word);
+        } else {
+            for (uint32_t b = 0; b < nbytes; b++) dst[byte0 + b] = (uint8_t)(word >> (24 - 8 * b));
+        }
+    }
+}
+
+}  // namespace alacb

@@ -1,0 +1,588 @@
+// alac_engine.cu -- host side of libalac_b200.so: engine object, batched encode / decode
+// orchestration and the extern "C" ABI declared in include/alac_b200.h.
+//
+// No CPU codec path exists here: every compute entry point launches the sm_100a kernels of
+// alac_encode.cuh / alac_decode.cuh and fails with ALAC_B200_CUDA_ERROR if that is impossible.
+#include "../../include/alac_b200.h"
+#include "alac_decode.cuh"
+#include "alac_encode.cuh"
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+using namespace alacb;
+
+namespace {
+
+struct DevBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    cudaError_t reserve(size_t bytes)
+    {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        size_t want = bytes + bytes / 8 + 256;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release()
+    {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+    template <class T> T *as() const { return reinterpret_cast<T *>(p); }
+};
+
+}  // namespace
+
+struct alac_b200_engine {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    cudaStream_t own_stream = nullptr;
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    std::string err;
+    // encode
+    DevBuf pcm, pkt_frame, pkt_samples, seg_first, seg_count, seg_stream, recs, scratch, sizes, offsets, out, state, counters;
+    // decode
+    DevBuf d_packets, d_sizes, d_pkt_off, d_pkt_samples, d_out_frame, d_status, d_pcm;
+    uint32_t launches = 0;
+};
+
+#define CU_CHECK(eng, call)                                                                        \
+    do {                                                                                           \
+        cudaError_t e__ = (call);                                                                  \
+        if (e__ != cudaSuccess) {                                                                  \
+            (eng)->err = std::string(#call) + ": " + cudaGetErrorString(e__);                      \
+            return e__ == cudaErrorMemoryAllocation ? ALAC_B200_MEM_ERROR : ALAC_B200_CUDA_ERROR;  \
+        }                                                                                          \
+    } while (0)
+
+// codec/ALACEncoder.cu:97-107 sChannelMaps: element tags per channel index, 3 bits each
+static const uint32_t kChannelMaps[8] = {
+    ID_SCE,
+    ID_CPE,
+    (ID_CPE << 3) | (ID_SCE),
+    (ID_SCE << 9) | (ID_CPE << 3) | (ID_SCE),
+    (ID_CPE << 9) | (ID_CPE << 3) | (ID_SCE),
+    (ID_SCE << 15) | (ID_CPE << 9) | (ID_CPE << 3) | (ID_SCE),
+    (ID_SCE << 18) | (ID_SCE << 15) | (ID_CPE << 9) | (ID_CPE << 3) | (ID_SCE),
+    (ID_SCE << 21) | (ID_CPE << 15) | (ID_CPE << 9) | (ID_CPE << 3) | (ID_SCE)};
+
+// codec/ALACAudioTypes.h:115-125
+static const uint32_t kLayoutTags[8] = {(100u << 16) | 1, (101u << 16) | 2, (113u << 16) | 3, (116u << 16) | 4,
+                                        (120u << 16) | 5, (124u << 16) | 6, (142u << 16) | 7, (127u << 16) | 8};
+
+static bool valid_depth(uint32_t d) { return d == 16 || d == 20 || d == 24 || d == 32; }
+static uint32_t bytes_per_sample(uint32_t d) { return d == 16 ? 2u : d == 32 ? 4u : 3u; }
+
+static bool valid_cfg(const alac_b200_enc_config *c)
+{
+    return c && c->channels >= 1 && c->channels <= 8 && valid_depth(c->bit_depth) && c->frame_size >= 1 &&
+           c->frame_size <= 16384;
+}
+
+// element walk of ALACEncoder::Encode (codec/ALACEncoder.cu:973-1057; >2 channels per sChannelMaps)
+static void build_layout(const alac_b200_enc_config *c, EncLayout &L, uint32_t &mono_mask, uint32_t &pair_mask)
+{
+    memset(&L, 0, sizeof(L));
+    L.channels = c->channels;
+    L.frame_size = c->frame_size;
+    L.fast_mode = c->fast_mode ? 1u : 0u;
+    mono_mask = pair_mask = 0;
+    uint32_t ch = 0, e = 0, chain = 0, mono_tag = 0, pair_tag = 0, lfe_tag = 0;
+    while (ch < c->channels) {
+        const uint32_t tag = (kChannelMaps[c->channels - 1] >> (ch * 3)) & 7u;
+        L.elem_tag[e] = (uint8_t)tag;
+        L.elem_chan[e] = (uint8_t)ch;
+        L.elem_chain[e] = (uint8_t)chain;
+        if (tag == ID_CPE) {
+            L.elem_inst[e] = (uint8_t)pair_tag++;
+            pair_mask |= 1u << e;
+            ch += 2;
+            chain += 2;
+        } else {
+            L.elem_inst[e] = (uint8_t)(tag == ID_LFE ? lfe_tag++ : mono_tag++);
+            mono_mask |= 1u << e;
+            ch += 1;
+            chain += 1;
+        }
+        e++;
+    }
+    L.elems_per_packet = e;
+    L.chains_per_packet = chain;
+}
+
+static inline void put_be32(uint8_t *p, uint32_t v) { p[0] = v >> 24; p[1] = v >> 16; p[2] = v >> 8; p[3] = v; }
+
+extern "C" {
+
+const char *alac_b200_version(void) { return "alac_b200 0.1 (sm_100a)"; }
+
+int32_t alac_b200_engine_create(int32_t device, alac_b200_engine **out_engine)
+{
+    if (!out_engine) return ALAC_B200_PARAM_ERROR;
+    *out_engine = nullptr;
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0) return ALAC_B200_CUDA_ERROR;
+    if (device < 0) {
+        if (cudaGetDevice(&device) != cudaSuccess) return ALAC_B200_CUDA_ERROR;
+    }
+    if (device >= count) return ALAC_B200_PARAM_ERROR;
+    if (cudaSetDevice(device) != cudaSuccess) return ALAC_B200_CUDA_ERROR;
+    alac_b200_engine *e = new alac_b200_engine();
+    e->device = device;
+    if (cudaStreamCreateWithFlags(&e->own_stream, cudaStreamNonBlocking) != cudaSuccess) {
+        delete e;
+        return ALAC_B200_CUDA_ERROR;
+    }
+    e->stream = e->own_stream;
+    for (auto &ev : e->ev) {
+        if (cudaEventCreate(&ev) != cudaSuccess) {
+            delete e;
+            return ALAC_B200_CUDA_ERROR;
+        }
+    }
+    *out_engine = e;
+    return ALAC_B200_OK;
+}
+
+void alac_b200_engine_destroy(alac_b200_engine *e)
+{
+    if (!e) return;
+    cudaSetDevice(e->device);
+    cudaStreamSynchronize(e->stream);
+    DevBuf *bufs[] = {&e->pcm, &e->pkt_frame, &e->pkt_samples, &e->seg_first, &e->seg_count, &e->seg_stream, &e->recs,
+                      &e->scratch, &e->sizes, &e->offsets, &e->out, &e->state, &e->counters, &e->d_packets, &e->d_sizes,
+                      &e->d_pkt_off, &e->d_pkt_samples, &e->d_out_frame, &e->d_status, &e->d_pcm};
+    for (DevBuf *b : bufs) b->release();
+    for (auto &ev : e->ev)
+        if (ev) cudaEventDestroy(ev);
+    if (e->own_stream) cudaStreamDestroy(e->own_stream);
+    delete e;
+}
+
+const char *alac_b200_last_error(const alac_b200_engine *e) { return e ? e->err.c_str() : "null engine"; }
+
+int32_t alac_b200_engine_set_stream(alac_b200_engine *e, void *cuda_stream)
+{
+    if (!e) return ALAC_B200_PARAM_ERROR;
+    e->stream = cuda_stream ? reinterpret_cast<cudaStream_t>(cuda_stream) : e->own_stream;
+    return ALAC_B200_OK;
+}
+
+uint32_t alac_b200_magic_cookie(const alac_b200_enc_config *c, uint32_t max_frame_bytes, uint32_t avg_bit_rate,
+                                void *out_cookie, uint32_t cap)
+{
+    // codec/ALACEncoder.cu:1082-1140; layout codec/ALACAudioTypes.h:162-176 (all big-endian)
+    if (!valid_cfg(c) || !out_cookie) return 0;
+    const uint32_t size = 24 + (c->channels > 2 ? 24u : 0u);
+    if (cap < size) return 0;       // "no incomplete cookies", :1136-1139
+    uint8_t *o = static_cast<uint8_t *>(out_cookie);
+    memset(o, 0, size);
+    put_be32(o, c->frame_size);
+    o[4] = 0;
+    o[5] = (uint8_t)c->bit_depth;
+    o[6] = (uint8_t)kPb0;
+    o[7] = (uint8_t)kMb0;
+    o[8] = (uint8_t)kKb0;
+    o[9] = (uint8_t)c->channels;
+    o[10] = 0;
+    o[11] = 255;                    // maxRun
+    put_be32(o + 12, max_frame_bytes);
+    put_be32(o + 16, avg_bit_rate);
+    put_be32(o + 20, c->sample_rate);
+    if (c->channels > 2) {
+        static const uint8_t atom[12] = {0, 0, 0, 24, 'c', 'h', 'a', 'n', 0, 0, 0, 0};
+        memcpy(o + 24, atom, 12);
+        const uint32_t tag = kLayoutTags[c->channels - 1];      // stored native-endian, :1120
+        memcpy(o + 36, &tag, 4);
+    }
+    return size;
+}
+
+int32_t alac_b200_parse_cookie(const void *cookie, uint32_t cookie_size, uint32_t f[11])
+{
+    // codec/ALACDecoder.cu:109-190
+    if (!cookie || !f) return ALAC_B200_PARAM_ERROR;
+    const uint8_t *p = static_cast<const uint8_t *>(cookie);
+    uint32_t left = cookie_size;
+    if (left >= 12 && p[4] == 'f' && p[5] == 'r' && p[6] == 'm' && p[7] == 'a') { p += 12; left -= 12; }
+    if (left >= 12 && p[4] == 'a' && p[5] == 'l' && p[6] == 'a' && p[7] == 'c') { p += 12; left -= 12; }
+    if (left < 24) return ALAC_B200_PARAM_ERROR;
+    auto be32 = [](const uint8_t *q) { return ((uint32_t)q[0] << 24) | ((uint32_t)q[1] << 16) | ((uint32_t)q[2] << 8) | q[3]; };
+    f[0] = be32(p);
+    f[1] = p[4]; f[2] = p[5]; f[3] = p[6]; f[4] = p[7]; f[5] = p[8]; f[6] = p[9];
+    f[7] = ((uint32_t)p[10] << 8) | p[11];
+    f[8] = be32(p + 12); f[9] = be32(p + 16); f[10] = be32(p + 20);
+    if (f[1] > 0) return ALAC_B200_PARAM_ERROR;     // compatibleVersion <= kALACVersion, :153
+    return ALAC_B200_OK;
+}
+
+uint64_t alac_b200_encode_bound(const alac_b200_enc_config *c, uint64_t num_sample_frames, uint64_t num_streams)
+{
+    if (!valid_cfg(c)) return 0;
+    if (num_streams == 0) num_streams = 1;
+    const uint64_t bpf = (uint64_t)bytes_per_sample(c->bit_depth) * c->channels;
+    const uint64_t packets = num_sample_frames / c->frame_size + num_streams;
+    // an element never exceeds its escape size: 7 + 16 + 32 header bits + raw samples; + ID_END + padding
+    return num_sample_frames * bpf + packets * (8ull * c->channels + 8ull);
+}
+
+}  // extern "C"
+
+// ------------------------------------------------------------------------------------------------
+// encode
+// ------------------------------------------------------------------------------------------------
+template <int DEPTH>
+static void launch_search(alac_b200_engine *e, const EncArgs &A, uint32_t mono_mask, uint32_t pair_mask)
+{
+    const uint32_t pairs = __builtin_popcount(pair_mask), monos = __builtin_popcount(mono_mask);
+    if (pairs) {
+        const uint64_t threads = (uint64_t)A.num_segments * pairs * 2;
+        enc_search_kernel<DEPTH, true><<<(uint32_t)((threads + 127) / 128), 128, 0, e->stream>>>(A, pairs, pair_mask);
+        e->launches++;
+    }
+    if (monos) {
+        const uint64_t threads = (uint64_t)A.num_segments * monos;
+        enc_search_kernel<DEPTH, false><<<(uint32_t)((threads + 127) / 128), 128, 0, e->stream>>>(A, monos, mono_mask);
+        e->launches++;
+    }
+}
+
+template <int DEPTH>
+static void launch_assemble(alac_b200_engine *e, const AsmArgs &A)
+{
+    enc_assemble_kernel<DEPTH><<<(A.num_packets + kAsmWarps - 1) / kAsmWarps, kAsmWarps * 32, 0, e->stream>>>(A);
+    e->launches++;
+}
+
+extern "C" int32_t alac_b200_encode(alac_b200_engine *e, const alac_b200_enc_config *cfg, const void *pcm,
+                                    uint64_t num_sample_frames, int32_t pcm_mem, const alac_b200_stream *streams,
+                                    uint64_t n_streams, void *packets_out, uint64_t packets_cap, uint32_t *packet_sizes,
+                                    uint64_t sizes_cap, int32_t out_mem, int16_t *coef_state, uint64_t *out_num_packets,
+                                    uint64_t *out_bytes, alac_b200_stats *stats)
+{
+    if (!e) return ALAC_B200_PARAM_ERROR;
+    e->err.clear();
+    if (!valid_cfg(cfg) || (!pcm && num_sample_frames) || !packets_out || !packet_sizes) return ALAC_B200_PARAM_ERROR;
+    if (out_num_packets) *out_num_packets = 0;
+    if (out_bytes) *out_bytes = 0;
+    if (stats) memset(stats, 0, sizeof(*stats));
+    CU_CHECK(e, cudaSetDevice(e->device));
+    e->launches = 0;
+
+    alac_b200_stream whole = {0, num_sample_frames};
+    if (!streams) { streams = &whole; n_streams = 1; }
+    const uint32_t F = cfg->frame_size, K = cfg->frames_per_segment;
+    const uint64_t bpf = (uint64_t)bytes_per_sample(cfg->bit_depth) * cfg->channels;
+
+    // ---- packet / segment tables (host) ----
+    std::vector<uint64_t> h_pkt_frame;
+    std::vector<uint32_t> h_pkt_samples, h_seg_first, h_seg_count, h_seg_stream;
+    for (uint64_t s = 0; s < n_streams; s++) {
+        const alac_b200_stream &st = streams[s];
+        if (st.first_sample_frame + st.num_sample_frames > num_sample_frames) return ALAC_B200_PARAM_ERROR;
+        const uint64_t packets = (st.num_sample_frames + F - 1) / F;
+        if (h_pkt_frame.size() + packets > 0x3fffffffull) return ALAC_B200_PARAM_ERROR;
+        const uint32_t first_pkt = (uint32_t)h_pkt_frame.size();
+        for (uint64_t p = 0; p < packets; p++) {
+            h_pkt_frame.push_back(st.first_sample_frame + p * F);
+            h_pkt_samples.push_back((uint32_t)std::min<uint64_t>(F, st.num_sample_frames - p * F));
+        }
+        const uint64_t per_seg = K ? K : std::max<uint64_t>(packets, 1);
+        const size_t seg0 = h_seg_first.size();
+        for (uint64_t p = 0; p < packets; p += per_seg) {
+            h_seg_first.push_back(first_pkt + (uint32_t)p);
+            h_seg_count.push_back((uint32_t)std::min<uint64_t>(per_seg, packets - p));
+            h_seg_stream.push_back((uint32_t)s);
+        }
+        if (h_seg_first.size() > seg0) {
+            h_seg_stream[seg0] |= 0x80000000u;
+            h_seg_stream.back() |= 0x40000000u;
+        }
+    }
+    const uint32_t P = (uint32_t)h_pkt_frame.size(), S = (uint32_t)h_seg_first.size();
+    if (P > sizes_cap) return ALAC_B200_PARAM_ERROR;
+    if (packets_cap < alac_b200_encode_bound(cfg, num_sample_frames, n_streams)) return ALAC_B200_PARAM_ERROR;
+    if (P == 0) return ALAC_B200_OK;
+
+    EncLayout L;
+    uint32_t mono_mask, pair_mask;
+    build_layout(cfg, L, mono_mask, pair_mask);
+
+    // ---- device buffers ----
+    const uint32_t cap_words = F + 8;       // >= worst-case Golomb words per channel (<= 32 bits/sample incl. run codes)
+    // chunking bounds the scratch: at most kChunkPackets packets (whole segments) per search launch
+    const uint64_t kChunkPackets = 65536;
+    uint64_t max_chunk = 0;
+    {
+        uint64_t cur = 0;
+        for (uint32_t s = 0; s < S; s++) {
+            if (cur && cur + h_seg_count[s] > kChunkPackets) { max_chunk = std::max(max_chunk, cur); cur = 0; }
+            cur += h_seg_count[s];
+        }
+        max_chunk = std::max(max_chunk, cur);
+    }
+    CU_CHECK(e, e->pkt_frame.reserve((size_t)P * 8));
+    CU_CHECK(e, e->pkt_samples.reserve((size_t)P * 4));
+    CU_CHECK(e, e->seg_first.reserve((size_t)S * 4));
+    CU_CHECK(e, e->seg_count.reserve((size_t)S * 4));
+    CU_CHECK(e, e->seg_stream.reserve((size_t)S * 4));
+    CU_CHECK(e, e->recs.reserve((size_t)max_chunk * L.elems_per_packet * sizeof(ElemRec)));
+    CU_CHECK(e, e->scratch.reserve((size_t)max_chunk * L.chains_per_packet * cap_words * 4));
+    CU_CHECK(e, e->sizes.reserve((size_t)P * 4));
+    CU_CHECK(e, e->offsets.reserve(((size_t)P + 1) * 8));
+    CU_CHECK(e, e->counters.reserve(64));
+
+    cudaStream_t st = e->stream;
+    CU_CHECK(e, cudaEventRecord(e->ev[0], st));
+    const uint8_t *d_pcm;
+    if (pcm_mem == ALAC_B200_MEM_DEVICE) {
+        d_pcm = static_cast<const uint8_t *>(pcm);
+    } else {
+        CU_CHECK(e, e->pcm.reserve((size_t)(num_sample_frames * bpf) + 64));
+        CU_CHECK(e, cudaMemcpyAsync(e->pcm.p, pcm, (size_t)(num_sample_frames * bpf), cudaMemcpyHostToDevice, st));
+        d_pcm = e->pcm.as<uint8_t>();
+    }
+    CU_CHECK(e, cudaMemcpyAsync(e->pkt_frame.p, h_pkt_frame.data(), (size_t)P * 8, cudaMemcpyHostToDevice, st));
+    CU_CHECK(e, cudaMemcpyAsync(e->pkt_samples.p, h_pkt_samples.data(), (size_t)P * 4, cudaMemcpyHostToDevice, st));
+    CU_CHECK(e, cudaMemcpyAsync(e->seg_first.p, h_seg_first.data(), (size_t)S * 4, cudaMemcpyHostToDevice, st));
+    CU_CHECK(e, cudaMemcpyAsync(e->seg_count.p, h_seg_count.data(), (size_t)S * 4, cudaMemcpyHostToDevice, st));
+    CU_CHECK(e, cudaMemcpyAsync(e->seg_stream.p, h_seg_stream.data(), (size_t)S * 4, cudaMemcpyHostToDevice, st));
+    int16_t *d_state = nullptr;
+    if (coef_state) {
+        CU_CHECK(e, e->state.reserve((size_t)n_streams * ALAC_B200_STATE_INT16S * 2));
+        CU_CHECK(e, cudaMemcpyAsync(e->state.p, coef_state, (size_t)n_streams * ALAC_B200_STATE_INT16S * 2, cudaMemcpyHostToDevice, st));
+        d_state = e->state.as<int16_t>();
+    }
+    CU_CHECK(e, cudaMemsetAsync(e->counters.p, 0, 64, st));
+    uint8_t *d_out;
+    if (out_mem == ALAC_B200_MEM_DEVICE) {
+        d_out = static_cast<uint8_t *>(packets_out);
+    } else {
+        CU_CHECK(e, e->out.reserve((size_t)alac_b200_encode_bound(cfg, num_sample_frames, n_streams) + 64));
+        d_out = e->out.as<uint8_t>();
+    }
+    CU_CHECK(e, cudaEventRecord(e->ev[1], st));
+
+    // ---- kernels, chunk by chunk ----
+    unsigned long long *d_escapes = e->counters.as<unsigned long long>();
+    uint32_t *d_max = reinterpret_cast<uint32_t *>(e->counters.as<uint8_t>() + 8);
+    uint32_t s0 = 0;
+    bool first_chunk = true;
+    while (s0 < S) {
+        uint32_t s1 = s0;
+        uint64_t cnt = 0;
+        while (s1 < S && (cnt == 0 || cnt + h_seg_count[s1] <= kChunkPackets)) cnt += h_seg_count[s1++];
+        const uint32_t p0 = h_seg_first[s0];
+
+        EncArgs A;
+        A.pcm = d_pcm;
+        A.pkt_frame = e->pkt_frame.as<uint64_t>();
+        A.pkt_samples = e->pkt_samples.as<uint32_t>();
+        A.seg_first = e->seg_first.as<uint32_t>();
+        A.seg_count = e->seg_count.as<uint32_t>();
+        A.seg_stream = e->seg_stream.as<uint32_t>();
+        A.seg_base = s0;
+        A.num_segments = s1 - s0;
+        A.pkt_base = p0;
+        A.lay = L;
+        A.recs = e->recs.as<ElemRec>();
+        A.scratch = e->scratch.as<uint32_t>();
+        A.cap_words = cap_words;
+        A.state = d_state;
+        switch (cfg->bit_depth) {
+        case 16: launch_search<16>(e, A, mono_mask, pair_mask); break;
+        case 20: launch_search<20>(e, A, mono_mask, pair_mask); break;
+        case 24: launch_search<24>(e, A, mono_mask, pair_mask); break;
+        default: launch_search<32>(e, A, mono_mask, pair_mask); break;
+        }
+        enc_size_kernel<<<(uint32_t)((cnt + 255) / 256), 256, 0, st>>>(A.recs, L.elems_per_packet, (uint32_t)cnt,
+                                                                     e->sizes.as<uint32_t>() + p0, d_escapes);
+        scan_u32_to_u64_kernel<<<1, 1024, 0, st>>>(e->sizes.as<uint32_t>() + p0, e->offsets.as<uint64_t>() + p0, cnt, d_max,
+                                                   first_chunk ? 0 : 1);
+        e->launches += 2;
+
+        AsmArgs B;
+        B.pcm = d_pcm;
+        B.pkt_frame = A.pkt_frame;
+        B.pkt_samples = A.pkt_samples;
+        B.recs = A.recs;
+        B.scratch = A.scratch;
+        B.cap_words = cap_words;
+        B.sizes = e->sizes.as<uint32_t>();
+        B.offsets = e->offsets.as<uint64_t>();
+        B.out = d_out;
+        B.pkt_base = p0;
+        B.num_packets = (uint32_t)cnt;
+        B.lay = L;
+        switch (cfg->bit_depth) {
+        case 16: launch_assemble<16>(e, B); break;
+        case 20: launch_assemble<20>(e, B); break;
+        case 24: launch_assemble<24>(e, B); break;
+        default: launch_assemble<32>(e, B); break;
+        }
+        first_chunk = false;
+        s0 = s1;
+    }
+    CU_CHECK(e, cudaGetLastError());
+    CU_CHECK(e, cudaEventRecord(e->ev[2], st));
+
+    // ---- results ----
+    uint64_t total = 0;
+    unsigned long long h_counters[2] = {0, 0};
+    CU_CHECK(e, cudaMemcpyAsync(&total, e->offsets.as<uint64_t>() + P, 8, cudaMemcpyDeviceToHost, st));
+    CU_CHECK(e, cudaMemcpyAsync(h_counters, e->counters.p, 16, cudaMemcpyDeviceToHost, st));
+    if (out_mem == ALAC_B200_MEM_DEVICE) {
+        CU_CHECK(e, cudaMemcpyAsync(packet_sizes, e->sizes.p, (size_t)P * 4, cudaMemcpyDeviceToDevice, st));
+    } else {
+        CU_CHECK(e, cudaMemcpyAsync(packet_sizes, e->sizes.p, (size_t)P * 4, cudaMemcpyDeviceToHost, st));
+    }
+    CU_CHECK(e, cudaStreamSynchronize(st));
+    if (total > packets_cap) { e->err = "output capacity exceeded"; return ALAC_B200_PARAM_ERROR; }
+    if (out_mem != ALAC_B200_MEM_DEVICE && total) {
+        CU_CHECK(e, cudaMemcpyAsync(packets_out, d_out, (size_t)total, cudaMemcpyDeviceToHost, st));
+    }
+    if (coef_state) {
+        CU_CHECK(e, cudaMemcpyAsync(coef_state, e->state.p, (size_t)n_streams * ALAC_B200_STATE_INT16S * 2, cudaMemcpyDeviceToHost, st));
+    }
+    CU_CHECK(e, cudaEventRecord(e->ev[3], st));
+    CU_CHECK(e, cudaStreamSynchronize(st));
+
+    if (out_num_packets) *out_num_packets = P;
+    if (out_bytes) *out_bytes = total;
+    if (stats) {
+        stats->num_packets = P;
+        stats->payload_bytes = total;
+        stats->escape_elements = h_counters[0];
+        stats->max_packet_bytes = (uint32_t)(h_counters[1] & 0xffffffffu);
+        stats->kernel_launches = e->launches;
+        cudaEventElapsedTime(&stats->ms_h2d, e->ev[0], e->ev[1]);
+        cudaEventElapsedTime(&stats->ms_kernels, e->ev[1], e->ev[2]);
+        cudaEventElapsedTime(&stats->ms_d2h, e->ev[2], e->ev[3]);
+    }
+    return ALAC_B200_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// decode
+// ------------------------------------------------------------------------------------------------
+extern "C" int32_t alac_b200_decode(alac_b200_engine *e, const void *cookie, uint32_t cookie_size, const void *packets,
+                                    const uint32_t *packet_sizes, uint64_t num_packets, int32_t in_mem, void *pcm_out,
+                                    uint64_t pcm_cap, uint32_t *packet_samples, int32_t *packet_status, int32_t out_mem,
+                                    uint64_t *out_sample_frames, alac_b200_stats *stats)
+{
+    if (!e) return ALAC_B200_PARAM_ERROR;
+    e->err.clear();
+    if (out_sample_frames) *out_sample_frames = 0;
+    if (stats) memset(stats, 0, sizeof(*stats));
+    uint32_t f[11];
+    int32_t rc = alac_b200_parse_cookie(cookie, cookie_size, f);
+    if (rc) return rc;
+    const uint32_t frame_length = f[0], depth = f[2], nch = f[6];
+    if (!valid_depth(depth) || nch == 0 || frame_length == 0) return ALAC_B200_PARAM_ERROR;
+    if (num_packets > 0x3fffffffull) return ALAC_B200_PARAM_ERROR;
+    if ((!packets || !packet_sizes || !pcm_out) && num_packets) return ALAC_B200_PARAM_ERROR;
+    if (num_packets == 0) return ALAC_B200_OK;
+    CU_CHECK(e, cudaSetDevice(e->device));
+    e->launches = 0;
+    const uint32_t P = (uint32_t)num_packets;
+    const uint64_t bpf = (uint64_t)bytes_per_sample(depth) * nch;
+    cudaStream_t st = e->stream;
+
+    CU_CHECK(e, e->d_pkt_off.reserve(((size_t)P + 1) * 8));
+    CU_CHECK(e, e->d_pkt_samples.reserve((size_t)P * 4));
+    CU_CHECK(e, e->d_out_frame.reserve(((size_t)P + 1) * 8));
+    CU_CHECK(e, e->d_status.reserve((size_t)P * 4));
+    CU_CHECK(e, e->counters.reserve(64));
+
+    CU_CHECK(e, cudaEventRecord(e->ev[0], st));
+    const uint32_t *d_sizes;
+    const uint8_t *d_packets;
+    if (in_mem == ALAC_B200_MEM_DEVICE) {
+        d_sizes = packet_sizes;
+        d_packets = static_cast<const uint8_t *>(packets);
+    } else {
+        uint64_t total = 0;
+        for (uint32_t i = 0; i < P; i++) total += packet_sizes[i];
+        CU_CHECK(e, e->d_sizes.reserve((size_t)P * 4));
+        CU_CHECK(e, e->d_packets.reserve((size_t)total + 64));
+        CU_CHECK(e, cudaMemcpyAsync(e->d_sizes.p, packet_sizes, (size_t)P * 4, cudaMemcpyHostToDevice, st));
+        CU_CHECK(e, cudaMemcpyAsync(e->d_packets.p, packets, (size_t)total, cudaMemcpyHostToDevice, st));
+        d_sizes = e->d_sizes.as<uint32_t>();
+        d_packets = e->d_packets.as<uint8_t>();
+    }
+    uint8_t *d_pcm;
+    if (out_mem == ALAC_B200_MEM_DEVICE) {
+        d_pcm = static_cast<uint8_t *>(pcm_out);
+    } else {
+        CU_CHECK(e, e->d_pcm.reserve((size_t)std::min<uint64_t>(pcm_cap, (uint64_t)P * frame_length * bpf) + 64));
+        d_pcm = e->d_pcm.as<uint8_t>();
+    }
+    CU_CHECK(e, cudaEventRecord(e->ev[1], st));
+
+    DecArgs A;
+    A.packets = d_packets;
+    A.pkt_off = e->d_pkt_off.as<uint64_t>();
+    A.pkt_size = d_sizes;
+    A.num_packets = P;
+    A.frame_length = frame_length;
+    A.pb = f[3];
+    A.mb = f[4];
+    A.kb = f[5];
+    A.num_channels = nch;
+    A.pcm_out = d_pcm;
+    A.out_frame = e->d_out_frame.as<uint64_t>();
+    A.pkt_samples = e->d_pkt_samples.as<uint32_t>();
+    A.pkt_status = e->d_status.as<int32_t>();
+
+    scan_u32_to_u64_kernel<<<1, 1024, 0, st>>>(d_sizes, e->d_pkt_off.as<uint64_t>(), P, nullptr, 0);
+    dec_header_kernel<<<(P + 127) / 128, 128, 0, st>>>(A);
+    scan_u32_to_u64_kernel<<<1, 1024, 0, st>>>(A.pkt_samples, e->d_out_frame.as<uint64_t>(), P, nullptr, 0);
+    e->launches += 3;
+    // the output capacity must be known to hold before the decode kernel writes
+    uint64_t total_frames = 0;
+    CU_CHECK(e, cudaMemcpyAsync(&total_frames, e->d_out_frame.as<uint64_t>() + P, 8, cudaMemcpyDeviceToHost, st));
+    CU_CHECK(e, cudaStreamSynchronize(st));
+    if (total_frames * bpf > pcm_cap) { e->err = "pcm capacity exceeded"; return ALAC_B200_PARAM_ERROR; }
+
+    switch (depth) {
+    case 16: dec_packet_kernel<16><<<(P + 127) / 128, 128, 0, st>>>(A); break;
+    case 20: dec_packet_kernel<20><<<(P + 127) / 128, 128, 0, st>>>(A); break;
+    case 24: dec_packet_kernel<24><<<(P + 127) / 128, 128, 0, st>>>(A); break;
+    default: dec_packet_kernel<32><<<(P + 127) / 128, 128, 0, st>>>(A); break;
+    }
+    e->launches++;
+    CU_CHECK(e, cudaGetLastError());
+    CU_CHECK(e, cudaEventRecord(e->ev[2], st));
+
+    std::vector<int32_t> h_status(P);
+    CU_CHECK(e, cudaMemcpyAsync(h_status.data(), A.pkt_status, (size_t)P * 4, cudaMemcpyDeviceToHost, st));
+    const cudaMemcpyKind to_user = out_mem == ALAC_B200_MEM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
+    if (packet_samples) CU_CHECK(e, cudaMemcpyAsync(packet_samples, A.pkt_samples, (size_t)P * 4, to_user, st));
+    if (packet_status) CU_CHECK(e, cudaMemcpyAsync(packet_status, A.pkt_status, (size_t)P * 4, to_user, st));
+    if (out_mem != ALAC_B200_MEM_DEVICE && total_frames)
+        CU_CHECK(e, cudaMemcpyAsync(pcm_out, d_pcm, (size_t)(total_frames * bpf), cudaMemcpyDeviceToHost, st));
+    CU_CHECK(e, cudaEventRecord(e->ev[3], st));
+    CU_CHECK(e, cudaStreamSynchronize(st));
+
+    if (out_sample_frames) *out_sample_frames = total_frames;
+    int32_t first_err = 0;
+    for (uint32_t i = 0; i < P && !first_err; i++) first_err = h_status[i];
+    if (stats) {
+        stats->num_packets = P;
+        stats->payload_bytes = total_frames * bpf;
+        stats->kernel_launches = e->launches;
+        cudaEventElapsedTime(&stats->ms_h2d, e->ev[0], e->ev[1]);
+        cudaEventElapsedTime(&stats->ms_kernels, e->ev[1], e->ev[2]);
+        cudaEventElapsedTime(&stats->ms_d2h, e->ev[2], e->ev[3]);
+    }
+    return first_err;
+}

@@ -1,0 +1,140 @@
+/*
+ * alac_b200.h -- C ABI of the B200-native ALAC codec engine (libalac_b200.so).
+ *
+ * This is the drop-in boundary for the encode/decode hot path of dark-Stallion/alac.
+ * The reference has no FFI layer of its own: its boundary is the C++ class API
+ *   ALACEncoder  (codec/ALACEncoder.h:34-102)   InitializeEncoder / Encode / GetMagicCookie
+ *   ALACDecoder  (codec/ALACDecoder.h:38-72)    Init / Decode
+ * driven one 4096-sample frame at a time by convert-utility/main.cu:391-632 (encode loop)
+ * and :635-778 (decode loop).  include/ALACEncoder.h and include/ALACDecoder.h re-declare
+ * those classes on top of this ABI; the batched entry points below replace the per-frame
+ * loops themselves (whole files / streams of frames in one call).
+ *
+ * Plain pointers and sizes only; every pointer argument is either host memory or CUDA
+ * device memory as stated by the accompanying ALAC_B200_MEM_* flag.  All functions return
+ * the reference's int32 status codes (codec/ALACAudioTypes.h:54-60):
+ *   0 ALAC_noErr, -4 kALAC_UnimplementedError, -50 kALAC_ParamError, -108 kALAC_MemFullError,
+ * plus ALAC_B200_CUDA_ERROR for a CUDA runtime failure (text via alac_b200_last_error()).
+ * There is NO CPU fallback: every entry point that computes fails with ALAC_B200_CUDA_ERROR
+ * when no sm_100 device is usable.
+ */
+#ifndef ALAC_B200_H
+#define ALAC_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ALAC_B200_OK            0
+#define ALAC_B200_UNIMPLEMENTED (-4)
+#define ALAC_B200_PARAM_ERROR   (-50)
+#define ALAC_B200_MEM_ERROR     (-108)
+#define ALAC_B200_CUDA_ERROR    (-1000)
+
+#define ALAC_B200_MEM_HOST      0
+#define ALAC_B200_MEM_DEVICE    1
+
+#define ALAC_B200_MAX_CHANNELS  8
+#define ALAC_B200_COOKIE_MAX    48
+/* per-stream encoder coefficient state: [channel 8][U,V][row 3, row 7][8 taps] int16
+   (the live part of ALACEncoder::mCoefsU/V, codec/ALACEncoder.h:89-90) */
+#define ALAC_B200_STATE_INT16S  (8 * 2 * 2 * 8)
+
+typedef struct alac_b200_engine alac_b200_engine;
+
+/* Encoder configuration.  Mirrors what InitializeEncoder()/SetFrameSize()/SetFastMode() take
+   (codec/ALACEncoder.cu:1457-1535, codec/ALACEncoder.h:44-47). */
+typedef struct alac_b200_enc_config {
+    uint32_t sample_rate;
+    uint32_t channels;            /* 1..8; element layout follows sChannelMaps, codec/ALACEncoder.cu:97-107 */
+    uint32_t bit_depth;           /* 16, 20, 24, 32 (mFormatFlags 1..4, codec/ALACEncoder.cu:1463-1479) */
+    uint32_t frame_size;          /* samples per packet, kALACDefaultFrameSize = 4096; <= 16384 */
+    uint32_t fast_mode;           /* SetFastMode(): EncodeStereoFast path, codec/ALACEncoder.cu:564-743 */
+    /* Encoder-reset schedule.  The output equals what libalac produces when a fresh
+       ALACEncoder is started at every frames_per_segment-th frame of each stream.  0 = never reset:
+       byte-identical to one ALACEncoder fed the whole stream (serial per stream). */
+    uint32_t frames_per_segment;
+} alac_b200_enc_config;
+
+/* One input stream inside a batch: a run of interleaved PCM sample-frames. */
+typedef struct alac_b200_stream {
+    uint64_t first_sample_frame;  /* offset into the pcm buffer, in sample-frames */
+    uint64_t num_sample_frames;   /* length; the last packet of a stream may be partial */
+} alac_b200_stream;
+
+typedef struct alac_b200_stats {
+    uint64_t num_packets;
+    uint64_t payload_bytes;       /* sum of packet sizes */
+    uint64_t escape_elements;     /* elements written uncompressed */
+    uint32_t max_packet_bytes;
+    uint32_t kernel_launches;     /* CUDA kernels launched by the call */
+    float    ms_h2d, ms_kernels, ms_d2h;   /* CUDA-event times of the three phases */
+} alac_b200_stats;
+
+/* ---- engine ------------------------------------------------------------------------------ */
+/* device < 0 selects the current CUDA device.  The engine owns its scratch and one stream. */
+int32_t     alac_b200_engine_create(int32_t device, alac_b200_engine **out_engine);
+void        alac_b200_engine_destroy(alac_b200_engine *engine);
+const char *alac_b200_last_error(const alac_b200_engine *engine);
+const char *alac_b200_version(void);
+/* make later calls run on `cuda_stream` (a cudaStream_t) instead of the engine's own stream */
+int32_t     alac_b200_engine_set_stream(alac_b200_engine *engine, void *cuda_stream);
+
+/* ---- magic cookie: ALACEncoder::GetMagicCookie, codec/ALACEncoder.cu:1109-1140 ------------- */
+/* Returns the cookie size (24, or 48 for > 2 channels) or 0 when cap is too small. */
+uint32_t    alac_b200_magic_cookie(const alac_b200_enc_config *cfg, uint32_t max_frame_bytes,
+                                   uint32_t avg_bit_rate, void *out_cookie, uint32_t cap);
+/* worst-case bytes alac_b200_encode can write for the given input size */
+uint64_t    alac_b200_encode_bound(const alac_b200_enc_config *cfg, uint64_t num_sample_frames, uint64_t num_streams);
+
+/* ---- batched encode: replaces the Encode() loop of convert-utility/main.cu:552-601 --------- */
+/*
+ * pcm            interleaved little-endian packed PCM (16-bit: int16; 20/24-bit: 3 bytes,
+ *                20-bit left-justified; 32-bit: int32), host or device (pcm_mem).
+ * streams        n_streams descriptors (host memory); NULL means one stream covering
+ *                [0, num_sample_frames).  Streams must not overlap.
+ * packets_out    packets back to back in stream order, packet_sizes[i] bytes each
+ *                (the 'data' chunk payload and the pakt entries of SURVEY.md App. E);
+ *                capacity >= alac_b200_encode_bound().  out_mem says where both outputs live.
+ * coef_state     optional, host memory, n_streams * ALAC_B200_STATE_INT16S int16: when non-NULL the
+ *                first segment of each stream starts from this state instead of init_coefs and the
+ *                state after the last frame is written back (incremental streaming / Encode()).
+ */
+int32_t alac_b200_encode(alac_b200_engine *engine, const alac_b200_enc_config *cfg,
+                         const void *pcm, uint64_t num_sample_frames, int32_t pcm_mem,
+                         const alac_b200_stream *streams, uint64_t n_streams,
+                         void *packets_out, uint64_t packets_cap,
+                         uint32_t *packet_sizes, uint64_t sizes_cap, int32_t out_mem,
+                         int16_t *coef_state,
+                         uint64_t *out_num_packets, uint64_t *out_bytes,
+                         alac_b200_stats *stats);
+
+/* ---- batched decode: replaces the Decode() loop of convert-utility/main.cu:717-744 --------- */
+/*
+ * cookie         magic cookie as stored in the CAF 'kuki' chunk (ALACDecoder::Init,
+ *                codec/ALACDecoder.cu:109-190; 'frma'/'alac' wrappers are skipped).
+ * packets        packets back to back, packet_sizes[i] bytes each (in_mem says where both live).
+ * pcm_out        decoded interleaved PCM, packets contiguous in order; capacity in bytes.
+ * packet_samples optional (same memory space as pcm_out): sample-frames produced by each packet.
+ * packet_status  optional (same memory space as pcm_out): per-packet status (0 or kALAC_ParamError).
+ * Returns 0, or the first non-zero packet status.
+ */
+int32_t alac_b200_decode(alac_b200_engine *engine, const void *cookie, uint32_t cookie_size,
+                         const void *packets, const uint32_t *packet_sizes, uint64_t num_packets,
+                         int32_t in_mem,
+                         void *pcm_out, uint64_t pcm_cap,
+                         uint32_t *packet_samples, int32_t *packet_status, int32_t out_mem,
+                         uint64_t *out_sample_frames,
+                         alac_b200_stats *stats);
+
+/* parse a cookie on the host (no GPU work): fills the 11 ALACSpecificConfig fields in order
+   frameLength, compatibleVersion, bitDepth, pb, mb, kb, numChannels, maxRun, maxFrameBytes,
+   avgBitRate, sampleRate (codec/ALACAudioTypes.h:162-176) */
+int32_t alac_b200_parse_cookie(const void *cookie, uint32_t cookie_size, uint32_t out_fields[11]);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ALAC_B200_H */

@@ -1,0 +1,147 @@
+"""GPU parity: the CUDA path (through the C ABI) against the CPU oracle, bit-exact.
+
+Packets and cookie on encode, PCM on decode, and round-trip identity; covers every depth,
+mono / stereo / multichannel, partial and tiny tail frames, escape and zero-run content,
+encoder-reset schedules K = 1, K > 1 and K = 0 (one serial chain per stream).
+"""
+import numpy as np
+import pytest
+
+from tests import synth
+
+pytestmark = pytest.mark.gpu
+
+
+def _oracle_encode(O, pcm, ch, depth, K, frame_size=4096, fast=False, sr=44100):
+    enc = O.Encoder(ch, depth, sr, frame_size=frame_size, fast_mode=fast, reference=O.have_reference())
+    return enc.encode_stream(pcm, K)
+
+
+def _check_encode(engine, O, pcm, ch, depth, K, frame_size=4096, fast=False):
+    import alac_b200
+    cfg = alac_b200.EncoderConfig(channels=ch, bit_depth=depth, sample_rate=44100, frame_size=frame_size,
+                                  fast_mode=fast, frames_per_segment=K)
+    got = engine.encode(pcm, cfg)
+    want = _oracle_encode(O, pcm, ch, depth, K, frame_size, fast)
+    assert got.cookie == want.cookie
+    assert got.num_packets == len(want.sizes)
+    assert np.array_equal(np.asarray(got.sizes, np.uint32), want.sizes), \
+        f"first size mismatch at packet {int(np.argmax(np.asarray(got.sizes) != want.sizes))}"
+    assert got.nbytes == want.packets.nbytes
+    if not np.array_equal(got.packets, want.packets):
+        bad = int(np.argmax(got.packets != want.packets))
+        offs = np.concatenate([[0], np.cumsum(want.sizes)])
+        pk = int(np.searchsorted(offs, bad, side="right") - 1)
+        raise AssertionError(f"packet bytes differ: byte {bad} (packet {pk}, byte {bad - offs[pk]} of {want.sizes[pk]})")
+    return got, want
+
+
+def _check_decode(engine, O, enc, pcm):
+    dec = engine.decode(enc.cookie, enc.packets, np.asarray(enc.sizes, np.uint32))
+    assert dec.status == 0
+    want, st = O.Decoder(enc.cookie, reference=O.have_reference()).decode_stream(np.asarray(enc.packets), np.asarray(enc.sizes, np.uint32))
+    assert not st.any()
+    assert np.array_equal(dec.pcm, want)
+    assert np.array_equal(dec.pcm, pcm), "round trip is not the identity"
+
+
+@pytest.mark.parametrize("depth", [16, 20, 24, 32])
+@pytest.mark.parametrize("ch", [1, 2])
+@pytest.mark.parametrize("kind", ["music", "noise", "silence"])
+def test_encode_decode_k1(engine, oracle, depth, ch, kind):
+    frames = 4096 * 5 + 1904
+    pcm = synth.make(kind, frames, ch, depth, seed=depth + ch)
+    got, _ = _check_encode(engine, oracle, pcm, ch, depth, K=1)
+    _check_decode(engine, oracle, got, pcm)
+
+
+@pytest.mark.parametrize("K", [0, 3])
+@pytest.mark.parametrize("ch,depth", [(2, 16), (1, 24), (2, 24)])
+def test_encode_chained_segments(engine, oracle, K, ch, depth):
+    pcm = synth.make("music", 4096 * 7 + 100, ch, depth, seed=9)
+    got, _ = _check_encode(engine, oracle, pcm, ch, depth, K=K)
+    _check_decode(engine, oracle, got, pcm)
+
+
+@pytest.mark.parametrize("ch,depth", [(3, 16), (6, 24), (8, 24), (5, 20), (4, 32), (7, 16)])
+def test_multichannel(engine, oracle, ch, depth):
+    pcm = synth.make("music", 4096 * 2 + 777, ch, depth, seed=ch)
+    got, _ = _check_encode(engine, oracle, pcm, ch, depth, K=1)
+    _check_decode(engine, oracle, got, pcm)
+
+
+@pytest.mark.parametrize("tail", [1, 2, 7, 8, 9, 31, 32, 33, 71, 72, 100, 287, 288, 4095])
+@pytest.mark.parametrize("ch,depth", [(2, 16), (1, 16), (2, 24)])
+def test_tiny_tails(engine, oracle, tail, ch, depth):
+    pcm = synth.make("music", 4096 + tail, ch, depth, seed=tail)
+    got, _ = _check_encode(engine, oracle, pcm, ch, depth, K=1)
+    _check_decode(engine, oracle, got, pcm)
+
+
+def test_square_full_scale(engine, oracle):
+    for ch, depth in [(2, 16), (1, 16), (2, 24), (2, 32)]:
+        pcm = synth.make("square", 4096 * 3, ch, depth)
+        got, _ = _check_encode(engine, oracle, pcm, ch, depth, K=1)
+        _check_decode(engine, oracle, got, pcm)
+
+
+def test_fast_mode(engine, oracle):
+    for kind in ["music", "noise"]:
+        pcm = synth.make(kind, 4096 * 3 + 50, 2, 16, seed=4)
+        got, _ = _check_encode(engine, oracle, pcm, 2, 16, K=1, fast=True)
+        _check_decode(engine, oracle, got, pcm)
+
+
+def test_small_frame_size(engine, oracle):
+    pcm = synth.make("music", 1024 * 9 + 300, 2, 16, seed=5)
+    got, _ = _check_encode(engine, oracle, pcm, 2, 16, K=2, frame_size=1024)
+    _check_decode(engine, oracle, got, pcm)
+
+
+def test_multi_stream_batch(engine, oracle):
+    import alac_b200
+    ch, depth = 2, 16
+    lens = [4096 * 2 + 5, 4096, 300, 4096 * 3]
+    parts = [synth.make("music", n, ch, depth, seed=10 + i) for i, n in enumerate(lens)]
+    pcm = np.concatenate(parts)
+    starts = np.concatenate([[0], np.cumsum(lens)[:-1]])
+    cfg = alac_b200.EncoderConfig(channels=ch, bit_depth=depth, frames_per_segment=0)
+    got = engine.encode(pcm, cfg, streams=[(int(a), int(n)) for a, n in zip(starts, lens)])
+    want_p, want_s = [], []
+    for part in parts:
+        es = _oracle_encode(oracle, part, ch, depth, 0)
+        want_p.append(es.packets)
+        want_s.append(es.sizes)
+    assert np.array_equal(np.asarray(got.sizes, np.uint32), np.concatenate(want_s))
+    assert np.array_equal(got.packets, np.concatenate(want_p))
+
+
+def test_device_buffers(engine, oracle):
+    """Same call with device-resident input/output (torch CUDA tensors)."""
+    import torch
+    import alac_b200
+    pcm = synth.make("music", 4096 * 4 + 123, 2, 16, seed=21)
+    cfg = alac_b200.EncoderConfig(channels=2, bit_depth=16, frames_per_segment=1)
+    got = engine.encode(torch.from_numpy(pcm).cuda(), cfg)
+    want = _oracle_encode(oracle, pcm, 2, 16, 1)
+    assert np.array_equal(got.packets.cpu().numpy(), want.packets)
+    assert np.array_equal(got.sizes.cpu().numpy().astype(np.uint32), want.sizes)
+    dec = engine.decode(got.cookie, got.packets, got.sizes)
+    assert np.array_equal(dec.pcm.cpu().numpy(), pcm)
+
+
+def test_coef_state_streaming(engine, oracle):
+    """K = 0 fed in two calls with the coefficient state carried equals one call (and the oracle)."""
+    import alac_b200
+    pcm = synth.make("music", 4096 * 6, 2, 16, seed=33)
+    cfg = alac_b200.EncoderConfig(channels=2, bit_depth=16, frames_per_segment=0)
+    half = 4096 * 3 * cfg.bytes_per_frame
+    state = np.zeros((1, 128), np.int16)
+    # a fresh state equals init_coefs rows
+    init = np.zeros(8, np.int16)
+    init[:3] = [1216, -928, -64]
+    state[:] = np.tile(init, 16)
+    a = engine.encode(pcm[:half], cfg, coef_state=state)
+    b = engine.encode(pcm[half:], cfg, coef_state=state)
+    want = _oracle_encode(oracle, pcm, 2, 16, 0)
+    assert np.array_equal(np.concatenate([a.packets, b.packets]), want.packets)

@@ -53,6 +53,20 @@ struct alac_b200_engine {
     // decode
     DevBuf d_packets, d_sizes, d_pkt_off, d_pkt_samples, d_out_frame, d_status, d_pcm;
     uint32_t launches = 0;
+    // per-kernel timers: (start, stop) event pairs, grown on demand, reused across calls
+    std::vector<cudaEvent_t> timers;
+    size_t timers_used = 0;
+    cudaEvent_t timer()
+    {
+        if (timers_used == timers.size()) {
+            cudaEvent_t ev = nullptr;
+            cudaEventCreate(&ev);
+            timers.push_back(ev);
+        }
+        cudaEvent_t ev = timers[timers_used++];
+        cudaEventRecord(ev, stream);
+        return ev;
+    }
 };
 
 #define CU_CHECK(eng, call)                                                                        \
@@ -164,6 +178,7 @@ void alac_b200_engine_destroy(alac_b200_engine *e)
     for (DevBuf *b : bufs) b->release();
     for (auto &ev : e->ev)
         if (ev) cudaEventDestroy(ev);
+    for (auto &ev : e->timers) cudaEventDestroy(ev);
     if (e->own_stream) cudaStreamDestroy(e->own_stream);
     delete e;
 }
@@ -277,6 +292,8 @@ extern "C" int32_t alac_b200_encode(alac_b200_engine *e, const alac_b200_enc_con
     if (stats) memset(stats, 0, sizeof(*stats));
     CU_CHECK(e, cudaSetDevice(e->device));
     e->launches = 0;
+    e->timers_used = 0;
+    std::vector<cudaEvent_t> t_search, t_asm;
 
     alac_b200_stream whole = {0, num_sample_frames};
     if (!streams) { streams = &whole; n_streams = 1; }
@@ -398,12 +415,14 @@ extern "C" int32_t alac_b200_encode(alac_b200_engine *e, const alac_b200_enc_con
         A.scratch = e->scratch.as<uint32_t>();
         A.cap_words = cap_words;
         A.state = d_state;
+        t_search.push_back(e->timer());
         switch (cfg->bit_depth) {
         case 16: launch_search<16>(e, A, mono_mask, pair_mask); break;
         case 20: launch_search<20>(e, A, mono_mask, pair_mask); break;
         case 24: launch_search<24>(e, A, mono_mask, pair_mask); break;
         default: launch_search<32>(e, A, mono_mask, pair_mask); break;
         }
+        t_search.push_back(e->timer());
         enc_size_kernel<<<(uint32_t)((cnt + 255) / 256), 256, 0, st>>>(A.recs, L.elems_per_packet, (uint32_t)cnt,
                                                                      e->sizes.as<uint32_t>() + p0, d_escapes);
         scan_u32_to_u64_kernel<<<1, 1024, 0, st>>>(e->sizes.as<uint32_t>() + p0, e->offsets.as<uint64_t>() + p0, cnt, d_max,
@@ -423,12 +442,14 @@ extern "C" int32_t alac_b200_encode(alac_b200_engine *e, const alac_b200_enc_con
         B.pkt_base = p0;
         B.num_packets = (uint32_t)cnt;
         B.lay = L;
+        t_asm.push_back(e->timer());
         switch (cfg->bit_depth) {
         case 16: launch_assemble<16>(e, B); break;
         case 20: launch_assemble<20>(e, B); break;
         case 24: launch_assemble<24>(e, B); break;
         default: launch_assemble<32>(e, B); break;
         }
+        t_asm.push_back(e->timer());
         first_chunk = false;
         s0 = s1;
     }
@@ -467,6 +488,8 @@ extern "C" int32_t alac_b200_encode(alac_b200_engine *e, const alac_b200_enc_con
         cudaEventElapsedTime(&stats->ms_h2d, e->ev[0], e->ev[1]);
         cudaEventElapsedTime(&stats->ms_kernels, e->ev[1], e->ev[2]);
         cudaEventElapsedTime(&stats->ms_d2h, e->ev[2], e->ev[3]);
+        for (size_t i = 0; i + 1 < t_search.size(); i += 2) { float ms = 0; cudaEventElapsedTime(&ms, t_search[i], t_search[i + 1]); stats->ms_search += ms; }
+        for (size_t i = 0; i + 1 < t_asm.size(); i += 2) { float ms = 0; cudaEventElapsedTime(&ms, t_asm[i], t_asm[i + 1]); stats->ms_assemble += ms; }
     }
     return ALAC_B200_OK;
 }
@@ -493,6 +516,7 @@ extern "C" int32_t alac_b200_decode(alac_b200_engine *e, const void *cookie, uin
     if (num_packets == 0) return ALAC_B200_OK;
     CU_CHECK(e, cudaSetDevice(e->device));
     e->launches = 0;
+    e->timers_used = 0;
     const uint32_t P = (uint32_t)num_packets;
     const uint64_t bpf = (uint64_t)bytes_per_sample(depth) * nch;
     cudaStream_t st = e->stream;
@@ -553,12 +577,14 @@ extern "C" int32_t alac_b200_decode(alac_b200_engine *e, const void *cookie, uin
     CU_CHECK(e, cudaStreamSynchronize(st));
     if (total_frames * bpf > pcm_cap) { e->err = "pcm capacity exceeded"; return ALAC_B200_PARAM_ERROR; }
 
+    cudaEvent_t t_dec0 = e->timer();
     switch (depth) {
     case 16: dec_packet_kernel<16><<<(P + 127) / 128, 128, 0, st>>>(A); break;
     case 20: dec_packet_kernel<20><<<(P + 127) / 128, 128, 0, st>>>(A); break;
     case 24: dec_packet_kernel<24><<<(P + 127) / 128, 128, 0, st>>>(A); break;
     default: dec_packet_kernel<32><<<(P + 127) / 128, 128, 0, st>>>(A); break;
     }
+    cudaEvent_t t_dec1 = e->timer();
     e->launches++;
     CU_CHECK(e, cudaGetLastError());
     CU_CHECK(e, cudaEventRecord(e->ev[2], st));
@@ -583,6 +609,7 @@ extern "C" int32_t alac_b200_decode(alac_b200_engine *e, const void *cookie, uin
         cudaEventElapsedTime(&stats->ms_h2d, e->ev[0], e->ev[1]);
         cudaEventElapsedTime(&stats->ms_kernels, e->ev[1], e->ev[2]);
         cudaEventElapsedTime(&stats->ms_d2h, e->ev[2], e->ev[3]);
+        cudaEventElapsedTime(&stats->ms_decode, t_dec0, t_dec1);
     }
     return first_err;
 }

@@ -46,7 +46,8 @@ class _Stream(C.Structure):
 class Stats(C.Structure):
     _fields_ = [("num_packets", C.c_uint64), ("payload_bytes", C.c_uint64), ("escape_elements", C.c_uint64),
                 ("max_packet_bytes", C.c_uint32), ("kernel_launches", C.c_uint32),
-                ("ms_h2d", C.c_float), ("ms_kernels", C.c_float), ("ms_d2h", C.c_float)]
+                ("ms_h2d", C.c_float), ("ms_kernels", C.c_float), ("ms_d2h", C.c_float),
+                ("ms_search", C.c_float), ("ms_assemble", C.c_float), ("ms_decode", C.c_float)]
 
     def as_dict(self) -> dict:
         return {n: getattr(self, n) for n, _ in self._fields_}
@@ -206,7 +207,7 @@ class Engine:
         """Encode interleaved PCM (uint8 view; numpy = host, torch CUDA tensor = device).
 
         streams: optional [(first_sample_frame, num_sample_frames), ...]; default one stream over
-        everything.  coef_state: optional int16 [n_streams, 128] carried encoder state (in/out).
+        everything.  coef_state: optional int16 [n_streams, 256] carried encoder state (in/out).
         out / out_sizes: optional preallocated outputs (same memory kind as pcm).
         """
         ptr, nbytes, mem = _buf(pcm)
@@ -242,7 +243,7 @@ class Engine:
         state_ptr = None
         if coef_state is not None:
             if coef_state.dtype != np.int16 or coef_state.size != n_streams * STATE_INT16S or not coef_state.flags["C_CONTIGUOUS"]:
-                raise ValueError("coef_state must be contiguous int16 [n_streams, 128]")
+                raise ValueError("coef_state must be contiguous int16 [n_streams, 256]")
             state_ptr = coef_state.ctypes.data
         npk, nb, stats = C.c_uint64(0), C.c_uint64(0), Stats()
         st = self.lib.alac_b200_encode(self.h, C.byref(ccfg), C.c_void_p(ptr), nsf, mem, arr, n_streams,

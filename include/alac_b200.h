@@ -71,6 +71,9 @@ typedef struct alac_b200_stats {
     uint32_t max_packet_bytes;
     uint32_t kernel_launches;     /* CUDA kernels launched by the call */
     float    ms_h2d, ms_kernels, ms_d2h;   /* CUDA-event times of the three phases */
+    float    ms_search;           /* encode: sum over launches of enc_search_kernel (the dominant kernel) */
+    float    ms_assemble;         /* encode: sum over launches of enc_assemble_kernel */
+    float    ms_decode;           /* decode: dec_packet_kernel */
 } alac_b200_stats;
 
 /* ---- engine ------------------------------------------------------------------------------ */
@@ -98,7 +101,7 @@ uint64_t    alac_b200_encode_bound(const alac_b200_enc_config *cfg, uint64_t num
  * packets_out    packets back to back in stream order, packet_sizes[i] bytes each
  *                (the 'data' chunk payload and the pakt entries of SURVEY.md App. E);
  *                capacity >= alac_b200_encode_bound().  out_mem says where both outputs live.
- * coef_state     optional, host memory, n_streams * ALAC_B200_STATE_INT16S int16: when non-NULL the
+ * coef_state     optional, host memory, n_streams * ALAC_B200_STATE_INT16S (= 256) int16: when non-NULL the
  *                first segment of each stream starts from this state instead of init_coefs and the
  *                state after the last frame is written back (incremental streaming / Encode()).
  */

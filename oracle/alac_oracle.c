@@ -876,7 +876,7 @@ int32_t orc_encode_packet(orc_encoder *e, const uint8_t *pcm, uint32_t num_sampl
     if (num_samples > e->frame_size) return ORC_PARAM_ERROR;
     const uint32_t bps = bytes_per_sample(e->bit_depth);
     orc_bits b;
-    orc_bits_init(&b, out, (uint64_t)num_samples * e->channels * bps + 64);
+    orc_bits_init(&b, out, (uint64_t)e->frame_size * e->channels * 5 + 64);   /* mMaxOutputBytes, :1489 */
     int32_t st = ORC_OK;
     uint32_t mono_tag = 0, stereo_tag = 0, lfe_tag = 0, ti = 0;
 
@@ -931,7 +931,7 @@ int32_t orc_encode_stream(orc_encoder *e, const uint8_t *pcm, uint64_t num_sampl
 {
     const uint64_t bpf = (uint64_t)bytes_per_sample(e->bit_depth) * e->channels;
     uint64_t done = 0, written = 0, pkt = 0;
-    uint8_t *tmp = (uint8_t *)malloc((size_t)e->frame_size * bpf + 128);
+    uint8_t *tmp = (uint8_t *)malloc((size_t)e->frame_size * e->channels * 5 + 128);   /* worst pre-escape size, :1489 */
     if (!tmp) return ORC_MEM_ERROR;
     int32_t st = ORC_OK;
     while (done < num_sample_frames) {

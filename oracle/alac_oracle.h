@@ -111,7 +111,8 @@ void     orc_encoder_reset(orc_encoder *e);
 uint32_t orc_encoder_cookie(const orc_encoder *e, uint8_t *out, uint32_t cap);
 /* codec/ALACEncoder.cu:973-1057 (+ multichannel loop via sChannelMaps :97-107).
    pcm: interleaved little-endian packed PCM, num_samples sample-frames (<= frame_size).
-   out must hold num_samples*channels*bytes + 64 bytes.  trace may be NULL (else >= 8 entries). */
+   out must hold frame_size*channels*5 + 64 bytes (the pre-escape worst case, mMaxOutputBytes).
+   trace may be NULL (else >= 8 entries). */
 int32_t  orc_encode_packet(orc_encoder *e, const uint8_t *pcm, uint32_t num_samples,
                            uint8_t *out, uint32_t *out_bytes, orc_trace *trace);
 /* whole stream: frames of frame_size, tail partial; encoder reset every frames_per_segment

@@ -245,7 +245,7 @@ class Encoder:
         assert pcm.nbytes >= num_samples * self.bytes_per_frame
         padded = np.zeros(pcm.nbytes + 64, np.uint8)   # tiny tails read a few entries past n*stride
         padded[:pcm.nbytes] = pcm
-        out = np.zeros(num_samples * self.bytes_per_frame + 128, np.uint8)
+        out = np.zeros(self.frame_size * self.channels * 5 + 128, np.uint8)
         nb = C.c_uint32(0)
         tr = (Trace * 8)()
         st = self.L.orc_encode_packet(self.h, _ptr(padded), num_samples, _ptr(out), C.byref(nb), tr if trace else None)

@@ -88,3 +88,56 @@ def make(kind: str, frames: int, channels: int, depth: int, seed: int = 1) -> np
     fn = KINDS[kind]
     s = fn(frames, channels, depth, seed) if kind != "square" else fn(frames, channels, depth)
     return pack(s, depth)
+
+
+# ---------------------------------------------------------------------------------------------
+# Integer-only corpus generator (torch): identical bytes on CPU and on any GPU, so the CUDA arm,
+# the CPU baseline and the reference arm of bench.py all see the same workload.
+# ---------------------------------------------------------------------------------------------
+def _hash32(t, salt: int):
+    h = (t * 2654435761 + salt * 40503 + 0x9E3779B9) & 0xFFFFFFFF
+    h = h ^ (h >> 15)
+    h = (h * 2246822519) & 0xFFFFFFFF
+    h = h ^ (h >> 13)
+    h = (h * 3266489917) & 0xFFFFFFFF
+    return h ^ (h >> 16)
+
+
+def _para_sine(t, step: int, phase: int = 0):
+    """Parabolic 'sine' of amplitude 2^15 from a 16-bit phase accumulator (integers only)."""
+    x = ((t * step + phase) & 0xFFFF) - 32768
+    return (x * (32768 - x.abs())) >> 13
+
+
+def corpus_torch(first_frame: int, frames: int, channels: int, depth: int, device, seed: int = 0):
+    """S-music corpus: per channel a sum of three detuned tones with slow AM plus a
+    triangular-PDF noise floor; R = L - (L >> 3) + an independent low-level tone so the mid/side
+    search is exercised.  Returns packed little-endian interleaved bytes as a torch.uint8 tensor."""
+    import torch
+    t = torch.arange(first_frame, first_frame + frames, dtype=torch.int64, device=device)
+    am = 192 + (_para_sine(t >> 6, 3, seed * 977) >> 9)                     # 128..256, slow
+    base = (_para_sine(t, 327 + 2 * seed) >> 2) + (_para_sine(t, 823, 1111) >> 3) + (_para_sine(t, 1961, 5000) >> 4)
+    base = (base * am) >> 8                                                  # ~ +-13000 peak at 16 bit
+    up = depth - 16 if depth != 32 else 0
+    nz_bits = 7 if depth == 16 else 7 + min(up, 4)
+    cols = []
+    for c in range(channels):
+        h = _hash32(t, 2 * c + 1 + 16 * seed)
+        noise = (h & ((1 << nz_bits) - 1)) - ((h >> 12) & ((1 << nz_bits) - 1))
+        if c % 2 == 0:
+            s = base - ((base * (c // 2)) >> 3)
+        else:
+            s = base - (base >> 3) + (_para_sine(t, 97 + 41 * c, 300 * c) >> 5)
+        s = (s << up) + noise if up else s + noise
+        if depth == 32:
+            s = (s << 16) | (_hash32(t, 99 + c) & 0xFFFF)                    # 16 busy low bits
+        cols.append(s)
+    x = torch.stack(cols, dim=1)                                             # [frames, channels] int64
+    if depth == 16:
+        return x.to(torch.int16).view(torch.uint8).reshape(-1)
+    if depth == 32:
+        return x.to(torch.int32).view(torch.uint8).reshape(-1)
+    if depth == 20:
+        x = x << 4
+    b = torch.stack([(x & 0xFF), ((x >> 8) & 0xFF), ((x >> 16) & 0xFF)], dim=2).to(torch.uint8)
+    return b.reshape(-1)

@@ -136,11 +136,11 @@ def test_coef_state_streaming(engine, oracle):
     pcm = synth.make("music", 4096 * 6, 2, 16, seed=33)
     cfg = alac_b200.EncoderConfig(channels=2, bit_depth=16, frames_per_segment=0)
     half = 4096 * 3 * cfg.bytes_per_frame
-    state = np.zeros((1, 128), np.int16)
+    state = np.zeros((1, 256), np.int16)
     # a fresh state equals init_coefs rows
     init = np.zeros(8, np.int16)
     init[:3] = [1216, -928, -64]
-    state[:] = np.tile(init, 16)
+    state[:] = np.tile(init, 32)
     a = engine.encode(pcm[:half], cfg, coef_state=state)
     b = engine.encode(pcm[half:], cfg, coef_state=state)
     want = _oracle_encode(oracle, pcm, 2, 16, 0)

@@ -247,7 +247,13 @@ uint64_t alac_b200_encode_bound(const alac_b200_enc_config *c, uint64_t num_samp
     const uint64_t bpf = (uint64_t)bytes_per_sample(c->bit_depth) * c->channels;
     const uint64_t packets = num_sample_frames / c->frame_size + num_streams;
     // an element never exceeds its escape size: 7 + 16 + 32 header bits + raw samples; + ID_END + padding
-    return num_sample_frames * bpf + packets * (8ull * c->channels + 8ull);
+    return num_sample_frames * bpf + packets * (7ull * c->channels + 1ull);
+}
+
+// used by ALACDecoder::fillWriteBuffer (fork signature): host -> caller's device buffer
+int32_t alac_b200_copy_to_device(void *dst, const void *src, uint64_t bytes)
+{
+    return cudaMemcpy(dst, src, (size_t)bytes, cudaMemcpyHostToDevice) == cudaSuccess ? ALAC_B200_OK : ALAC_B200_CUDA_ERROR;
 }
 
 }  // extern "C"

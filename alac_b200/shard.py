@@ -1,0 +1,69 @@
+"""Frame-range sharding across ranks (one process per GPU).
+
+Encode shards by whole segments of frames_per_segment packets, decode by packets;
+both are byte-identical to the unsharded result by construction.  The only cross-rank step is
+putting the per-rank packet blocks back in order: every rank contributes (sizes, bytes) and the
+gather concatenates them in rank order -- a size all-gather plus a padded byte all-gather.
+Works with any torch.distributed backend (NCCL on GPUs, gloo in the CPU tests).
+"""
+from __future__ import annotations
+
+from typing import List, Tuple
+
+
+def plan_packet_shards(num_packets: int, world: int, frames_per_segment: int) -> List[Tuple[int, int]]:
+    """Contiguous [first_packet, count) per rank, boundaries aligned to whole segments.
+
+    frames_per_segment == 0 means the stream is one serial chain: it cannot be split, rank 0 gets it.
+    """
+    if world < 1:
+        raise ValueError("world must be >= 1")
+    if frames_per_segment == 0:
+        return [(0, num_packets)] + [(num_packets, 0)] * (world - 1)
+    segs = (num_packets + frames_per_segment - 1) // frames_per_segment
+    out = []
+    for r in range(world):
+        s0 = segs * r // world
+        s1 = segs * (r + 1) // world
+        p0 = min(s0 * frames_per_segment, num_packets)
+        p1 = min(s1 * frames_per_segment, num_packets)
+        out.append((p0, p1 - p0))
+    return out
+
+
+def plan_frame_shards(num_sample_frames: int, frame_size: int, world: int, frames_per_segment: int) -> List[Tuple[int, int]]:
+    """Per-rank [first_sample_frame, num_sample_frames) following plan_packet_shards."""
+    num_packets = (num_sample_frames + frame_size - 1) // frame_size
+    out = []
+    for p0, n in plan_packet_shards(num_packets, world, frames_per_segment):
+        a = min(p0 * frame_size, num_sample_frames)
+        b = min((p0 + n) * frame_size, num_sample_frames)
+        out.append((a, b - a))
+    return out
+
+
+def gather_packets(packets, sizes, group=None):
+    """All ranks call this with their packet bytes (uint8 tensor) and sizes (int32 tensor); every rank
+    gets back (all packets in rank order, all sizes).  Tensors stay on their device."""
+    import torch
+    import torch.distributed as dist
+
+    world = dist.get_world_size(group)
+    dev = packets.device
+    meta = torch.tensor([packets.numel(), sizes.numel()], dtype=torch.int64, device=dev)
+    metas = [torch.zeros_like(meta) for _ in range(world)]
+    dist.all_gather(metas, meta, group=group)
+    nbytes = [int(m[0]) for m in metas]
+    ncount = [int(m[1]) for m in metas]
+    pad_b, pad_c = max(max(nbytes), 1), max(max(ncount), 1)
+    pb = torch.zeros(pad_b, dtype=torch.uint8, device=dev)
+    pb[:packets.numel()] = packets
+    pc = torch.zeros(pad_c, dtype=torch.int32, device=dev)
+    pc[:sizes.numel()] = sizes.to(torch.int32)
+    all_b = [torch.empty_like(pb) for _ in range(world)]
+    all_c = [torch.empty_like(pc) for _ in range(world)]
+    dist.all_gather(all_b, pb, group=group)
+    dist.all_gather(all_c, pc, group=group)
+    out_p = torch.cat([b[:n] for b, n in zip(all_b, nbytes)])
+    out_s = torch.cat([c[:n] for c, n in zip(all_c, ncount)])
+    return out_p, out_s

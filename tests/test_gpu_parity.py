@@ -145,3 +145,85 @@ def test_coef_state_streaming(engine, oracle):
     b = engine.encode(pcm[half:], cfg, coef_state=state)
     want = _oracle_encode(oracle, pcm, 2, 16, 0)
     assert np.array_equal(np.concatenate([a.packets, b.packets]), want.packets)
+
+
+# ---------------------------------------------------------------------------------------------
+# golden vectors (made through the reference's own primitives, tests/golden/make_golden.py)
+# ---------------------------------------------------------------------------------------------
+import glob
+import os
+import subprocess
+
+_GOLDEN = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.npz")))
+_ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.mark.parametrize("path", _GOLDEN, ids=[os.path.basename(p)[:-4] for p in _GOLDEN])
+def test_golden_vectors(engine, path):
+    import alac_b200
+    g = np.load(path)
+    cfg = alac_b200.EncoderConfig(channels=int(g["channels"]), bit_depth=int(g["depth"]), sample_rate=int(g["sample_rate"]),
+                                  fast_mode=bool(g["fast_mode"]), frames_per_segment=int(g["frames_per_segment"]))
+    got = engine.encode(g["pcm"], cfg)
+    assert got.cookie == bytes(g["cookie"])
+    assert np.array_equal(np.asarray(got.sizes, np.uint32), g["sizes"])
+    assert np.array_equal(got.packets, g["packets"])
+    dec = engine.decode(bytes(g["cookie"]), g["packets"], g["sizes"])
+    assert dec.status == 0 and np.array_equal(dec.pcm, g["pcm"])
+
+
+def test_decode_error_status(engine):
+    """Truncated / corrupt packets give kALAC_ParamError per packet; good packets still decode."""
+    import alac_b200
+    g = np.load([p for p in _GOLDEN if "music_stereo16_k1" in p][0])
+    sizes = g["sizes"].copy()
+    packets = g["packets"].copy()
+    bad = packets.copy()
+    bad[1] |= 0x10                                  # unused header bits of packet 0 must be zero
+    dec = engine.decode(bytes(g["cookie"]), bad, sizes, raise_on_error=False)
+    assert dec.status == -50
+    assert int(dec.packet_status[0]) == -50 and not np.any(np.asarray(dec.packet_status[1:]))
+    # truncate the stream in the middle of packet 0
+    cut = int(sizes[0]) // 2
+    dec = engine.decode(bytes(g["cookie"]), packets[:cut].copy(), np.array([cut], np.uint32), raise_on_error=False)
+    assert dec.status == -50
+
+
+def test_decode_mixed_short_packets(engine, oracle):
+    """Config-5 shape at test size: many short packets with mixed frame sizes (32-bit samples)."""
+    rng = np.random.default_rng(0)
+    ch, depth = 2, 32
+    enc = oracle.Encoder(ch, depth, 48000, reference=oracle.have_reference())
+    pk, sz, pcms = [], [], []
+    for i in range(300):
+        n = int(rng.integers(32, 4097))
+        pcm = synth.make("music", n, ch, depth, seed=i)
+        enc.reset()
+        p = enc.encode_packet(pcm, n)
+        pk.append(p); sz.append(len(p)); pcms.append(pcm)
+    packets, sizes = np.concatenate(pk), np.array(sz, np.uint32)
+    dec = engine.decode(enc.cookie(), packets, sizes)
+    assert dec.status == 0
+    assert np.array_equal(dec.pcm, np.concatenate(pcms))
+
+
+# ---------------------------------------------------------------------------------------------
+# the C++ class API, driven like alacconvert drives libalac (one Encode() per frame)
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", ["wav05_mono16_k0", "wav50_stereo16_k0", "music_stereo24_k0", "music_5ch16_k0"])
+def test_class_api_demo(tmp_path, name):
+    import alac_b200
+    libdir = os.path.dirname(alac_b200.library_path())
+    exe = str(tmp_path / "class_api_demo")
+    subprocess.run(["g++", "-O2", "-std=c++17", "-I" + os.path.join(_ROOT, "include"),
+                    os.path.join(_ROOT, "tests", "cpp", "class_api_demo.cpp"), "-L" + libdir, "-lalac_b200",
+                    "-Wl,-rpath," + libdir, "-o", exe], check=True)
+    g = np.load(os.path.join(_ROOT, "tests", "golden", name + ".npz"))
+    raw = str(tmp_path / "in.raw")
+    g["pcm"].tofile(raw)
+    prefix = str(tmp_path / "out")
+    subprocess.run([exe, raw, str(int(g["channels"])), str(int(g["depth"])), str(int(g["sample_rate"])), prefix], check=True)
+    assert open(prefix + ".cookie", "rb").read() == bytes(g["cookie"])
+    assert np.array_equal(np.fromfile(prefix + ".sizes", np.uint32), g["sizes"])
+    assert np.array_equal(np.fromfile(prefix + ".packets", np.uint8), g["packets"])
+    assert np.array_equal(np.fromfile(prefix + ".pcm", np.uint8), g["pcm"])

@@ -124,7 +124,7 @@ __device__ __forceinline__ void decode_channel_fast(BitReader &br, uint32_t cap_
     }
     for (uint32_t j = TAPS + 1; j < n; j++) {
         const int32_t r = ag.next(br, cap_bits);
-        out(j, predict_dec_step<TAPS>(r, hist, a, chanshift));
+        out(j, predict_dec_step<TAPS, true>(r, hist, a, chanshift));
     }
 }
 

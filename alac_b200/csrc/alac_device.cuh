@@ -79,31 +79,35 @@ __device__ __forceinline__ void store_sample(uint8_t *p, int32_t v)
 
 // ---- sign-LMS predictor step -------------------------------------------------------------------
 // hist[0] = newest previous sample ... hist[TAPS-1], hist[TAPS] = "top" (codec/dp_enc.c:202-214).
-// Coefficients are carried as int32 holding int16 values; every update re-wraps to int16
-// exactly like the reference's int16_t registers.
-template <int TAPS>
+// Coefficients are carried as int32 holding int16 values.  WRAP = true re-wraps every update to
+// int16 exactly like the reference's int16_t registers; WRAP = false is used when the caller has
+// proved the values cannot leave the int16 range during the pass (|a| + steps <= 32767), in which
+// case the two are identical.
+template <int TAPS, bool WRAP>
 __device__ __forceinline__ void lms_adapt(int32_t (&a)[TAPS], const int32_t (&b)[TAPS], int32_t err)
 {
     // codec/dp_enc.c:236-329.  Branch-free ladder: the walk goes from the last tap to the first and
-    // stops when the running error crosses zero; "live" masks the taps after the stop.
-    // For err < 0 the reference shifts the non-positive product (-|b|) >> 9, i.e. rounds toward
-    // -inf: -ceil(|b|/512) == -((|b| + 511) >> 9)  (dp_enc.c:288).
-    const int32_t sg = err > 0 ? 1 : -1;
-    const uint32_t rnd = err > 0 ? 0u : 511u;
-    int32_t left = abs(err);
+    // stops once the running error `left` reaches or crosses zero; "live" masks the taps after that.
+    //   err > 0:  sgn =  sign(b);  a -= sgn;  left -= w * ((sgn * b) >> 9);  go on while left > 0
+    //   err < 0:  sgn = -sign(b);  a -= sgn;  left -= w * ((sgn * b) >> 9);  go on while left < 0
+    // (sgn * b) is +|b| or -|b|; the arithmetic shift of -|b| rounds toward -inf as in dp_enc.c:288.
+    // With m = err >> 31 the loop test is (left ^ m) > m for both signs.
+    const int32_t m = err >> 31;
+    const int32_t sg = m | 1;
+    int32_t left = err;
     bool live = (err != 0);
 #pragma unroll
     for (int k = TAPS - 1; k >= 0; k--) {
         const int32_t s = sign3(b[k]) * sg;
-        a[k] = live ? sext16(a[k] - s) : a[k];
-        const int32_t q = (int32_t)(((uint32_t)abs(b[k]) + rnd) >> kDenShift);
-        left -= (TAPS - k) * q;
-        live = live && (left > 0);
+        const int32_t upd = a[k] - s;
+        a[k] = live ? (WRAP ? sext16(upd) : upd) : a[k];
+        left -= (TAPS - k) * ((s * b[k]) >> kDenShift);
+        live = live && ((left ^ m) > m);
     }
 }
 
 // encode: returns the residual of x given the history, adapts coefficients, shifts the history in
-template <int TAPS>
+template <int TAPS, bool WRAP>
 __device__ __forceinline__ int32_t predict_enc_step(int32_t x, int32_t (&hist)[TAPS + 1], int32_t (&a)[TAPS], uint32_t chanshift)
 {
     const int32_t top = hist[TAPS];
@@ -115,7 +119,7 @@ __device__ __forceinline__ int32_t predict_enc_step(int32_t x, int32_t (&hist)[T
         acc -= a[k] * b[k];
     }
     const int32_t err = sext_bits(x - top - (acc >> kDenShift), chanshift);     // dp_enc.c:228-233
-    lms_adapt<TAPS>(a, b, err);
+    lms_adapt<TAPS, WRAP>(a, b, err);
 #pragma unroll
     for (int k = TAPS; k > 0; k--) hist[k] = hist[k - 1];
     hist[0] = x;
@@ -123,7 +127,7 @@ __device__ __forceinline__ int32_t predict_enc_step(int32_t x, int32_t (&hist)[T
 }
 
 // decode: returns the reconstructed sample for residual err (codec/dp_dec.c:206-282)
-template <int TAPS>
+template <int TAPS, bool WRAP>
 __device__ __forceinline__ int32_t predict_dec_step(int32_t err, int32_t (&hist)[TAPS + 1], int32_t (&a)[TAPS], uint32_t chanshift)
 {
     const int32_t top = hist[TAPS];
@@ -135,7 +139,7 @@ __device__ __forceinline__ int32_t predict_dec_step(int32_t err, int32_t (&hist)
         acc -= a[k] * b[k];
     }
     const int32_t x = sext_bits(err + top + (acc >> kDenShift), chanshift);
-    lms_adapt<TAPS>(a, b, err);
+    lms_adapt<TAPS, WRAP>(a, b, err);
 #pragma unroll
     for (int k = TAPS; k > 0; k--) hist[k] = hist[k - 1];
     hist[0] = x;
@@ -159,28 +163,25 @@ struct AgEnc {
 };
 
 // MSB-first bit sink: 32-bit words, word w holds stream bits [32w, 32w+32) with bit 32w in the MSB
+// The destination must hold the worst case: every sample code is <= 9 + 23 = 32 bits and a run code
+// (<= 25 bits) only ever follows a short sample code, so frame_size + 1 words always suffice.
 struct BitSink {
     uint32_t *dst;      // next word to write
-    uint32_t *end;      // capacity guard
     uint64_t acc;
     uint32_t nacc;
-    __device__ __forceinline__ void start(uint32_t *p, uint32_t cap_words) { dst = p; end = p + cap_words; acc = 0; nacc = 0; }
+    __device__ __forceinline__ void start(uint32_t *p, uint32_t /*cap_words*/) { dst = p; acc = 0; nacc = 0; }
     __device__ __forceinline__ void put(uint32_t value, uint32_t len)   // len 1..32, value < 2^len
     {
         acc = (acc << len) | value;
         nacc += len;
         if (nacc >= 32) {
             nacc -= 32;
-            if (dst < end) *dst = (uint32_t)(acc >> nacc);
-            dst++;
+            *dst++ = (uint32_t)(acc >> nacc);
         }
     }
     __device__ __forceinline__ void finish()
     {
-        if (nacc) {
-            if (dst < end) *dst = (uint32_t)(acc << (32 - nacc));
-            dst++;
-        }
+        if (nacc) *dst++ = (uint32_t)(acc << (32 - nacc));
     }
 };
 struct NoSink {

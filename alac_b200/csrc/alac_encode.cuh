@@ -54,35 +54,79 @@ struct EncArgs {
 // One lane's view of its channel after the reference's mix/copy stage (codec/matrix_enc.cu,
 // codec/ALACEncoder.cu:1144-1382): get(j) is u[j] (U lane) or v[j] (V lane); samples at or
 // beyond `valid` read as zero (deterministic-padding rule).
-template <int DEPTH, bool STEREO>
+// Loading is split from mixing so the predictor loop can issue the load of sample j + kAhead
+// while it works on sample j: fetch() only loads (no arithmetic on the result), mix() unpacks.
+// PACKED: a pure stereo stream (L, R adjacent, nothing in between) at natural alignment, so one
+// sample-frame is a single 32/64-bit load (16/32-bit) or three 16-bit loads (20/24-bit).
+template <int DEPTH, bool STEREO, bool PACKED>
 struct MixSrc {
+    static constexpr int kWords = !STEREO ? ((DEPTH == 16 || DEPTH == 32) ? 1 : 3)
+                                  : PACKED ? (DEPTH == 16 ? 1 : DEPTH == 32 ? 2 : 3)
+                                           : ((DEPTH == 16 || DEPTH == 32) ? 2 : 6);
+    static constexpr int kAhead = kWords <= 2 ? 4 : 2;      // prefetch distance in samples
+    struct Raw { uint32_t w[kWords]; };
+
     const uint8_t *base;    // sample-frame 0 of the packet, first channel of the element
     uint32_t stride;        // bytes per sample-frame
     uint32_t valid;
     int32_t mix_res;
     bool is_v;
+
+    __device__ __forceinline__ Raw fetch(uint32_t j) const
+    {
+        Raw r;
+        const uint8_t *p = base + (size_t)j * stride;
+        if (!STEREO) {
+            if (DEPTH == 16) r.w[0] = __ldg(reinterpret_cast<const uint16_t *>(p));
+            else if (DEPTH == 32) r.w[0] = __ldg(reinterpret_cast<const uint32_t *>(p));
+            else { r.w[0] = __ldg(p); r.w[1] = __ldg(p + 1); r.w[2] = __ldg(p + 2); }
+        } else if (PACKED) {
+            if (DEPTH == 16) r.w[0] = __ldg(reinterpret_cast<const uint32_t *>(p));
+            else if (DEPTH == 32) { const uint2 t = __ldg(reinterpret_cast<const uint2 *>(p)); r.w[0] = t.x; r.w[1] = t.y; }
+            else { const uint16_t *q = reinterpret_cast<const uint16_t *>(p); r.w[0] = __ldg(q); r.w[1] = __ldg(q + 1); r.w[2] = __ldg(q + 2); }
+        } else {
+            if (DEPTH == 16) { r.w[0] = __ldg(reinterpret_cast<const uint16_t *>(p)); r.w[1] = __ldg(reinterpret_cast<const uint16_t *>(p + 2)); }
+            else if (DEPTH == 32) { r.w[0] = __ldg(reinterpret_cast<const uint32_t *>(p)); r.w[1] = __ldg(reinterpret_cast<const uint32_t *>(p + 4)); }
+            else { for (int i = 0; i < 6; i++) r.w[i] = __ldg(p + i); }
+        }
+        return r;
+    }
+    static __device__ __forceinline__ int32_t widen(uint32_t w24)   // 20/24-bit container -> sample >> shift
+    {
+        return DEPTH == 20 ? ((int32_t)(w24 << 8) >> 12) : ((int32_t)(w24 << 8) >> (8 + DepthTraits<DEPTH>::kShift));
+    }
+    __device__ __forceinline__ int32_t mix(const Raw &r) const
+    {
+        constexpr uint32_t sh = DepthTraits<DEPTH>::kShift;
+        int32_t l, rr;
+        if (!STEREO) {
+            if (DEPTH == 16) return (int32_t)(int16_t)r.w[0];
+            if (DEPTH == 32) return (int32_t)r.w[0] >> sh;
+            return widen(r.w[0] | (r.w[1] << 8) | (r.w[2] << 16));
+        } else if (PACKED) {
+            if (DEPTH == 16) { l = (int32_t)(int16_t)(r.w[0] & 0xffffu); rr = (int32_t)r.w[0] >> 16; }
+            else if (DEPTH == 32) { l = (int32_t)r.w[0] >> sh; rr = (int32_t)r.w[1] >> sh; }
+            else { l = widen(r.w[0] | ((r.w[1] & 0xffu) << 16)); rr = widen((r.w[1] >> 8) | (r.w[2] << 8)); }
+        } else {
+            if (DEPTH == 16) { l = (int32_t)(int16_t)r.w[0]; rr = (int32_t)(int16_t)r.w[1]; }
+            else if (DEPTH == 32) { l = (int32_t)r.w[0] >> sh; rr = (int32_t)r.w[1] >> sh; }
+            else { l = widen(r.w[0] | (r.w[1] << 8) | (r.w[2] << 16)); rr = widen(r.w[3] | (r.w[4] << 8) | (r.w[5] << 16)); }
+        }
+        if (mix_res != 0) return is_v ? (l - rr) : ((mix_res * l + ((1 << kMixBits) - mix_res) * rr) >> kMixBits);
+        return is_v ? rr : l;
+    }
     __device__ __forceinline__ int32_t get(uint32_t j) const
     {
         if (j >= valid) return 0;
-        const uint8_t *p = base + (size_t)j * stride;
-        constexpr uint32_t sh = DepthTraits<DEPTH>::kShift;
-        if (!STEREO) {
-            return load_sample<DEPTH>(p) >> sh;
-        } else {
-            const int32_t l = load_sample<DEPTH>(p) >> sh;
-            const int32_t r = load_sample<DEPTH>(p + DepthTraits<DEPTH>::kBytes) >> sh;
-            if (mix_res != 0) {
-                return is_v ? (l - r) : ((mix_res * l + ((1 << kMixBits) - mix_res) * r) >> kMixBits);
-            }
-            return is_v ? r : l;
-        }
+        return mix(fetch(j));
     }
 };
 
 // pc_block(in, res, num, coefs, TAPS) streamed: sink(j, residual) is called for j = 0..max(num,TAPS+1)-1
 // exactly as the reference writes pc1[j] (warm-up entries 1..TAPS are written regardless of num,
-// codec/dp_enc.c:108-112).
-template <int TAPS, class Src, class Sink>
+// codec/dp_enc.c:108-112).  Requires num <= src.valid (true for every caller), so the main loop
+// needs no bounds checks; its loads run kAhead samples ahead of the arithmetic.
+template <int TAPS, bool WRAP, class Src, class Sink>
 __device__ __forceinline__ void predict_pass(const Src &src, uint32_t num, int32_t (&a)[TAPS], uint32_t chanshift, Sink &sink)
 {
     int32_t hist[TAPS + 1];
@@ -96,9 +140,18 @@ __device__ __forceinline__ void predict_pass(const Src &src, uint32_t num, int32
         hist[TAPS - j] = x;
         prev = x;
     }
+    if (num <= TAPS + 1) return;
+    constexpr int D = Src::kAhead;
+    const uint32_t last = num - 1;
+    typename Src::Raw q[D];
+#pragma unroll
+    for (int d = 0; d < D; d++) q[d] = src.fetch(min((uint32_t)(TAPS + 1 + d), last));
     for (uint32_t j = TAPS + 1; j < num; j++) {
-        const int32_t x = src.get(j);
-        const int32_t err = predict_enc_step<TAPS>(x, hist, a, chanshift);
+        const int32_t x = src.mix(q[0]);
+#pragma unroll
+        for (int d = 0; d + 1 < D; d++) q[d] = q[d + 1];
+        q[D - 1] = src.fetch(min(j + D, last));
+        const int32_t err = predict_enc_step<TAPS, WRAP>(x, hist, a, chanshift);
         sink(j, err);
     }
 }
@@ -141,25 +194,46 @@ __device__ __forceinline__ void init_coefs_row(int32_t *a, int n)
     a[2] = (-2 * 512) >> 4;
 }
 
-template <int DEPTH, bool STEREO>
-__global__ void __launch_bounds__(128)
+constexpr int kSearchThreads = 128;
+
+// What the final pass (stage C) of one channel needs; lets any lane of the CTA run it.
+struct FinalJob {
+    const uint8_t *base;    // sample-frame 0 of the packet, first channel of the element
+    uint32_t *slab;         // Golomb stream destination
+    int32_t coef[8];        // the selected coefficient row (in: after the search, out: after the pass)
+    uint32_t n;             // in: samples in the frame; out: Golomb bits produced
+    uint32_t flags;         // bit 0: V channel, bits 1..3: mixRes
+};
+
+template <int DEPTH, bool STEREO, bool PACKED, bool WRAP>
+__global__ void __launch_bounds__(kSearchThreads)
 enc_search_kernel(EncArgs A, uint32_t elems_of_kind, uint32_t kind_elem0 /* bitmask of element slots of this kind */)
 {
+    // Stages A and B keep the U and V chains of a pair on adjacent lanes (they trade bit counts by
+    // shuffle and always run the same tap count).  The final pass runs 4 OR 8 taps per channel, so
+    // before it the CTA's chains are regrouped by tap count through shared memory: lanes [0, n4) run
+    // the 4-tap pass, lanes [n4, n4 + n8) the 8-tap pass, and each warp stays uniform.
+    __shared__ FinalJob s_job[kSearchThreads];
+    __shared__ uint32_t s_cnt[kSearchThreads / 32][2];
+    __shared__ uint32_t s_pn_max;
+
     constexpr uint32_t kLanesPerJob = STEREO ? 2 : 1;
     const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t lane = threadIdx.x & 31u, wid = threadIdx.x >> 5;
     const uint32_t job = tid / kLanesPerJob;
     const bool is_v = STEREO && (tid & 1u);
     const uint32_t total_jobs = A.num_segments * elems_of_kind;
-    // lanes of a pair are both in or both out, so the shuffles below stay converged per pair
-    if (job >= total_jobs) return;
-    const uint32_t pair_mask = STEREO ? (3u << ((threadIdx.x & 31u) & ~1u)) : 0u;
+    const bool in_range = job < total_jobs;         // lanes of a pair are both in or both out
+    const uint32_t pair_mask = STEREO ? (3u << (lane & ~1u)) : 0u;
 
-    const uint32_t seg = A.seg_base + job / elems_of_kind;
-    uint32_t which = job % elems_of_kind;
-    // slot = index of the which-th element of this kind inside the packet
-    uint32_t slot = 0;
-    for (uint32_t s = 0, m = kind_elem0; s < 8; s++, m >>= 1) {
-        if (m & 1u) { if (which == 0) { slot = s; break; } which--; }
+    uint32_t slot = 0, seg = A.seg_base;
+    if (in_range) {
+        seg = A.seg_base + job / elems_of_kind;
+        uint32_t which = job % elems_of_kind;
+        // slot = index of the which-th element of this kind inside the packet
+        for (uint32_t s = 0, m = kind_elem0; s < 8; s++, m >>= 1) {
+            if (m & 1u) { if (which == 0) { slot = s; break; } which--; }
+        }
     }
     const uint32_t chan = A.lay.elem_chan[slot];
     const uint32_t chain = A.lay.elem_chain[slot] + (is_v ? 1u : 0u);
@@ -171,9 +245,9 @@ enc_search_kernel(EncArgs A, uint32_t elems_of_kind, uint32_t kind_elem0 /* bitm
 
     // coefficient rows 3 (4 taps) and 7 (8 taps) of this channel (codec/ALACEncoder.h:89-90)
     int32_t c4[4], c8[8];
-    const uint32_t seg_info = A.seg_stream[seg];
+    const uint32_t seg_info = in_range ? A.seg_stream[seg] : 0u;
     const uint32_t stream = seg_info & 0x3fffffffu;
-    int16_t *st = A.state ? A.state + ((size_t)stream * 8 + chan) * 32 + (is_v ? 16 : 0) : nullptr;
+    int16_t *st = (A.state && in_range) ? A.state + ((size_t)stream * 8 + chan) * 32 + (is_v ? 16 : 0) : nullptr;
     if (st && (seg_info & 0x80000000u)) {
         for (int k = 0; k < 4; k++) c4[k] = st[k];
         for (int k = 0; k < 8; k++) c8[k] = st[8 + k];
@@ -182,16 +256,23 @@ enc_search_kernel(EncArgs A, uint32_t elems_of_kind, uint32_t kind_elem0 /* bitm
         init_coefs_row(c8, 8);
     }
 
-    const uint32_t p0 = A.seg_first[seg];
-    const uint32_t pn = A.seg_count[seg];
-    for (uint32_t pi = 0; pi < pn; pi++) {
-        const uint32_t pkt = p0 + pi;
-        const uint32_t n = A.pkt_samples[pkt];
+    const uint32_t p0 = in_range ? A.seg_first[seg] : 0u;
+    const uint32_t pn = in_range ? A.seg_count[seg] : 0u;
+    if (threadIdx.x == 0) s_pn_max = 0;
+    __syncthreads();
+    atomicMax(&s_pn_max, pn);
+    __syncthreads();
+    const uint32_t pn_max = s_pn_max;               // CTA-uniform trip count (barriers inside the loop)
+
+    for (uint32_t pi = 0; pi < pn_max; pi++) {
+        const bool valid = pi < pn;
+        const uint32_t pkt = valid ? p0 + pi : A.pkt_base;
+        const uint32_t n = valid ? A.pkt_samples[pkt] : 0u;
         const uint8_t *base = A.pcm + (A.pkt_frame[pkt] * A.lay.channels + chan) * bps;
         uint32_t *slab = A.scratch + ((size_t)(pkt - A.pkt_base) * A.lay.chains_per_packet + chain) * A.cap_words;
         const uint32_t partial = (n != A.lay.frame_size);
 
-        MixSrc<DEPTH, STEREO> src;
+        MixSrc<DEPTH, STEREO, PACKED> src;
         src.base = base; src.stride = stride; src.is_v = is_v; src.mix_res = 0; src.valid = n;
 
         uint32_t best_res = 0;
@@ -200,7 +281,7 @@ enc_search_kernel(EncArgs A, uint32_t elems_of_kind, uint32_t kind_elem0 /* bitm
         int do_escape = 0;
 
         const bool fast = STEREO && A.lay.fast_mode;   // EncodeMono has no fast variant
-        if (!fast) {
+        if (!fast && valid) {
             if (STEREO) {
                 // stage A: mixRes search, first n/8 samples, chained on row 7 (:353-379)
                 const uint32_t na = n / 8;
@@ -212,7 +293,7 @@ enc_search_kernel(EncArgs A, uint32_t elems_of_kind, uint32_t kind_elem0 /* bitm
                     cs.ag.start(na);
                     cs.bit_size = chan_bits;
                     cs.keep = (r == kMaxRes) ? reinterpret_cast<int32_t *>(slab) : nullptr;
-                    predict_pass<8>(src, na, c8, chanshift, cs);
+                    predict_pass<8, WRAP>(src, na, c8, chanshift, cs);
                     const uint32_t both = cs.ag.bits + __shfl_xor_sync(pair_mask, cs.ag.bits, 1);
                     if (both < min_bits) { min_bits = both; best_res = (uint32_t)r; }
                 }
@@ -231,11 +312,11 @@ enc_search_kernel(EncArgs A, uint32_t elems_of_kind, uint32_t kind_elem0 /* bitm
                 cs.keep = nullptr;
                 NullSink null_sink;
                 if (taps == 4) {
-                    for (int pass = 0; pass < 7; pass++) predict_pass<4>(src, nb, c4, chanshift, null_sink);
-                    predict_pass<4>(src, STEREO ? nb : nc, c4, chanshift, cs);
+                    for (int pass = 0; pass < 7; pass++) predict_pass<4, WRAP>(src, nb, c4, chanshift, null_sink);
+                    predict_pass<4, WRAP>(src, STEREO ? nb : nc, c4, chanshift, cs);
                 } else {
-                    for (int pass = 0; pass < 7; pass++) predict_pass<8>(src, nb, c8, chanshift, null_sink);
-                    predict_pass<8>(src, STEREO ? nb : nc, c8, chanshift, cs);
+                    for (int pass = 0; pass < 7; pass++) predict_pass<8, WRAP>(src, nb, c8, chanshift, null_sink);
+                    predict_pass<8, WRAP>(src, STEREO ? nb : nc, c8, chanshift, cs);
                 }
                 if (STEREO) {
                     // residuals [max(n/32, taps+1), n/8) are what the mixRes=4 trial left behind (F4)
@@ -264,30 +345,74 @@ enc_search_kernel(EncArgs A, uint32_t elems_of_kind, uint32_t kind_elem0 /* bitm
 
         // header coefficients are the post-search, pre-final-pass values (:479-485)
         ElemRec *rec = A.recs + (size_t)(pkt - A.pkt_base) * A.lay.elems_per_packet + slot;
-        {
+        if (valid) {
             int16_t *hc = is_v ? rec->coef_v : rec->coef_u;
             if (num_mine == 4) { for (int k = 0; k < 4; k++) hc[k] = (int16_t)c4[k]; for (int k = 4; k < 8; k++) hc[k] = 0; }
             else { for (int k = 0; k < 8; k++) hc[k] = (int16_t)c8[k]; }
         }
 
-        uint32_t my_bits = 0;
-        if (!do_escape) {
-            // stage C: final predictor + Golomb pass over the whole frame (:507-531, :941-945)
+        // ---- stage C: final predictor + Golomb pass over the whole frame (:507-531, :941-945),
+        //      regrouped by tap count across the CTA
+        const uint32_t key = (valid && !do_escape) ? (num_mine == 8 ? 1u : 0u) : 2u;
+        const uint32_t b4 = __ballot_sync(0xffffffffu, key == 0), b8 = __ballot_sync(0xffffffffu, key == 1);
+        if (lane == 0) { s_cnt[wid][0] = __popc(b4); s_cnt[wid][1] = __popc(b8); }
+        __syncthreads();
+        uint32_t n4 = 0, n8 = 0, before4 = 0, before8 = 0;
+#pragma unroll
+        for (uint32_t w = 0; w < kSearchThreads / 32; w++) {
+            if (w < wid) { before4 += s_cnt[w][0]; before8 += s_cnt[w][1]; }
+            n4 += s_cnt[w][0];
+            n8 += s_cnt[w][1];
+        }
+        const uint32_t lt = (1u << lane) - 1u;
+        const uint32_t my_slot = key == 0 ? before4 + __popc(b4 & lt) : n4 + before8 + __popc(b8 & lt);
+        if (key < 2) {
+            FinalJob &J = s_job[my_slot];
+            J.base = base;
+            J.slab = slab;
+            J.n = n;
+            J.flags = (is_v ? 1u : 0u) | (best_res << 1);
+            if (key == 0) { for (int k = 0; k < 4; k++) J.coef[k] = c4[k]; }
+            else { for (int k = 0; k < 8; k++) J.coef[k] = c8[k]; }
+        }
+        __syncthreads();
+        if (threadIdx.x < n4 + n8) {
+            FinalJob &J = s_job[threadIdx.x];
+            MixSrc<DEPTH, STEREO, PACKED> fs;
+            fs.base = J.base; fs.stride = stride; fs.is_v = (J.flags & 1u) != 0; fs.mix_res = (int32_t)(J.flags >> 1);
+            fs.valid = J.n;
             EmitSink es;
-            es.ag.start(n);
+            es.ag.start(J.n);
             es.bit_size = chan_bits;
-            es.bits.start(slab, A.cap_words);
-            if (num_mine == 4) predict_pass<4>(src, n, c4, chanshift, es);
-            else predict_pass<8>(src, n, c8, chanshift, es);
+            es.bits.start(J.slab, A.cap_words);
+            if (threadIdx.x < n4) {
+                int32_t a[4];
+                for (int k = 0; k < 4; k++) a[k] = J.coef[k];
+                predict_pass<4, WRAP>(fs, J.n, a, chanshift, es);
+                for (int k = 0; k < 4; k++) J.coef[k] = a[k];
+            } else {
+                int32_t a[8];
+                for (int k = 0; k < 8; k++) a[k] = J.coef[k];
+                predict_pass<8, WRAP>(fs, J.n, a, chanshift, es);
+                for (int k = 0; k < 8; k++) J.coef[k] = a[k];
+            }
             es.bits.finish();
-            my_bits = es.ag.bits;
+            J.n = es.ag.bits;
+        }
+        __syncthreads();
+        uint32_t my_bits = 0;
+        if (key < 2) {
+            const FinalJob &J = s_job[my_slot];
+            my_bits = J.n;
+            if (key == 0) { for (int k = 0; k < 4; k++) c4[k] = J.coef[k]; }
+            else { for (int k = 0; k < 8; k++) c8[k] = J.coef[k]; }
         }
 
         // sizes, post-check (:537-543, :952-958; fast mode :703-725)
         uint32_t other_bits = 0, other_num = 0;
         if (STEREO) {
-            other_bits = __shfl_xor_sync(pair_mask, my_bits, 1);
-            other_num = __shfl_xor_sync(pair_mask, num_mine, 1);
+            other_bits = __shfl_xor_sync(0xffffffffu, my_bits, 1);
+            other_num = __shfl_xor_sync(0xffffffffu, num_mine, 1);
         }
         const uint32_t escape_bits = n * DEPTH * kLanesPerJob + (partial ? 32u : 0u) + 16;
         uint32_t body_bits;     // element bits after tag+instance when compressed
@@ -301,7 +426,7 @@ enc_search_kernel(EncArgs A, uint32_t elems_of_kind, uint32_t kind_elem0 /* bitm
             }
             if (!do_escape && body_bits >= escape_bits) do_escape = 2;
         }
-        if (!is_v) {
+        if (valid && !is_v) {
             rec->escape = (uint8_t)do_escape;
             rec->mix_res = (uint8_t)best_res;
             rec->bits_u = my_bits;

@@ -261,19 +261,35 @@ int32_t alac_b200_copy_to_device(void *dst, const void *src, uint64_t bytes)
 // ------------------------------------------------------------------------------------------------
 // encode
 // ------------------------------------------------------------------------------------------------
-template <int DEPTH>
-static void launch_search(alac_b200_engine *e, const EncArgs &A, uint32_t mono_mask, uint32_t pair_mask)
+template <int DEPTH, bool PACKED, bool WRAP>
+static void launch_search_v(alac_b200_engine *e, const EncArgs &A, uint32_t mono_mask, uint32_t pair_mask)
 {
     const uint32_t pairs = __builtin_popcount(pair_mask), monos = __builtin_popcount(mono_mask);
     if (pairs) {
         const uint64_t threads = (uint64_t)A.num_segments * pairs * 2;
-        enc_search_kernel<DEPTH, true><<<(uint32_t)((threads + 127) / 128), 128, 0, e->stream>>>(A, pairs, pair_mask);
+        enc_search_kernel<DEPTH, true, PACKED, WRAP>
+            <<<(uint32_t)((threads + kSearchThreads - 1) / kSearchThreads), kSearchThreads, 0, e->stream>>>(A, pairs, pair_mask);
         e->launches++;
     }
     if (monos) {
         const uint64_t threads = (uint64_t)A.num_segments * monos;
-        enc_search_kernel<DEPTH, false><<<(uint32_t)((threads + 127) / 128), 128, 0, e->stream>>>(A, monos, mono_mask);
+        enc_search_kernel<DEPTH, false, false, WRAP>
+            <<<(uint32_t)((threads + kSearchThreads - 1) / kSearchThreads), kSearchThreads, 0, e->stream>>>(A, monos, mono_mask);
         e->launches++;
+    }
+}
+
+// packed: pure stereo PCM at 8-byte alignment (one wide load per sample-frame);
+// wrap: the int16 coefficient range could be left during a segment, so every update re-wraps
+template <int DEPTH>
+static void launch_search(alac_b200_engine *e, const EncArgs &A, uint32_t mono_mask, uint32_t pair_mask, bool packed, bool wrap)
+{
+    if (packed) {
+        if (wrap) launch_search_v<DEPTH, true, true>(e, A, mono_mask, pair_mask);
+        else launch_search_v<DEPTH, true, false>(e, A, mono_mask, pair_mask);
+    } else {
+        if (wrap) launch_search_v<DEPTH, false, true>(e, A, mono_mask, pair_mask);
+        else launch_search_v<DEPTH, false, false>(e, A, mono_mask, pair_mask);
     }
 }
 
@@ -396,6 +412,10 @@ extern "C" int32_t alac_b200_encode(alac_b200_engine *e, const alac_b200_enc_con
     CU_CHECK(e, cudaEventRecord(e->ev[1], st));
 
     // ---- kernels, chunk by chunk ----
+    // coefficients move by at most 1 per predictor step and a frame runs < 2 * frame_size steps on a row:
+    // starting from init_coefs (|a| <= 1216) the int16 range cannot be left within K frames if this holds
+    const bool wrap = coef_state != nullptr || K == 0 || (uint64_t)K * 2u * F + 1216u > 32767u;
+    const bool packed = cfg->channels == 2 && (reinterpret_cast<uintptr_t>(d_pcm) & 7u) == 0;
     unsigned long long *d_escapes = e->counters.as<unsigned long long>();
     uint32_t *d_max = reinterpret_cast<uint32_t *>(e->counters.as<uint8_t>() + 8);
     uint32_t s0 = 0;
@@ -423,10 +443,10 @@ extern "C" int32_t alac_b200_encode(alac_b200_engine *e, const alac_b200_enc_con
         A.state = d_state;
         t_search.push_back(e->timer());
         switch (cfg->bit_depth) {
-        case 16: launch_search<16>(e, A, mono_mask, pair_mask); break;
-        case 20: launch_search<20>(e, A, mono_mask, pair_mask); break;
-        case 24: launch_search<24>(e, A, mono_mask, pair_mask); break;
-        default: launch_search<32>(e, A, mono_mask, pair_mask); break;
+        case 16: launch_search<16>(e, A, mono_mask, pair_mask, packed, wrap); break;
+        case 20: launch_search<20>(e, A, mono_mask, pair_mask, packed, wrap); break;
+        case 24: launch_search<24>(e, A, mono_mask, pair_mask, packed, wrap); break;
+        default: launch_search<32>(e, A, mono_mask, pair_mask, packed, wrap); break;
         }
         t_search.push_back(e->timer());
         enc_size_kernel<<<(uint32_t)((cnt + 255) / 256), 256, 0, st>>>(A.recs, L.elems_per_packet, (uint32_t)cnt,

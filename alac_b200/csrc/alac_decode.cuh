@@ -2,11 +2,18 @@
 //
 //   dec_header_kernel   one lane per packet: reads the first audio element's header to learn the
 //                       packet's sample count (partial-frame field), so output offsets can be scanned.
-//   dec_packet_kernel   one lane per packet: ALACDecoder::Decode (codec/ALACDecoder.cu:571-1002)
-//                       with dyn_decomp, unpc_block, the shift-byte merge and unmixNN /
-//                       copyPredictorToNN (codec/ALACDecoder.cu:193-495) fused per sample.
-//                       A pair's U samples are parked in the pair's own output slots (>= 4 bytes
-//                       per sample-frame) until V arrives, so no side buffer exists.
+//                       Also classifies the packet by predictor orders; dec_perm_kernel turns the
+//                       classes into a lane -> packet permutation so warps run uniform tap counts.
+//   dec_lane_kernel     one lane per packet: the serial part of ALACDecoder::Decode
+//                       (codec/ALACDecoder.cu:571-1002): element loop, header parse, dyn_decomp and
+//                       unpc_block fused per sample.  Each channel's int32 samples (u / v / mono) go
+//                       to a scratch laid out [group of 32 packets][channel][sample][lane], so every
+//                       store of a warp is one 128-byte line; a DecChanMeta per channel says how to
+//                       finish it.  The bitstream arrives through a cp.async shared-memory ring.
+//   dec_output_kernel   the data-parallel part (codec/ALACDecoder.cu:193-495 unmixNN /
+//                       copyPredictorToNN): 32 packets x 32 samples tiles are transposed through
+//                       shared memory, un-mixed, merged with the shift bytes read straight from the
+//                       packet, packed and stored with coalesced writes.
 #pragma once
 #include "alac_device.cuh"
 
@@ -22,7 +29,24 @@ struct DecArgs {
     const uint64_t *out_frame;    // first output sample-frame of each packet (exclusive scan)
     uint32_t *pkt_samples;
     int32_t *pkt_status;
+    // lane -> packet permutation that groups packets by predictor order (warp-uniform tap counts)
+    uint32_t *pkt_class, *pkt_rank, *class_count, *perm;
+    int32_t *chan_scratch;        // [group][channel][frame_length][32]
+    struct DecChanMeta *chan_meta; // [packet][channel]
 };
+
+// how dec_output_kernel finishes one channel of one packet
+enum : uint32_t { CH_ZERO = 0, CH_MONO = 1, CH_PAIR_U = 2, CH_PAIR_V = 3 };
+struct DecChanMeta {
+    uint32_t n;             // samples
+    uint32_t shift_pos;     // bit position of the element's shift region inside the packet
+    uint8_t kind;           // CH_*
+    uint8_t shift;          // shifted-off bits per sample (0, 8, 16)
+    int8_t mix_res;
+    uint8_t mix_bits;
+};
+
+constexpr uint32_t kDecClasses = 16;
 
 // walk element tags until the first SCE/LFE/CPE and return its sample count
 __global__ void dec_header_kernel(DecArgs A)
@@ -30,9 +54,10 @@ __global__ void dec_header_kernel(DecArgs A)
     const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= A.num_packets) return;
     const uint32_t size = A.pkt_size[p];
-    BitReader br;
+    BitPeek br;
     br.start(A.packets + A.pkt_off[p], size);
     uint32_t n = A.frame_length;
+    uint32_t cls = kDecClasses - 1;     // escape / no audio element / unusual orders
     for (int guard = 0; guard < 64; guard++) {
         if (!((br.pos >> 3) < size)) break;
         const uint32_t tag = br.get(3);
@@ -40,6 +65,14 @@ __global__ void dec_header_kernel(DecArgs A)
             br.pos += 4 + 12;
             const uint32_t hb = br.get(4);
             if (hb >> 3) { n = br.get(16) << 16; n |= br.get(16); }
+            if (!(hb & 1u)) {
+                // predictor orders of the first element: class = 3 * order(U) + order(V), order in {4, 8, other}
+                br.pos += 16 + 8;
+                const uint32_t nu = br.get(8) & 0x1fu;
+                uint32_t nv = 4;
+                if (tag == ID_CPE) { br.pos += nu * 16 + 8; nv = br.get(8) & 0x1fu; }
+                cls = 3 * (nu == 4 ? 0u : nu == 8 ? 1u : 2u) + (nv == 4 ? 0u : nv == 8 ? 1u : 2u);
+            }
             break;
         } else if (tag == ID_DSE) {                 // codec/ALACDecoder.cu:1033-1059
             br.pos += 4;
@@ -57,32 +90,19 @@ __global__ void dec_header_kernel(DecArgs A)
         }
     }
     A.pkt_samples[p] = n <= A.frame_length ? n : 0u;
+    A.pkt_class[p] = cls;
+    A.pkt_rank[p] = atomicAdd(&A.class_count[cls], 1u);
 }
 
-// U samples parked in the pair's output slot (2 * bytes-per-sample >= 4 bytes, see file header)
-template <int DEPTH>
-__device__ __forceinline__ void park_store(uint8_t *p, int32_t v)
+// perm[first slot of the packet's class + its rank inside the class] = packet
+__global__ void dec_perm_kernel(DecArgs A)
 {
-    if (DEPTH == 16) {
-        reinterpret_cast<uint16_t *>(p)[0] = (uint16_t)v;
-        reinterpret_cast<uint16_t *>(p)[1] = (uint16_t)((uint32_t)v >> 16);
-    } else if (DEPTH == 32) {
-        *reinterpret_cast<int32_t *>(p) = v;
-    } else {
-        p[0] = (uint8_t)v; p[1] = (uint8_t)(v >> 8); p[2] = (uint8_t)(v >> 16);
-    }
-}
-template <int DEPTH>
-__device__ __forceinline__ int32_t park_load(const uint8_t *p)
-{
-    if (DEPTH == 16) {
-        return (int32_t)((uint32_t)reinterpret_cast<const uint16_t *>(p)[0] | ((uint32_t)reinterpret_cast<const uint16_t *>(p)[1] << 16));
-    } else if (DEPTH == 32) {
-        return *reinterpret_cast<const int32_t *>(p);
-    } else {
-        const uint32_t w = (uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16);
-        return (int32_t)(w << 8) >> 8;
-    }
+    const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= A.num_packets) return;
+    const uint32_t cls = A.pkt_class[p];
+    uint32_t first = 0;
+    for (uint32_t c = 0; c < cls; c++) first += A.class_count[c];
+    A.perm[first + A.pkt_rank[p]] = p;
 }
 
 struct ChanHeader {
@@ -102,7 +122,7 @@ __device__ __forceinline__ void read_chan_header(BitReader &br, ChanHeader &h)
 }
 
 // dyn_decomp + unpc_block for one channel, streamed; out(j, sample) receives the n samples.
-template <int TAPS, class Out>
+template <int TAPS, bool WRAP, class Out>
 __device__ __forceinline__ void decode_channel_fast(BitReader &br, uint32_t cap_bits, AgDec &ag, uint32_t n,
                                                     const ChanHeader &h, uint32_t chanshift, Out &out)
 {
@@ -124,14 +144,17 @@ __device__ __forceinline__ void decode_channel_fast(BitReader &br, uint32_t cap_
     }
     for (uint32_t j = TAPS + 1; j < n; j++) {
         const int32_t r = ag.next(br, cap_bits);
-        out(j, predict_dec_step<TAPS, true>(r, hist, a, chanshift));
+        out(j, predict_dec_step<TAPS, WRAP>(r, hist, a, chanshift));
     }
 }
 
 // any numactive 0..31, any denShift, mode != 0 (codec/dp_dec.c:67-95, :335-380; codec/ALACDecoder.cu:686-694)
+// Everything is taken BY VALUE (and the reader / coder state handed back) so that this rarely-run,
+// out-of-line routine does not force the hot objects of the fast paths into local memory.
+struct GeneralState { BitReader br; AgDec ag; };
 template <class Out>
-__device__ __noinline__ void decode_channel_general(BitReader &br, uint32_t cap_bits, AgDec &ag, uint32_t n,
-                                                    ChanHeader &h, uint32_t chanshift, Out &out)
+__device__ __noinline__ GeneralState decode_channel_general(BitReader br, uint32_t cap_bits, AgDec ag, uint32_t n,
+                                                            ChanHeader h, uint32_t chanshift, Out out)
 {
     int32_t ring[32];
     for (int k = 0; k < 32; k++) ring[k] = 0;
@@ -179,6 +202,10 @@ __device__ __noinline__ void decode_channel_general(BitReader &br, uint32_t cap_
         prev = x;
         out(j, x);
     }
+    GeneralState gs;
+    gs.br = br;
+    gs.ag = ag;
+    return gs;
 }
 
 template <class Out>
@@ -188,69 +215,57 @@ __device__ __forceinline__ int32_t decode_channel(BitReader &br, uint32_t cap_bi
     AgDec ag;
     ag.start(br, n, A.mb, (A.pb * h.pb_factor) / 4, A.kb, chan_bits);       // codec/ALACDecoder.cu:682
     const uint32_t chanshift = 32u - chan_bits;
-    if (h.mode == 0 && h.den_shift == kDenShift && h.num == 4) decode_channel_fast<4>(br, cap_bits, ag, n, h, chanshift, out);
-    else if (h.mode == 0 && h.den_shift == kDenShift && h.num == 8) decode_channel_fast<8>(br, cap_bits, ag, n, h, chanshift, out);
-    else decode_channel_general(br, cap_bits, ag, n, h, chanshift, out);
+    // coefficients move by at most 1 per sample: if max|a| + n stays inside int16 no update can wrap and
+    // the cheaper no-wrap step is exact
+    int32_t amax = 0;
+    for (uint32_t i = 0; i < h.num; i++) amax = max(amax, abs((int32_t)h.coefs[i]));
+    const bool safe = (uint32_t)amax + n <= 32767u;
+    const bool fast = h.mode == 0 && h.den_shift == kDenShift;
+    if (fast && h.num == 4) {
+        if (safe) decode_channel_fast<4, false>(br, cap_bits, ag, n, h, chanshift, out);
+        else decode_channel_fast<4, true>(br, cap_bits, ag, n, h, chanshift, out);
+    } else if (fast && h.num == 8) {
+        if (safe) decode_channel_fast<8, false>(br, cap_bits, ag, n, h, chanshift, out);
+        else decode_channel_fast<8, true>(br, cap_bits, ag, n, h, chanshift, out);
+    } else {
+        const GeneralState gs = decode_channel_general(br, cap_bits, ag, n, h, chanshift, out);
+        br = gs.br;
+        ag = gs.ag;
+    }
     // dyn_decomp's exit check "cur <= end" (codec/ag_dec.c:359)
     if (!ag.status && (br.pos >> 3) > (cap_bits >> 3)) ag.status = -50;
     return ag.status;
 }
 
-template <int DEPTH>
-struct MonoOut {
-    uint8_t *base; uint32_t stride; uint32_t shift; BitReader sr;
-    __device__ __forceinline__ void operator()(uint32_t j, int32_t v)
-    {
-        if (shift) v = (int32_t)(((uint32_t)v << shift) | sr.get(shift));     // codec/ALACDecoder.cu:436-495
-        store_sample<DEPTH>(base + (size_t)j * stride, v);
-    }
-};
-template <int DEPTH>
-struct ParkOut {
-    uint8_t *base; uint32_t stride;
-    __device__ __forceinline__ void operator()(uint32_t j, int32_t v) { park_store<DEPTH>(base + (size_t)j * stride, v); }
-};
-template <int DEPTH>
-struct PairOut {
-    uint8_t *base; uint32_t stride; uint32_t shift; int32_t mix_res; uint32_t mix_bits; BitReader sr;
-    __device__ __forceinline__ void operator()(uint32_t j, int32_t v)
-    {
-        uint8_t *p = base + (size_t)j * stride;
-        const int32_t u = park_load<DEPTH>(p);
-        int32_t l, r;
-        if (mix_res != 0) {                         // codec/ALACDecoder.cu:193-223
-            l = u + v - ((mix_res * v) >> mix_bits);
-            r = l - v;
-        } else {
-            l = u;
-            r = v;
-        }
-        if (shift) {                                // :282-383
-            const uint32_t both = sr.get(2 * shift);
-            l = (int32_t)(((uint32_t)l << shift) | (both >> shift));
-            r = (int32_t)(((uint32_t)r << shift) | (both & ((1u << shift) - 1u)));
-        }
-        store_sample<DEPTH>(p, l);
-        store_sample<DEPTH>(p + DepthTraits<DEPTH>::kBytes, r);
-    }
+// channel samples -> scratch [sample][lane]: one coalesced line per warp store
+struct ScratchOut {
+    int32_t *dst;           // this lane's column of the channel's [frame_length][32] tile
+    __device__ __forceinline__ void operator()(uint32_t j, int32_t v) { dst[(size_t)j * 32u] = v; }
 };
 
 template <int DEPTH>
-__global__ void __launch_bounds__(128) dec_packet_kernel(DecArgs A)
+__global__ void __launch_bounds__(kRingStride) dec_lane_kernel(DecArgs A)
 {
-    const uint32_t pkt = blockIdx.x * blockDim.x + threadIdx.x;
-    if (pkt >= A.num_packets) return;
-    constexpr uint32_t bps = DepthTraits<DEPTH>::kBytes;
+    __shared__ uint32_t s_ring[kRingSlots][kRingStride];
+    const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
+    if (tid >= A.num_packets) return;
+    const uint32_t pkt = A.perm[tid];
     const uint32_t nch = A.num_channels;
-    const uint32_t stride = nch * bps;
     const uint32_t size = A.pkt_size[pkt];
     const uint32_t cap_bits = size * 8u;
     const uint32_t slot_samples = A.pkt_samples[pkt];
-    uint8_t *out_base = A.pcm_out + A.out_frame[pkt] * stride;
+    const uint32_t F = A.frame_length;
+    int32_t *tile0 = A.chan_scratch + ((size_t)(tid >> 5) * nch * F) * 32u + (tid & 31u);
+    DecChanMeta *meta = A.chan_meta + (size_t)pkt * nch;
+    for (uint32_t c = 0; c < nch; c++) {            // channels that never arrive are zero-filled (:972-998)
+        DecChanMeta z;
+        z.n = slot_samples; z.shift_pos = 0; z.kind = CH_ZERO; z.shift = 0; z.mix_res = 0; z.mix_bits = 0;
+        meta[c] = z;
+    }
     BitReader br;
-    br.start(A.packets + A.pkt_off[pkt], size);
+    br.start(A.packets + A.pkt_off[pkt], size, &s_ring[0][threadIdx.x]);
 
-    uint32_t n = A.frame_length;
+    uint32_t n = F;
     uint32_t channel_index = 0;
     int32_t status = 0;
     ChanHeader hu, hv;
@@ -258,81 +273,52 @@ __global__ void __launch_bounds__(128) dec_packet_kernel(DecArgs A)
     while (status == 0) {
         if (!((br.pos >> 3) < size)) { status = -50; break; }                   // :615
         const uint32_t tag = br.get(3);
-        if (tag == ID_SCE || tag == ID_LFE) {
+        if (tag == ID_SCE || tag == ID_LFE || tag == ID_CPE) {
+            const bool pair = (tag == ID_CPE);
+            if (pair && channel_index + 2 > nch) break;                         // :759-760
+            if (!pair && channel_index >= nch) { status = -50; break; }
             br.pos += 4;                                                        // element instance tag
             if (br.get(12) != 0) { status = -50; break; }                       // :633
             const uint32_t hb = br.get(4);
             const uint32_t partial = hb >> 3;
-            uint32_t bytes_shifted = (hb >> 1) & 3u;
+            const uint32_t bytes_shifted = (hb >> 1) & 3u;
             if (bytes_shifted == 3) { status = -50; break; }                    // :641
             const uint32_t escape = hb & 1u;
-            const uint32_t chan_bits = DEPTH - bytes_shifted * 8;
             if (partial) { n = br.get(16) << 16; n |= br.get(16); }             // :650-654
             if (n > slot_samples) { status = -50; break; }
-            const bool in_range = channel_index < nch;
-            MonoOut<DEPTH> out;
-            out.base = out_base + (size_t)(in_range ? channel_index : 0) * bps;
-            out.stride = stride;
-            out.shift = 0;
-            if (!in_range) { status = -50; break; }
+            DecChanMeta mu;
+            mu.n = n; mu.shift_pos = 0; mu.kind = pair ? CH_PAIR_U : CH_MONO; mu.shift = 0; mu.mix_res = 0; mu.mix_bits = 0;
+            ScratchOut ou, ov;
+            ou.dst = tile0 + (size_t)channel_index * F * 32u;
+            ov.dst = ou.dst + (size_t)F * 32u;
             if (!escape) {
-                br.pos += 16;                                                   // mixBits, mixRes
+                const uint32_t chan_bits = DEPTH - bytes_shifted * 8 + (pair ? 1u : 0u);
+                mu.mix_bits = (uint8_t)br.get(8);
+                mu.mix_res = (int8_t)br.get(8);
                 read_chan_header(br, hu);
-                if (bytes_shifted) {                                            // :675-679
-                    out.shift = bytes_shifted * 8;
-                    out.sr = br;
-                    br.pos += out.shift * n;
+                if (pair) read_chan_header(br, hv);
+                if (bytes_shifted) {                                            // :675-679, :818-822
+                    mu.shift = (uint8_t)(bytes_shifted * 8);
+                    mu.shift_pos = br.pos;
+                    br.pos += mu.shift * (pair ? 2u : 1u) * n;
                 }
-                status = decode_channel(br, cap_bits, A, n, chan_bits, hu, out);
+                status = decode_channel(br, cap_bits, A, n, chan_bits, hu, ou);
+                if (status == 0 && pair) status = decode_channel(br, cap_bits, A, n, chan_bits, hv, ov);
             } else {
-                const uint32_t sh = 32u - chan_bits;                            // :697-727
-                for (uint32_t j = 0; j < n; j++) out(j, (int32_t)(br.get(chan_bits) << sh) >> sh);
-            }
-            channel_index += 1;
-        } else if (tag == ID_CPE) {
-            if (channel_index + 2 > nch) break;                                 // :759-760
-            br.pos += 4;
-            if (br.get(12) != 0) { status = -50; break; }
-            const uint32_t hb = br.get(4);
-            const uint32_t partial = hb >> 3;
-            const uint32_t bytes_shifted = (hb >> 1) & 3u;
-            if (bytes_shifted == 3) { status = -50; break; }
-            const uint32_t escape = hb & 1u;
-            const uint32_t chan_bits = DEPTH - bytes_shifted * 8 + 1;
-            if (partial) { n = br.get(16) << 16; n |= br.get(16); }
-            if (n > slot_samples) { status = -50; break; }
-            uint8_t *eb = out_base + (size_t)channel_index * bps;
-            PairOut<DEPTH> pout;
-            pout.base = eb; pout.stride = stride; pout.shift = 0; pout.mix_res = 0; pout.mix_bits = 0;
-            if (!escape) {
-                pout.mix_bits = br.get(8);
-                pout.mix_res = (int32_t)(int8_t)br.get(8);
-                read_chan_header(br, hu);
-                read_chan_header(br, hv);
-                if (bytes_shifted) {                                            // :818-822
-                    pout.shift = bytes_shifted * 8;
-                    pout.sr = br;
-                    br.pos += pout.shift * 2 * n;
-                }
-                ParkOut<DEPTH> park;
-                park.base = eb; park.stride = stride;
-                status = decode_channel(br, cap_bits, A, n, chan_bits, hu, park);
-                if (status) break;
-                status = decode_channel(br, cap_bits, A, n, chan_bits, hv, pout);
-            } else {
-                const uint32_t sh = 32u - DEPTH;                                // :856-896
+                // uncompressed element (:697-727, :856-896): raw samples, pairs interleaved
+                const uint32_t sh = 32u - DEPTH;
                 for (uint32_t j = 0; j < n; j++) {
-                    const int32_t l = (int32_t)(br.get(DEPTH) << sh) >> sh;
-                    const int32_t r = (int32_t)(br.get(DEPTH) << sh) >> sh;
-                    uint8_t *p = eb + (size_t)j * stride;
-                    store_sample<DEPTH>(p, l);
-                    store_sample<DEPTH>(p + bps, r);
+                    ou(j, (int32_t)(br.get(DEPTH) << sh) >> sh);
+                    if (pair) ov(j, (int32_t)(br.get(DEPTH) << sh) >> sh);
                 }
             }
-            channel_index += 2;
+            if (status) break;
+            meta[channel_index] = mu;
+            if (pair) { mu.kind = CH_PAIR_V; meta[channel_index + 1] = mu; }
+            channel_index += pair ? 2u : 1u;
         } else if (tag == ID_CCE || tag == ID_PCE) {
             status = -50;                                                       // :932-939
-        } else if (tag == ID_DSE) {
+        } else if (tag == ID_DSE) {                                             // :1033-1059
             br.pos += 4;
             const uint32_t align = br.get(1);
             uint32_t count = br.get(8);
@@ -340,7 +326,7 @@ __global__ void __launch_bounds__(128) dec_packet_kernel(DecArgs A)
             if (align && (br.pos & 7u)) br.pos += 8u - (br.pos & 7u);
             br.pos += count * 8;
             if ((br.pos >> 3) > size) status = -50;
-        } else if (tag == ID_FIL) {
+        } else if (tag == ID_FIL) {                                             // :1012-1027
             int32_t count = (int32_t)br.get(4);
             if (count == 15) count += (int32_t)br.get(8) - 1;
             br.pos += (uint32_t)count * 8;
@@ -350,13 +336,76 @@ __global__ void __launch_bounds__(128) dec_packet_kernel(DecArgs A)
         }
         if (channel_index >= nch) break;                                        // :966-967
     }
-    // channels that never arrived are zero-filled (:972-998)
-    if (status == 0) {
-        for (; channel_index < nch; channel_index++)
-            for (uint32_t j = 0; j < slot_samples; j++)
-                store_sample<DEPTH>(out_base + ((size_t)j * nch + channel_index) * bps, 0);
-    }
     A.pkt_status[pkt] = status;
+}
+
+// grid: x = 32-sample tiles of a frame, y = groups of 32 packets (permuted order), z = channel
+template <int DEPTH>
+__global__ void __launch_bounds__(256) dec_output_kernel(DecArgs A)
+{
+    __shared__ int32_t su[32][33], sv[32][33];
+    constexpr uint32_t bps = DepthTraits<DEPTH>::kBytes;
+    const uint32_t nch = A.num_channels, F = A.frame_length;
+    const uint32_t group = blockIdx.y, c = blockIdx.z, j0 = blockIdx.x * 32u;
+    const uint32_t tx = threadIdx.x, ty = threadIdx.y;
+    const uint32_t stride = nch * bps;
+
+    // does any packet of the group need this channel slot written from here? (CH_PAIR_V is written by its U)
+    const uint32_t my_slot = group * 32u + tx;
+    uint32_t kind_x = CH_PAIR_V;
+    if (my_slot < A.num_packets && ty == 0) {
+        const DecChanMeta &m = A.chan_meta[(size_t)A.perm[my_slot] * nch + c];
+        kind_x = (j0 < m.n) ? m.kind : (uint32_t)CH_PAIR_V;
+    }
+    const int any = __syncthreads_or(kind_x != CH_PAIR_V);
+    if (!any) return;
+
+    const int32_t *tile_u = A.chan_scratch + ((size_t)(group * nch + c) * F) * 32u;
+    const int32_t *tile_v = tile_u + (size_t)F * 32u;
+    const bool have_v = (c + 1 < nch);
+    for (uint32_t r = ty; r < 32; r += 8) {
+        const uint32_t j = j0 + r;
+        su[r][tx] = j < F ? tile_u[(size_t)j * 32u + tx] : 0;
+        sv[r][tx] = (have_v && j < F) ? tile_v[(size_t)j * 32u + tx] : 0;
+    }
+    __syncthreads();
+
+    const uint32_t j = j0 + tx;
+    for (uint32_t pr = ty; pr < 32; pr += 8) {
+        const uint32_t slot = group * 32u + pr;
+        if (slot >= A.num_packets) break;
+        const uint32_t pkt = A.perm[slot];
+        const DecChanMeta m = A.chan_meta[(size_t)pkt * nch + c];
+        if (j >= m.n || m.kind == CH_PAIR_V) continue;
+        uint8_t *out = A.pcm_out + (A.out_frame[pkt] + j) * stride + (size_t)c * bps;
+        int32_t l = su[tx][pr];
+        if (m.kind == CH_ZERO) {
+            store_sample<DEPTH>(out, 0);
+            continue;
+        }
+        BitPeek bp;
+        if (m.shift) bp.start(A.packets + A.pkt_off[pkt], A.pkt_size[pkt]);
+        if (m.kind == CH_MONO) {
+            if (m.shift) l = (int32_t)(((uint32_t)l << m.shift) | bp.bits_at(m.shift_pos + j * m.shift, m.shift));   // :436-495
+            store_sample<DEPTH>(out, l);
+        } else {
+            const int32_t v = sv[tx][pr];
+            int32_t r;
+            if (m.mix_res != 0) {                       // :193-223
+                l = l + v - (((int32_t)m.mix_res * v) >> m.mix_bits);
+                r = l - v;
+            } else {
+                r = v;
+            }
+            if (m.shift) {                              // :282-383
+                const uint32_t both = bp.bits_at(m.shift_pos + j * 2u * m.shift, 2u * m.shift);
+                l = (int32_t)(((uint32_t)l << m.shift) | (both >> m.shift));
+                r = (int32_t)(((uint32_t)r << m.shift) | (both & ((1u << m.shift) - 1u)));
+            }
+            store_sample<DEPTH>(out, l);
+            store_sample<DEPTH>(out + bps, r);
+        }
+    }
 }
 
 }  // namespace alacb

@@ -267,19 +267,17 @@ __device__ __forceinline__ void ag_put(AgEnc &s, int32_t del, uint32_t bit_size,
     }
 }
 
-// ---- MSB-first bit reader over global memory (decoder) --------------------------------------------------
-// Reads 32-bit aligned words (byte-swapped) and keeps a 64-bit window; positions are in bits from
-// the packet's first byte.  Words past the packet's last byte read as zero.
-struct BitReader {
+// ---- MSB-first bit readers over global memory (decoder) -------------------------------------------------
+// Positions are in bits from the packet's first byte; words past the packet's last byte read as zero.
+
+// Stateless random-access reader: two aligned word loads per peek.  Used where reads are sparse
+// (header pre-pass) or naturally coalesced across a warp (shift bytes in the output kernel).
+struct BitPeek {
     const uint32_t *base;   // 4-byte aligned address at or before the packet
     uint32_t bias;          // bit offset of the packet's first bit inside base[0]
     uint32_t last_word;     // index of the last word holding packet bytes
-    uint32_t wi;            // index of w0
-    uint32_t w0, w1;
-    uint32_t pos;           // current bit position (packet relative)
-    bool valid;             // false for an empty packet: every read gives zero
-
-    __device__ __forceinline__ uint32_t word(uint32_t i) const { return (valid && i <= last_word) ? bswap32(__ldg(base + i)) : 0u; }
+    uint32_t pos;
+    bool valid;
     __device__ __forceinline__ void start(const uint8_t *packet, uint32_t nbytes)
     {
         const uintptr_t addr = reinterpret_cast<uintptr_t>(packet);
@@ -288,18 +286,90 @@ struct BitReader {
         valid = nbytes != 0;
         last_word = valid ? (bias + nbytes * 8u - 1u) >> 5 : 0u;
         pos = 0;
-        wi = 0;
-        w0 = word(0);
-        w1 = word(1);
+    }
+    __device__ __forceinline__ uint32_t word(uint32_t i) const { return (valid && i <= last_word) ? bswap32(__ldg(base + i)) : 0u; }
+    __device__ __forceinline__ uint32_t peek32_at(uint32_t p) const
+    {
+        const uint32_t abs_bit = bias + p;
+        const uint32_t i = abs_bit >> 5;
+        return __funnelshift_l(word(i + 1), word(i), abs_bit & 31u);
+    }
+    __device__ __forceinline__ uint32_t bits_at(uint32_t p, uint32_t nbits) const { return nbits ? peek32_at(p) >> (32u - nbits) : 0u; }
+    __device__ __forceinline__ uint32_t get(uint32_t nbits)
+    {
+        const uint32_t v = bits_at(pos, nbits);
+        pos += nbits;
+        return v;
+    }
+};
+
+// Sequential reader for the serial Golomb decode: the packet's words stream through a private
+// shared-memory ring filled by cp.async (LDGSTS) kAhead words in front of the read position, so the
+// global-load latency never sits on the decode's dependency chain and no register is ever the
+// target of a load in flight.  Ring slot s of this lane is ring[s * kRingStride] (bank == lane).
+constexpr uint32_t kRingSlots = 8;
+constexpr uint32_t kRingAhead = 6;
+constexpr uint32_t kRingStride = 128;     // lanes per CTA of the kernels that use BitReader
+
+__device__ __forceinline__ void cp_async_word(uint32_t *smem_dst, const uint32_t *gsrc)
+{
+    const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+struct BitReader {
+    const uint32_t *base;
+    uint32_t bias, last_word;
+    uint32_t *ring;         // this lane's column of the CTA's ring
+    uint32_t wi;            // word index of w0
+    uint32_t w0, w1, w2;    // byte-swapped words wi, wi+1, wi+2
+    uint32_t pos;
+    bool valid;
+
+    __device__ __forceinline__ void issue(uint32_t i)
+    {
+        uint32_t *dst = ring + (i & (kRingSlots - 1u)) * kRingStride;
+        if (valid && i <= last_word) cp_async_word(dst, base + i);
+        else *dst = 0u;
+        cp_async_commit();
+    }
+    __device__ __forceinline__ uint32_t slot(uint32_t i) const { return bswap32(ring[(i & (kRingSlots - 1u)) * kRingStride]); }
+    __device__ __forceinline__ void fill(uint32_t i)
+    {
+        wi = i;
+#pragma unroll
+        for (uint32_t d = 0; d <= kRingAhead; d++) issue(i + d);
+        cp_async_wait<kRingAhead - 2>();        // all but the 4 newest requests done: words i, i+1, i+2 are in
+        w0 = slot(i); w1 = slot(i + 1); w2 = slot(i + 2);
+    }
+    __device__ __forceinline__ void advance()
+    {
+        wi++;
+        w0 = w1; w1 = w2;
+        issue(wi + kRingAhead);                 // reuses the slot of word wi - 2
+        cp_async_wait<kRingAhead - 2>();        // word wi + 2 is in
+        w2 = slot(wi + 2);
+    }
+    __device__ __forceinline__ void start(const uint8_t *packet, uint32_t nbytes, uint32_t *ring_column)
+    {
+        const uintptr_t addr = reinterpret_cast<uintptr_t>(packet);
+        base = reinterpret_cast<const uint32_t *>(addr & ~(uintptr_t)3);
+        bias = (uint32_t)(addr & 3u) * 8u;
+        valid = nbytes != 0;
+        last_word = valid ? (bias + nbytes * 8u - 1u) >> 5 : 0u;
+        ring = ring_column;
+        pos = 0;
+        fill(0);
     }
     __device__ __forceinline__ uint32_t peek32_at(uint32_t p)
     {
         const uint32_t abs_bit = bias + p;
         const uint32_t i = abs_bit >> 5;
         if (i != wi) {
-            if (i == wi + 1) { w0 = w1; w1 = word(i + 1); }
-            else { w0 = word(i); w1 = word(i + 1); }
-            wi = i;
+            if (i - wi <= 2u) { while (wi != i) advance(); }
+            else fill(i);
         }
         return __funnelshift_l(w1, w0, abs_bit & 31u);
     }

@@ -51,7 +51,7 @@ struct alac_b200_engine {
     // encode
     DevBuf pcm, pkt_frame, pkt_samples, seg_first, seg_count, seg_stream, recs, scratch, sizes, offsets, out, state, counters;
     // decode
-    DevBuf d_packets, d_sizes, d_pkt_off, d_pkt_samples, d_out_frame, d_status, d_pcm;
+    DevBuf d_packets, d_sizes, d_pkt_off, d_pkt_samples, d_out_frame, d_status, d_pcm, d_class, d_rank, d_perm, d_chan, d_meta;
     uint32_t launches = 0;
     // per-kernel timers: (start, stop) event pairs, grown on demand, reused across calls
     std::vector<cudaEvent_t> timers;
@@ -174,7 +174,7 @@ void alac_b200_engine_destroy(alac_b200_engine *e)
     cudaStreamSynchronize(e->stream);
     DevBuf *bufs[] = {&e->pcm, &e->pkt_frame, &e->pkt_samples, &e->seg_first, &e->seg_count, &e->seg_stream, &e->recs,
                       &e->scratch, &e->sizes, &e->offsets, &e->out, &e->state, &e->counters, &e->d_packets, &e->d_sizes,
-                      &e->d_pkt_off, &e->d_pkt_samples, &e->d_out_frame, &e->d_status, &e->d_pcm};
+                      &e->d_pkt_off, &e->d_pkt_samples, &e->d_out_frame, &e->d_status, &e->d_pcm, &e->d_class, &e->d_rank, &e->d_perm, &e->d_chan, &e->d_meta};
     for (DevBuf *b : bufs) b->release();
     for (auto &ev : e->ev)
         if (ev) cudaEventDestroy(ev);
@@ -551,6 +551,12 @@ extern "C" int32_t alac_b200_decode(alac_b200_engine *e, const void *cookie, uin
     CU_CHECK(e, e->d_pkt_samples.reserve((size_t)P * 4));
     CU_CHECK(e, e->d_out_frame.reserve(((size_t)P + 1) * 8));
     CU_CHECK(e, e->d_status.reserve((size_t)P * 4));
+    CU_CHECK(e, e->d_class.reserve((size_t)P * 4));
+    CU_CHECK(e, e->d_rank.reserve((size_t)P * 4));
+    CU_CHECK(e, e->d_perm.reserve((size_t)P * 4));
+    const uint32_t groups = (P + 31) / 32;
+    CU_CHECK(e, e->d_chan.reserve((size_t)groups * 32 * nch * frame_length * 4));
+    CU_CHECK(e, e->d_meta.reserve((size_t)P * nch * sizeof(DecChanMeta)));
     CU_CHECK(e, e->counters.reserve(64));
 
     CU_CHECK(e, cudaEventRecord(e->ev[0], st));
@@ -592,11 +598,19 @@ extern "C" int32_t alac_b200_decode(alac_b200_engine *e, const void *cookie, uin
     A.out_frame = e->d_out_frame.as<uint64_t>();
     A.pkt_samples = e->d_pkt_samples.as<uint32_t>();
     A.pkt_status = e->d_status.as<int32_t>();
+    A.pkt_class = e->d_class.as<uint32_t>();
+    A.pkt_rank = e->d_rank.as<uint32_t>();
+    A.class_count = e->counters.as<uint32_t>();
+    A.perm = e->d_perm.as<uint32_t>();
+    A.chan_scratch = e->d_chan.as<int32_t>();
+    A.chan_meta = e->d_meta.as<DecChanMeta>();
+    CU_CHECK(e, cudaMemsetAsync(e->counters.p, 0, 64, st));
 
     scan_u32_to_u64_kernel<<<1, 1024, 0, st>>>(d_sizes, e->d_pkt_off.as<uint64_t>(), P, nullptr, 0);
     dec_header_kernel<<<(P + 127) / 128, 128, 0, st>>>(A);
+    dec_perm_kernel<<<(P + 127) / 128, 128, 0, st>>>(A);
     scan_u32_to_u64_kernel<<<1, 1024, 0, st>>>(A.pkt_samples, e->d_out_frame.as<uint64_t>(), P, nullptr, 0);
-    e->launches += 3;
+    e->launches += 4;
     // the output capacity must be known to hold before the decode kernel writes
     uint64_t total_frames = 0;
     CU_CHECK(e, cudaMemcpyAsync(&total_frames, e->d_out_frame.as<uint64_t>() + P, 8, cudaMemcpyDeviceToHost, st));
@@ -604,13 +618,15 @@ extern "C" int32_t alac_b200_decode(alac_b200_engine *e, const void *cookie, uin
     if (total_frames * bpf > pcm_cap) { e->err = "pcm capacity exceeded"; return ALAC_B200_PARAM_ERROR; }
 
     cudaEvent_t t_dec0 = e->timer();
+    const dim3 ogrid((frame_length + 31) / 32, groups, nch), oblock(32, 8);
     switch (depth) {
-    case 16: dec_packet_kernel<16><<<(P + 127) / 128, 128, 0, st>>>(A); break;
-    case 20: dec_packet_kernel<20><<<(P + 127) / 128, 128, 0, st>>>(A); break;
-    case 24: dec_packet_kernel<24><<<(P + 127) / 128, 128, 0, st>>>(A); break;
-    default: dec_packet_kernel<32><<<(P + 127) / 128, 128, 0, st>>>(A); break;
+    case 16: dec_lane_kernel<16><<<(P + kRingStride - 1) / kRingStride, kRingStride, 0, st>>>(A); dec_output_kernel<16><<<ogrid, oblock, 0, st>>>(A); break;
+    case 20: dec_lane_kernel<20><<<(P + kRingStride - 1) / kRingStride, kRingStride, 0, st>>>(A); dec_output_kernel<20><<<ogrid, oblock, 0, st>>>(A); break;
+    case 24: dec_lane_kernel<24><<<(P + kRingStride - 1) / kRingStride, kRingStride, 0, st>>>(A); dec_output_kernel<24><<<ogrid, oblock, 0, st>>>(A); break;
+    default: dec_lane_kernel<32><<<(P + kRingStride - 1) / kRingStride, kRingStride, 0, st>>>(A); dec_output_kernel<32><<<ogrid, oblock, 0, st>>>(A); break;
     }
     cudaEvent_t t_dec1 = e->timer();
+    e->launches += 2;
     e->launches++;
     CU_CHECK(e, cudaGetLastError());
     CU_CHECK(e, cudaEventRecord(e->ev[2], st));

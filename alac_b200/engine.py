@@ -31,7 +31,8 @@ class AlacError(RuntimeError):
 
 
 def library_path() -> str:
-    return os.path.join(_HERE, "csrc", _LIB_NAME)
+    # ALAC_B200_LIB: developer override used to A/B-test kernel variants (still a CUDA build of the same ABI)
+    return os.environ.get("ALAC_B200_LIB") or os.path.join(_HERE, "csrc", _LIB_NAME)
 
 
 class _EncConfig(C.Structure):

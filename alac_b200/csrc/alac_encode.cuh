@@ -194,19 +194,26 @@ __device__ __forceinline__ void init_coefs_row(int32_t *a, int n)
     a[2] = (-2 * 512) >> 4;
 }
 
-constexpr int kSearchThreads = 128;
+// 128 chain lanes + one spare warp: the spare warp owns no chain; it only takes final-pass jobs so that
+// the 4-tap and the 8-tap jobs can each start on a warp boundary and no warp ever runs both loops.
+constexpr int kChainThreads = 128;
+#ifndef ALAC_SPARE_WARPS
+#define ALAC_SPARE_WARPS 1
+#endif
+constexpr int kSearchThreads = kChainThreads + 32 * ALAC_SPARE_WARPS;
 
 // What the final pass (stage C) of one channel needs; lets any lane of the CTA run it.
 struct FinalJob {
     const uint8_t *base;    // sample-frame 0 of the packet, first channel of the element
     uint32_t *slab;         // Golomb stream destination
     int32_t coef[8];        // the selected coefficient row (in: after the search, out: after the pass)
-    uint32_t n;             // in: samples in the frame; out: Golomb bits produced
+    uint32_t *bits_out;     // where the pass reports its Golomb bit count (ElemRec::bits_u / bits_v)
+    uint32_t n;             // samples in the frame
     uint32_t flags;         // bit 0: V channel, bits 1..3: mixRes
 };
 
 template <int DEPTH, bool STEREO, bool PACKED, bool WRAP>
-__global__ void __launch_bounds__(kSearchThreads)
+__global__ void __launch_bounds__(kSearchThreads, 5)
 enc_search_kernel(EncArgs A, uint32_t elems_of_kind, uint32_t kind_elem0 /* bitmask of element slots of this kind */)
 {
     // Stages A and B keep the U and V chains of a pair on adjacent lanes (they trade bit counts by
@@ -218,12 +225,13 @@ enc_search_kernel(EncArgs A, uint32_t elems_of_kind, uint32_t kind_elem0 /* bitm
     __shared__ uint32_t s_pn_max;
 
     constexpr uint32_t kLanesPerJob = STEREO ? 2 : 1;
-    const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t tid = blockIdx.x * kChainThreads + threadIdx.x;
     const uint32_t lane = threadIdx.x & 31u, wid = threadIdx.x >> 5;
     const uint32_t job = tid / kLanesPerJob;
     const bool is_v = STEREO && (tid & 1u);
     const uint32_t total_jobs = A.num_segments * elems_of_kind;
-    const bool in_range = job < total_jobs;         // lanes of a pair are both in or both out
+    // lanes of a pair are both in or both out; the spare warp(s) own no chain
+    const bool in_range = threadIdx.x < kChainThreads && job < total_jobs;
     const uint32_t pair_mask = STEREO ? (3u << (lane & ~1u)) : 0u;
 
     uint32_t slot = 0, seg = A.seg_base;
@@ -345,10 +353,22 @@ enc_search_kernel(EncArgs A, uint32_t elems_of_kind, uint32_t kind_elem0 /* bitm
 
         // header coefficients are the post-search, pre-final-pass values (:479-485)
         ElemRec *rec = A.recs + (size_t)(pkt - A.pkt_base) * A.lay.elems_per_packet + slot;
+        const uint32_t other_num = STEREO ? __shfl_xor_sync(0xffffffffu, num_mine, 1) : 0u;
         if (valid) {
             int16_t *hc = is_v ? rec->coef_v : rec->coef_u;
             if (num_mine == 4) { for (int k = 0; k < 4; k++) hc[k] = (int16_t)c4[k]; for (int k = 4; k < 8; k++) hc[k] = 0; }
             else { for (int k = 0; k < 8; k++) hc[k] = (int16_t)c8[k]; }
+            // the post-check and the element size are finished by enc_size_kernel once both bit counts exist
+            if (is_v) {
+                rec->bits_v = 0;
+            } else {
+                rec->escape = (uint8_t)do_escape;
+                rec->mix_res = (uint8_t)best_res;
+                rec->num_u = (uint8_t)num_mine;
+                rec->num_v = (uint8_t)other_num;
+                rec->bits_u = 0;
+                if (!STEREO) rec->bits_v = 0;
+            }
         }
 
         // ---- stage C: final predictor + Golomb pass over the whole frame (:507-531, :941-945),
@@ -365,18 +385,21 @@ enc_search_kernel(EncArgs A, uint32_t elems_of_kind, uint32_t kind_elem0 /* bitm
             n8 += s_cnt[w][1];
         }
         const uint32_t lt = (1u << lane) - 1u;
-        const uint32_t my_slot = key == 0 ? before4 + __popc(b4 & lt) : n4 + before8 + __popc(b8 & lt);
+        // 8-tap jobs start on the next warp boundary after the 4-tap jobs (fits thanks to the spare warp)
+        const uint32_t first8 = ALAC_SPARE_WARPS ? ((n4 + 31u) & ~31u) : n4;
+        const uint32_t my_slot = key == 0 ? before4 + __popc(b4 & lt) : first8 + before8 + __popc(b8 & lt);
         if (key < 2) {
             FinalJob &J = s_job[my_slot];
             J.base = base;
             J.slab = slab;
+            J.bits_out = is_v ? &rec->bits_v : &rec->bits_u;
             J.n = n;
             J.flags = (is_v ? 1u : 0u) | (best_res << 1);
             if (key == 0) { for (int k = 0; k < 4; k++) J.coef[k] = c4[k]; }
             else { for (int k = 0; k < 8; k++) J.coef[k] = c8[k]; }
         }
         __syncthreads();
-        if (threadIdx.x < n4 + n8) {
+        if (threadIdx.x < n4 || (threadIdx.x >= first8 && threadIdx.x < first8 + n8)) {
             FinalJob &J = s_job[threadIdx.x];
             MixSrc<DEPTH, STEREO, PACKED> fs;
             fs.base = J.base; fs.stride = stride; fs.is_v = (J.flags & 1u) != 0; fs.mix_res = (int32_t)(J.flags >> 1);
@@ -397,44 +420,18 @@ enc_search_kernel(EncArgs A, uint32_t elems_of_kind, uint32_t kind_elem0 /* bitm
                 for (int k = 0; k < 8; k++) J.coef[k] = a[k];
             }
             es.bits.finish();
-            J.n = es.ag.bits;
+            *J.bits_out = es.ag.bits;
         }
-        __syncthreads();
-        uint32_t my_bits = 0;
-        if (key < 2) {
-            const FinalJob &J = s_job[my_slot];
-            my_bits = J.n;
-            if (key == 0) { for (int k = 0; k < 4; k++) c4[k] = J.coef[k]; }
-            else { for (int k = 0; k < 8; k++) c8[k] = J.coef[k]; }
+        // the adapted coefficients only matter if another frame of the segment follows or the state is exported
+        if (pi + 1 < pn_max || A.state != nullptr) {
+            __syncthreads();
+            if (key < 2) {
+                const FinalJob &J = s_job[my_slot];
+                if (key == 0) { for (int k = 0; k < 4; k++) c4[k] = J.coef[k]; }
+                else { for (int k = 0; k < 8; k++) c8[k] = J.coef[k]; }
+            }
         }
 
-        // sizes, post-check (:537-543, :952-958; fast mode :703-725)
-        uint32_t other_bits = 0, other_num = 0;
-        if (STEREO) {
-            other_bits = __shfl_xor_sync(0xffffffffu, my_bits, 1);
-            other_num = __shfl_xor_sync(0xffffffffu, num_mine, 1);
-        }
-        const uint32_t escape_bits = n * DEPTH * kLanesPerJob + (partial ? 32u : 0u) + 16;
-        uint32_t body_bits;     // element bits after tag+instance when compressed
-        if (STEREO) body_bits = 12 + 4 + (partial ? 32u : 0u) + 16 + (16 + 16 * num_mine) + (16 + 16 * other_num) + n * shift * 2 + my_bits + other_bits;
-        else        body_bits = 12 + 4 + (partial ? 32u : 0u) + 16 + (16 + 16 * num_mine) + n * shift + my_bits;
-        if (!do_escape) {
-            if (fast) {
-                uint32_t min_bits = (my_bits + num_mine * 16) + (other_bits + other_num * 16) + 64 + (partial ? 32u : 0u);
-                if (shift) min_bits += n * shift * 2;
-                if (min_bits >= escape_bits) do_escape = 2;
-            }
-            if (!do_escape && body_bits >= escape_bits) do_escape = 2;
-        }
-        if (valid && !is_v) {
-            rec->escape = (uint8_t)do_escape;
-            rec->mix_res = (uint8_t)best_res;
-            rec->bits_u = my_bits;
-            rec->bits_v = other_bits;
-            rec->num_u = (uint8_t)num_mine;
-            rec->num_v = (uint8_t)other_num;
-            rec->elem_bits = 7 + (do_escape ? (12 + 4 + (partial ? 32u : 0u) + n * DEPTH * kLanesPerJob) : body_bits);
-        }
     }
 
     if (st && (seg_info & 0x40000000u)) {
@@ -445,17 +442,38 @@ enc_search_kernel(EncArgs A, uint32_t elems_of_kind, uint32_t kind_elem0 /* bitm
 }
 
 // ---- packet sizes ------------------------------------------------------------------------------------
-__global__ void enc_size_kernel(const ElemRec *recs, uint32_t elems_per_packet, uint32_t num_packets,
-                                uint32_t *sizes, unsigned long long *escapes)
+// Finishes each element record (post-check of codec/ALACEncoder.cu:537-543 / :952-958, fast mode
+// :703-725: a compressed element that is not smaller than the escape form is sent as escape) and
+// sums the element bits of a packet.
+__global__ void enc_size_kernel(ElemRec *recs, EncLayout lay, uint32_t depth, const uint32_t *pkt_samples,
+                                uint32_t num_packets, uint32_t *sizes, unsigned long long *escapes)
 {
     const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= num_packets) return;
+    const uint32_t n = pkt_samples[p];
+    const uint32_t partial = (n != lay.frame_size) ? 32u : 0u;
+    const uint32_t shift = depth == 32 ? 16u : depth == 24 ? 8u : 0u;
     uint32_t bits = 3;      // ID_END, codec/ALACEncoder.cu:1036
     uint32_t esc = 0;
-    for (uint32_t e = 0; e < elems_per_packet; e++) {
-        const ElemRec &r = recs[(size_t)p * elems_per_packet + e];
+    for (uint32_t e = 0; e < lay.elems_per_packet; e++) {
+        ElemRec &r = recs[(size_t)p * lay.elems_per_packet + e];
+        const bool stereo = (lay.elem_tag[e] == ID_CPE);
+        const uint32_t nch = stereo ? 2u : 1u;
+        const uint32_t escape_bits = n * depth * nch + partial + 16;
+        const uint32_t body_bits = 12 + 4 + partial + 16 + (16 + 16 * r.num_u) + (stereo ? 16 + 16 * r.num_v : 0u) +
+                                   n * shift * nch + r.bits_u + (stereo ? r.bits_v : 0u);
+        uint32_t do_escape = r.escape;
+        if (!do_escape) {
+            if (stereo && lay.fast_mode) {
+                const uint32_t min_bits = (r.bits_u + r.num_u * 16) + (r.bits_v + r.num_v * 16) + 64 + partial + n * shift * 2;
+                if (min_bits >= escape_bits) do_escape = 2;
+            }
+            if (!do_escape && body_bits >= escape_bits) do_escape = 2;
+        }
+        r.escape = (uint8_t)do_escape;
+        r.elem_bits = 7 + (do_escape ? (12 + 4 + partial + n * depth * nch) : body_bits);
         bits += r.elem_bits;
-        esc += r.escape ? 1u : 0u;
+        esc += do_escape ? 1u : 0u;
     }
     sizes[p] = (bits + 7) >> 3;     // byte-align, :1039
     if (esc) atomicAdd(escapes, (unsigned long long)esc);

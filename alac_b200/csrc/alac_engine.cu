@@ -268,13 +268,13 @@ static void launch_search_v(alac_b200_engine *e, const EncArgs &A, uint32_t mono
     if (pairs) {
         const uint64_t threads = (uint64_t)A.num_segments * pairs * 2;
         enc_search_kernel<DEPTH, true, PACKED, WRAP>
-            <<<(uint32_t)((threads + kSearchThreads - 1) / kSearchThreads), kSearchThreads, 0, e->stream>>>(A, pairs, pair_mask);
+            <<<(uint32_t)((threads + kChainThreads - 1) / kChainThreads), kSearchThreads, 0, e->stream>>>(A, pairs, pair_mask);
         e->launches++;
     }
     if (monos) {
         const uint64_t threads = (uint64_t)A.num_segments * monos;
         enc_search_kernel<DEPTH, false, false, WRAP>
-            <<<(uint32_t)((threads + kSearchThreads - 1) / kSearchThreads), kSearchThreads, 0, e->stream>>>(A, monos, mono_mask);
+            <<<(uint32_t)((threads + kChainThreads - 1) / kChainThreads), kSearchThreads, 0, e->stream>>>(A, monos, mono_mask);
         e->launches++;
     }
 }
@@ -449,7 +449,7 @@ extern "C" int32_t alac_b200_encode(alac_b200_engine *e, const alac_b200_enc_con
         default: launch_search<32>(e, A, mono_mask, pair_mask, packed, wrap); break;
         }
         t_search.push_back(e->timer());
-        enc_size_kernel<<<(uint32_t)((cnt + 255) / 256), 256, 0, st>>>(A.recs, L.elems_per_packet, (uint32_t)cnt,
+        enc_size_kernel<<<(uint32_t)((cnt + 255) / 256), 256, 0, st>>>(A.recs, L, cfg->bit_depth, A.pkt_samples + p0, (uint32_t)cnt,
                                                                      e->sizes.as<uint32_t>() + p0, d_escapes);
         scan_u32_to_u64_kernel<<<1, 1024, 0, st>>>(e->sizes.as<uint32_t>() + p0, e->offsets.as<uint64_t>() + p0, cnt, d_max,
                                                    first_chunk ? 0 : 1);

@@ -23,7 +23,8 @@ struct DecArgs {
     const uint8_t *packets;
     const uint64_t *pkt_off;      // byte offset of each packet (exclusive scan of sizes)
     const uint32_t *pkt_size;
-    uint32_t num_packets;
+    uint32_t pkt_base;            // chunk: first packet of this launch (perm / scratch slots are chunk-relative)
+    uint32_t num_packets;         // chunk: packets in this launch
     uint32_t frame_length, pb, mb, kb, num_channels;
     uint8_t *pcm_out;
     const uint64_t *out_frame;    // first output sample-frame of each packet (exclusive scan)
@@ -51,8 +52,9 @@ constexpr uint32_t kDecClasses = 16;
 // walk element tags until the first SCE/LFE/CPE and return its sample count
 __global__ void dec_header_kernel(DecArgs A)
 {
-    const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= A.num_packets) return;
+    const uint32_t local = blockIdx.x * blockDim.x + threadIdx.x;
+    if (local >= A.num_packets) return;
+    const uint32_t p = A.pkt_base + local;
     const uint32_t size = A.pkt_size[p];
     BitPeek br;
     br.start(A.packets + A.pkt_off[p], size);
@@ -97,12 +99,13 @@ __global__ void dec_header_kernel(DecArgs A)
 // perm[first slot of the packet's class + its rank inside the class] = packet
 __global__ void dec_perm_kernel(DecArgs A)
 {
-    const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= A.num_packets) return;
+    const uint32_t local = blockIdx.x * blockDim.x + threadIdx.x;
+    if (local >= A.num_packets) return;
+    const uint32_t p = A.pkt_base + local;
     const uint32_t cls = A.pkt_class[p];
     uint32_t first = 0;
     for (uint32_t c = 0; c < cls; c++) first += A.class_count[c];
-    A.perm[first + A.pkt_rank[p]] = p;
+    A.perm[A.pkt_base + first + A.pkt_rank[p]] = p;
 }
 
 struct ChanHeader {
@@ -249,7 +252,7 @@ __global__ void __launch_bounds__(kRingStride) dec_lane_kernel(DecArgs A)
     __shared__ uint32_t s_ring[kRingSlots][kRingStride];
     const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
     if (tid >= A.num_packets) return;
-    const uint32_t pkt = A.perm[tid];
+    const uint32_t pkt = A.perm[A.pkt_base + tid];
     const uint32_t nch = A.num_channels;
     const uint32_t size = A.pkt_size[pkt];
     const uint32_t cap_bits = size * 8u;
@@ -354,7 +357,7 @@ __global__ void __launch_bounds__(256) dec_output_kernel(DecArgs A)
     const uint32_t my_slot = group * 32u + tx;
     uint32_t kind_x = CH_PAIR_V;
     if (my_slot < A.num_packets && ty == 0) {
-        const DecChanMeta &m = A.chan_meta[(size_t)A.perm[my_slot] * nch + c];
+        const DecChanMeta &m = A.chan_meta[(size_t)A.perm[A.pkt_base + my_slot] * nch + c];
         kind_x = (j0 < m.n) ? m.kind : (uint32_t)CH_PAIR_V;
     }
     const int any = __syncthreads_or(kind_x != CH_PAIR_V);
@@ -374,7 +377,7 @@ __global__ void __launch_bounds__(256) dec_output_kernel(DecArgs A)
     for (uint32_t pr = ty; pr < 32; pr += 8) {
         const uint32_t slot = group * 32u + pr;
         if (slot >= A.num_packets) break;
-        const uint32_t pkt = A.perm[slot];
+        const uint32_t pkt = A.perm[A.pkt_base + slot];
         const DecChanMeta m = A.chan_meta[(size_t)pkt * nch + c];
         if (j >= m.n || m.kind == CH_PAIR_V) continue;
         uint8_t *out = A.pcm_out + (A.out_frame[pkt] + j) * stride + (size_t)c * bps;

@@ -9,6 +9,7 @@
 
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -42,10 +43,14 @@ struct DevBuf {
 
 }  // namespace
 
+constexpr size_t kMaxChunks = 4096;
+
 struct alac_b200_engine {
     int device = 0;
     cudaStream_t stream = nullptr;
     cudaStream_t own_stream = nullptr;
+    cudaStream_t copy_in = nullptr, copy_out = nullptr;     // transfer streams of the host-buffer pipeline
+    uint64_t *h_totals = nullptr;                           // pinned: running byte / frame totals per chunk
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     std::string err;
     // encode
@@ -56,6 +61,17 @@ struct alac_b200_engine {
     // per-kernel timers: (start, stop) event pairs, grown on demand, reused across calls
     std::vector<cudaEvent_t> timers;
     size_t timers_used = 0;
+    cudaEvent_t event_on(cudaStream_t s)
+    {
+        if (timers_used == timers.size()) {
+            cudaEvent_t ev = nullptr;
+            cudaEventCreate(&ev);
+            timers.push_back(ev);
+        }
+        cudaEvent_t ev = timers[timers_used++];
+        cudaEventRecord(ev, s);
+        return ev;
+    }
     cudaEvent_t timer()
     {
         if (timers_used == timers.size()) {
@@ -92,6 +108,17 @@ static const uint32_t kChannelMaps[8] = {
 // codec/ALACAudioTypes.h:115-125
 static const uint32_t kLayoutTags[8] = {(100u << 16) | 1, (101u << 16) | 2, (113u << 16) | 3, (116u << 16) | 4,
                                         (120u << 16) | 5, (124u << 16) | 6, (142u << 16) | 7, (127u << 16) | 8};
+
+// how many chunks the host-buffer pipeline cuts a call into (ALAC_B200_PIPELINE_CHUNKS overrides)
+static uint32_t pipeline_chunks()
+{
+    static const uint32_t n = [] {
+        const char *v = getenv("ALAC_B200_PIPELINE_CHUNKS");
+        const long k = v ? atol(v) : 2;
+        return (uint32_t)(k < 1 ? 1 : k > 64 ? 64 : k);
+    }();
+    return n;
+}
 
 static bool valid_depth(uint32_t d) { return d == 16 || d == 20 || d == 24 || d == 32; }
 static uint32_t bytes_per_sample(uint32_t d) { return d == 16 ? 2u : d == 32 ? 4u : 3u; }
@@ -157,6 +184,12 @@ int32_t alac_b200_engine_create(int32_t device, alac_b200_engine **out_engine)
         return ALAC_B200_CUDA_ERROR;
     }
     e->stream = e->own_stream;
+    if (cudaStreamCreateWithFlags(&e->copy_in, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&e->copy_out, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaHostAlloc(&e->h_totals, kMaxChunks * sizeof(uint64_t), cudaHostAllocDefault) != cudaSuccess) {
+        delete e;
+        return ALAC_B200_CUDA_ERROR;
+    }
     for (auto &ev : e->ev) {
         if (cudaEventCreate(&ev) != cudaSuccess) {
             delete e;
@@ -180,6 +213,9 @@ void alac_b200_engine_destroy(alac_b200_engine *e)
         if (ev) cudaEventDestroy(ev);
     for (auto &ev : e->timers) cudaEventDestroy(ev);
     if (e->own_stream) cudaStreamDestroy(e->own_stream);
+    if (e->copy_in) cudaStreamDestroy(e->copy_in);
+    if (e->copy_out) cudaStreamDestroy(e->copy_out);
+    if (e->h_totals) cudaFreeHost(e->h_totals);
     delete e;
 }
 
@@ -356,19 +392,35 @@ extern "C" int32_t alac_b200_encode(alac_b200_engine *e, const alac_b200_enc_con
     uint32_t mono_mask, pair_mask;
     build_layout(cfg, L, mono_mask, pair_mask);
 
-    // ---- device buffers ----
+    // ---- chunks ----
+    // Work is cut into chunks of whole segments.  A chunk bounds the scratch (<= 65,536 packets), and when
+    // host memory is involved the chunks form a 3-stage pipeline: H2D of chunk c+1 (copy-in stream) overlaps
+    // the kernels of chunk c (compute stream) and the D2H of chunk c-1's packets (copy-out stream).
     const uint32_t cap_words = F + 8;       // >= worst-case Golomb words per channel (<= 32 bits/sample incl. run codes)
-    // chunking bounds the scratch: at most kChunkPackets packets (whole segments) per search launch
-    const uint64_t kChunkPackets = 65536;
+    const bool in_host = pcm_mem != ALAC_B200_MEM_DEVICE, out_host = out_mem != ALAC_B200_MEM_DEVICE;
+    uint64_t chunk_target = 65536;
+    if (in_host || out_host) chunk_target = std::min<uint64_t>(65536, std::max<uint64_t>(2048, (P + pipeline_chunks() - 1) / pipeline_chunks()));
+    struct Chunk { uint32_t s0, s1, p0, cnt; uint64_t f_lo, f_hi; };
+    std::vector<Chunk> chunks;
     uint64_t max_chunk = 0;
-    {
-        uint64_t cur = 0;
-        for (uint32_t s = 0; s < S; s++) {
-            if (cur && cur + h_seg_count[s] > kChunkPackets) { max_chunk = std::max(max_chunk, cur); cur = 0; }
-            cur += h_seg_count[s];
+    for (uint32_t s0 = 0; s0 < S;) {
+        uint32_t s1 = s0;
+        uint64_t cnt = 0;
+        while (s1 < S && (cnt == 0 || cnt + h_seg_count[s1] <= chunk_target)) cnt += h_seg_count[s1++];
+        Chunk c;
+        c.s0 = s0; c.s1 = s1; c.p0 = h_seg_first[s0]; c.cnt = (uint32_t)cnt;
+        c.f_lo = ~0ull; c.f_hi = 0;
+        for (uint32_t p = c.p0; p < c.p0 + c.cnt; p++) {
+            c.f_lo = std::min(c.f_lo, h_pkt_frame[p]);
+            c.f_hi = std::max(c.f_hi, h_pkt_frame[p] + h_pkt_samples[p]);
         }
-        max_chunk = std::max(max_chunk, cur);
+        chunks.push_back(c);
+        max_chunk = std::max(max_chunk, cnt);
+        s0 = s1;
     }
+    if (chunks.size() > kMaxChunks) { e->err = "too many chunks"; return ALAC_B200_PARAM_ERROR; }
+
+    // ---- device buffers ----
     CU_CHECK(e, e->pkt_frame.reserve((size_t)P * 8));
     CU_CHECK(e, e->pkt_samples.reserve((size_t)P * 4));
     CU_CHECK(e, e->seg_first.reserve((size_t)S * 4));
@@ -379,16 +431,32 @@ extern "C" int32_t alac_b200_encode(alac_b200_engine *e, const alac_b200_enc_con
     CU_CHECK(e, e->sizes.reserve((size_t)P * 4));
     CU_CHECK(e, e->offsets.reserve(((size_t)P + 1) * 8));
     CU_CHECK(e, e->counters.reserve(64));
+    const uint8_t *d_pcm;
+    if (in_host) {
+        CU_CHECK(e, e->pcm.reserve((size_t)(num_sample_frames * bpf) + 64));
+        d_pcm = e->pcm.as<uint8_t>();
+    } else {
+        d_pcm = static_cast<const uint8_t *>(pcm);
+    }
+    uint8_t *d_out;
+    if (out_host) {
+        CU_CHECK(e, e->out.reserve((size_t)alac_b200_encode_bound(cfg, num_sample_frames, n_streams) + 64));
+        d_out = e->out.as<uint8_t>();
+    } else {
+        d_out = static_cast<uint8_t *>(packets_out);
+    }
 
     cudaStream_t st = e->stream;
     CU_CHECK(e, cudaEventRecord(e->ev[0], st));
-    const uint8_t *d_pcm;
-    if (pcm_mem == ALAC_B200_MEM_DEVICE) {
-        d_pcm = static_cast<const uint8_t *>(pcm);
-    } else {
-        CU_CHECK(e, e->pcm.reserve((size_t)(num_sample_frames * bpf) + 64));
-        CU_CHECK(e, cudaMemcpyAsync(e->pcm.p, pcm, (size_t)(num_sample_frames * bpf), cudaMemcpyHostToDevice, st));
-        d_pcm = e->pcm.as<uint8_t>();
+    // copy-in stream: PCM chunks, each followed by an event the compute stream waits on
+    std::vector<cudaEvent_t> h2d_done;
+    if (in_host) {
+        CU_CHECK(e, cudaStreamWaitEvent(e->copy_in, e->ev[0], 0));
+        for (const Chunk &c : chunks) {
+            CU_CHECK(e, cudaMemcpyAsync(e->pcm.as<uint8_t>() + c.f_lo * bpf, static_cast<const uint8_t *>(pcm) + c.f_lo * bpf,
+                                        (size_t)((c.f_hi - c.f_lo) * bpf), cudaMemcpyHostToDevice, e->copy_in));
+            h2d_done.push_back(e->event_on(e->copy_in));
+        }
     }
     CU_CHECK(e, cudaMemcpyAsync(e->pkt_frame.p, h_pkt_frame.data(), (size_t)P * 8, cudaMemcpyHostToDevice, st));
     CU_CHECK(e, cudaMemcpyAsync(e->pkt_samples.p, h_pkt_samples.data(), (size_t)P * 4, cudaMemcpyHostToDevice, st));
@@ -402,30 +470,19 @@ extern "C" int32_t alac_b200_encode(alac_b200_engine *e, const alac_b200_enc_con
         d_state = e->state.as<int16_t>();
     }
     CU_CHECK(e, cudaMemsetAsync(e->counters.p, 0, 64, st));
-    uint8_t *d_out;
-    if (out_mem == ALAC_B200_MEM_DEVICE) {
-        d_out = static_cast<uint8_t *>(packets_out);
-    } else {
-        CU_CHECK(e, e->out.reserve((size_t)alac_b200_encode_bound(cfg, num_sample_frames, n_streams) + 64));
-        d_out = e->out.as<uint8_t>();
-    }
     CU_CHECK(e, cudaEventRecord(e->ev[1], st));
 
-    // ---- kernels, chunk by chunk ----
+    // ---- kernels, chunk by chunk (compute stream) ----
     // coefficients move by at most 1 per predictor step and a frame runs < 2 * frame_size steps on a row:
     // starting from init_coefs (|a| <= 1216) the int16 range cannot be left within K frames if this holds
     const bool wrap = coef_state != nullptr || K == 0 || (uint64_t)K * 2u * F + 1216u > 32767u;
     const bool packed = cfg->channels == 2 && (reinterpret_cast<uintptr_t>(d_pcm) & 7u) == 0;
     unsigned long long *d_escapes = e->counters.as<unsigned long long>();
     uint32_t *d_max = reinterpret_cast<uint32_t *>(e->counters.as<uint8_t>() + 8);
-    uint32_t s0 = 0;
-    bool first_chunk = true;
-    while (s0 < S) {
-        uint32_t s1 = s0;
-        uint64_t cnt = 0;
-        while (s1 < S && (cnt == 0 || cnt + h_seg_count[s1] <= kChunkPackets)) cnt += h_seg_count[s1++];
-        const uint32_t p0 = h_seg_first[s0];
-
+    std::vector<cudaEvent_t> comp_done;
+    for (size_t ci = 0; ci < chunks.size(); ci++) {
+        const Chunk &c = chunks[ci];
+        if (in_host) CU_CHECK(e, cudaStreamWaitEvent(st, h2d_done[ci], 0));
         EncArgs A;
         A.pcm = d_pcm;
         A.pkt_frame = e->pkt_frame.as<uint64_t>();
@@ -433,9 +490,9 @@ extern "C" int32_t alac_b200_encode(alac_b200_engine *e, const alac_b200_enc_con
         A.seg_first = e->seg_first.as<uint32_t>();
         A.seg_count = e->seg_count.as<uint32_t>();
         A.seg_stream = e->seg_stream.as<uint32_t>();
-        A.seg_base = s0;
-        A.num_segments = s1 - s0;
-        A.pkt_base = p0;
+        A.seg_base = c.s0;
+        A.num_segments = c.s1 - c.s0;
+        A.pkt_base = c.p0;
         A.lay = L;
         A.recs = e->recs.as<ElemRec>();
         A.scratch = e->scratch.as<uint32_t>();
@@ -449,10 +506,10 @@ extern "C" int32_t alac_b200_encode(alac_b200_engine *e, const alac_b200_enc_con
         default: launch_search<32>(e, A, mono_mask, pair_mask, packed, wrap); break;
         }
         t_search.push_back(e->timer());
-        enc_size_kernel<<<(uint32_t)((cnt + 255) / 256), 256, 0, st>>>(A.recs, L, cfg->bit_depth, A.pkt_samples + p0, (uint32_t)cnt,
-                                                                     e->sizes.as<uint32_t>() + p0, d_escapes);
-        scan_u32_to_u64_kernel<<<1, 1024, 0, st>>>(e->sizes.as<uint32_t>() + p0, e->offsets.as<uint64_t>() + p0, cnt, d_max,
-                                                   first_chunk ? 0 : 1);
+        enc_size_kernel<<<(c.cnt + 255) / 256, 256, 0, st>>>(A.recs, L, cfg->bit_depth, A.pkt_samples + c.p0, c.cnt,
+                                                            e->sizes.as<uint32_t>() + c.p0, d_escapes);
+        scan_u32_to_u64_kernel<<<1, 1024, 0, st>>>(e->sizes.as<uint32_t>() + c.p0, e->offsets.as<uint64_t>() + c.p0, c.cnt, d_max,
+                                                   ci == 0 ? 0 : 1);
         e->launches += 2;
 
         AsmArgs B;
@@ -465,8 +522,8 @@ extern "C" int32_t alac_b200_encode(alac_b200_engine *e, const alac_b200_enc_con
         B.sizes = e->sizes.as<uint32_t>();
         B.offsets = e->offsets.as<uint64_t>();
         B.out = d_out;
-        B.pkt_base = p0;
-        B.num_packets = (uint32_t)cnt;
+        B.pkt_base = c.p0;
+        B.num_packets = c.cnt;
         B.lay = L;
         t_asm.push_back(e->timer());
         switch (cfg->bit_depth) {
@@ -476,31 +533,32 @@ extern "C" int32_t alac_b200_encode(alac_b200_engine *e, const alac_b200_enc_con
         default: launch_assemble<32>(e, B); break;
         }
         t_asm.push_back(e->timer());
-        first_chunk = false;
-        s0 = s1;
+        // running byte total after this chunk -> pinned host word; the host needs it to size the chunk's D2H
+        CU_CHECK(e, cudaMemcpyAsync(&e->h_totals[ci], e->offsets.as<uint64_t>() + c.p0 + c.cnt, 8, cudaMemcpyDeviceToHost, st));
+        comp_done.push_back(e->event_on(st));
     }
     CU_CHECK(e, cudaGetLastError());
     CU_CHECK(e, cudaEventRecord(e->ev[2], st));
 
-    // ---- results ----
-    uint64_t total = 0;
+    // ---- results (copy-out stream) ----
     unsigned long long h_counters[2] = {0, 0};
-    CU_CHECK(e, cudaMemcpyAsync(&total, e->offsets.as<uint64_t>() + P, 8, cudaMemcpyDeviceToHost, st));
-    CU_CHECK(e, cudaMemcpyAsync(h_counters, e->counters.p, 16, cudaMemcpyDeviceToHost, st));
-    if (out_mem == ALAC_B200_MEM_DEVICE) {
-        CU_CHECK(e, cudaMemcpyAsync(packet_sizes, e->sizes.p, (size_t)P * 4, cudaMemcpyDeviceToDevice, st));
-    } else {
-        CU_CHECK(e, cudaMemcpyAsync(packet_sizes, e->sizes.p, (size_t)P * 4, cudaMemcpyDeviceToHost, st));
+    uint64_t total = 0, copied = 0;
+    for (size_t ci = 0; ci < chunks.size(); ci++) {
+        CU_CHECK(e, cudaEventSynchronize(comp_done[ci]));       // all later GPU work is already queued
+        total = e->h_totals[ci];
+        if (out_host && total > copied) {
+            CU_CHECK(e, cudaMemcpyAsync(static_cast<uint8_t *>(packets_out) + copied, d_out + copied, (size_t)(total - copied),
+                                        cudaMemcpyDeviceToHost, e->copy_out));
+            copied = total;
+        }
     }
-    CU_CHECK(e, cudaStreamSynchronize(st));
-    if (total > packets_cap) { e->err = "output capacity exceeded"; return ALAC_B200_PARAM_ERROR; }
-    if (out_mem != ALAC_B200_MEM_DEVICE && total) {
-        CU_CHECK(e, cudaMemcpyAsync(packets_out, d_out, (size_t)total, cudaMemcpyDeviceToHost, st));
-    }
+    CU_CHECK(e, cudaMemcpyAsync(packet_sizes, e->sizes.p, (size_t)P * 4, out_host ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice, e->copy_out));
+    CU_CHECK(e, cudaMemcpyAsync(h_counters, e->counters.p, 16, cudaMemcpyDeviceToHost, e->copy_out));
     if (coef_state) {
-        CU_CHECK(e, cudaMemcpyAsync(coef_state, e->state.p, (size_t)n_streams * ALAC_B200_STATE_INT16S * 2, cudaMemcpyDeviceToHost, st));
+        CU_CHECK(e, cudaMemcpyAsync(coef_state, e->state.p, (size_t)n_streams * ALAC_B200_STATE_INT16S * 2, cudaMemcpyDeviceToHost, e->copy_out));
     }
-    CU_CHECK(e, cudaEventRecord(e->ev[3], st));
+    CU_CHECK(e, cudaEventRecord(e->ev[3], e->copy_out));
+    CU_CHECK(e, cudaStreamSynchronize(e->copy_out));
     CU_CHECK(e, cudaStreamSynchronize(st));
 
     if (out_num_packets) *out_num_packets = P;
@@ -511,7 +569,10 @@ extern "C" int32_t alac_b200_encode(alac_b200_engine *e, const alac_b200_enc_con
         stats->escape_elements = h_counters[0];
         stats->max_packet_bytes = (uint32_t)(h_counters[1] & 0xffffffffu);
         stats->kernel_launches = e->launches;
-        cudaEventElapsedTime(&stats->ms_h2d, e->ev[0], e->ev[1]);
+        // with host buffers the three phases overlap: h2d = start .. last PCM chunk landed, kernels = first .. last
+        // kernel, d2h = last kernel .. last byte on the host
+        if (in_host) cudaEventElapsedTime(&stats->ms_h2d, e->ev[0], h2d_done.back());
+        else cudaEventElapsedTime(&stats->ms_h2d, e->ev[0], e->ev[1]);
         cudaEventElapsedTime(&stats->ms_kernels, e->ev[1], e->ev[2]);
         cudaEventElapsedTime(&stats->ms_d2h, e->ev[2], e->ev[3]);
         for (size_t i = 0; i + 1 < t_search.size(); i += 2) { float ms = 0; cudaEventElapsedTime(&ms, t_search[i], t_search[i + 1]); stats->ms_search += ms; }
@@ -546,6 +607,26 @@ extern "C" int32_t alac_b200_decode(alac_b200_engine *e, const void *cookie, uin
     const uint32_t P = (uint32_t)num_packets;
     const uint64_t bpf = (uint64_t)bytes_per_sample(depth) * nch;
     cudaStream_t st = e->stream;
+    const bool in_host = in_mem != ALAC_B200_MEM_DEVICE, out_host = out_mem != ALAC_B200_MEM_DEVICE;
+
+    // ---- chunks: with host output the packets are processed in up to 8 pipelined chunks (H2D of chunk c+1,
+    //      kernels of chunk c and D2H of chunk c-1's PCM overlap); with device output one chunk and a capacity check
+    struct Chunk { uint32_t p0, cnt; uint64_t b0, b1; };
+    std::vector<Chunk> chunks;
+    uint64_t total_bytes = 0;
+    {
+        const uint32_t per = out_host ? std::max<uint32_t>(2048, (P + pipeline_chunks() - 1) / pipeline_chunks()) : P;
+        for (uint32_t p0 = 0; p0 < P; p0 += per) {
+            Chunk c;
+            c.p0 = p0; c.cnt = std::min(per, P - p0); c.b0 = total_bytes;
+            if (in_host) for (uint32_t i = p0; i < p0 + c.cnt; i++) total_bytes += packet_sizes[i];
+            c.b1 = total_bytes;
+            chunks.push_back(c);
+        }
+    }
+    if (chunks.size() > kMaxChunks) { e->err = "too many chunks"; return ALAC_B200_PARAM_ERROR; }
+    const uint32_t max_cnt = chunks[0].cnt;
+    const uint32_t groups = (max_cnt + 31) / 32;
 
     CU_CHECK(e, e->d_pkt_off.reserve(((size_t)P + 1) * 8));
     CU_CHECK(e, e->d_pkt_samples.reserve((size_t)P * 4));
@@ -554,7 +635,6 @@ extern "C" int32_t alac_b200_decode(alac_b200_engine *e, const void *cookie, uin
     CU_CHECK(e, e->d_class.reserve((size_t)P * 4));
     CU_CHECK(e, e->d_rank.reserve((size_t)P * 4));
     CU_CHECK(e, e->d_perm.reserve((size_t)P * 4));
-    const uint32_t groups = (P + 31) / 32;
     CU_CHECK(e, e->d_chan.reserve((size_t)groups * 32 * nch * frame_length * 4));
     CU_CHECK(e, e->d_meta.reserve((size_t)P * nch * sizeof(DecChanMeta)));
     CU_CHECK(e, e->counters.reserve(64));
@@ -562,25 +642,30 @@ extern "C" int32_t alac_b200_decode(alac_b200_engine *e, const void *cookie, uin
     CU_CHECK(e, cudaEventRecord(e->ev[0], st));
     const uint32_t *d_sizes;
     const uint8_t *d_packets;
-    if (in_mem == ALAC_B200_MEM_DEVICE) {
-        d_sizes = packet_sizes;
-        d_packets = static_cast<const uint8_t *>(packets);
-    } else {
-        uint64_t total = 0;
-        for (uint32_t i = 0; i < P; i++) total += packet_sizes[i];
+    std::vector<cudaEvent_t> h2d_done;
+    if (in_host) {
         CU_CHECK(e, e->d_sizes.reserve((size_t)P * 4));
-        CU_CHECK(e, e->d_packets.reserve((size_t)total + 64));
-        CU_CHECK(e, cudaMemcpyAsync(e->d_sizes.p, packet_sizes, (size_t)P * 4, cudaMemcpyHostToDevice, st));
-        CU_CHECK(e, cudaMemcpyAsync(e->d_packets.p, packets, (size_t)total, cudaMemcpyHostToDevice, st));
+        CU_CHECK(e, e->d_packets.reserve((size_t)total_bytes + 64));
+        CU_CHECK(e, cudaStreamWaitEvent(e->copy_in, e->ev[0], 0));
+        CU_CHECK(e, cudaMemcpyAsync(e->d_sizes.p, packet_sizes, (size_t)P * 4, cudaMemcpyHostToDevice, e->copy_in));
+        for (const Chunk &c : chunks) {
+            if (c.b1 > c.b0)
+                CU_CHECK(e, cudaMemcpyAsync(e->d_packets.as<uint8_t>() + c.b0, static_cast<const uint8_t *>(packets) + c.b0,
+                                            (size_t)(c.b1 - c.b0), cudaMemcpyHostToDevice, e->copy_in));
+            h2d_done.push_back(e->event_on(e->copy_in));
+        }
         d_sizes = e->d_sizes.as<uint32_t>();
         d_packets = e->d_packets.as<uint8_t>();
+    } else {
+        d_sizes = packet_sizes;
+        d_packets = static_cast<const uint8_t *>(packets);
     }
     uint8_t *d_pcm;
-    if (out_mem == ALAC_B200_MEM_DEVICE) {
-        d_pcm = static_cast<uint8_t *>(pcm_out);
-    } else {
-        CU_CHECK(e, e->d_pcm.reserve((size_t)std::min<uint64_t>(pcm_cap, (uint64_t)P * frame_length * bpf) + 64));
+    if (out_host) {
+        CU_CHECK(e, e->d_pcm.reserve((size_t)((uint64_t)P * frame_length * bpf) + 64));
         d_pcm = e->d_pcm.as<uint8_t>();
+    } else {
+        d_pcm = static_cast<uint8_t *>(pcm_out);
     }
     CU_CHECK(e, cudaEventRecord(e->ev[1], st));
 
@@ -588,7 +673,6 @@ extern "C" int32_t alac_b200_decode(alac_b200_engine *e, const void *cookie, uin
     A.packets = d_packets;
     A.pkt_off = e->d_pkt_off.as<uint64_t>();
     A.pkt_size = d_sizes;
-    A.num_packets = P;
     A.frame_length = frame_length;
     A.pb = f[3];
     A.mb = f[4];
@@ -604,42 +688,68 @@ extern "C" int32_t alac_b200_decode(alac_b200_engine *e, const void *cookie, uin
     A.perm = e->d_perm.as<uint32_t>();
     A.chan_scratch = e->d_chan.as<int32_t>();
     A.chan_meta = e->d_meta.as<DecChanMeta>();
-    CU_CHECK(e, cudaMemsetAsync(e->counters.p, 0, 64, st));
 
-    scan_u32_to_u64_kernel<<<1, 1024, 0, st>>>(d_sizes, e->d_pkt_off.as<uint64_t>(), P, nullptr, 0);
-    dec_header_kernel<<<(P + 127) / 128, 128, 0, st>>>(A);
-    dec_perm_kernel<<<(P + 127) / 128, 128, 0, st>>>(A);
-    scan_u32_to_u64_kernel<<<1, 1024, 0, st>>>(A.pkt_samples, e->d_out_frame.as<uint64_t>(), P, nullptr, 0);
-    e->launches += 4;
-    // the output capacity must be known to hold before the decode kernel writes
+    std::vector<cudaEvent_t> comp_done, t_dec;
     uint64_t total_frames = 0;
-    CU_CHECK(e, cudaMemcpyAsync(&total_frames, e->d_out_frame.as<uint64_t>() + P, 8, cudaMemcpyDeviceToHost, st));
-    CU_CHECK(e, cudaStreamSynchronize(st));
-    if (total_frames * bpf > pcm_cap) { e->err = "pcm capacity exceeded"; return ALAC_B200_PARAM_ERROR; }
-
-    cudaEvent_t t_dec0 = e->timer();
-    const dim3 ogrid((frame_length + 31) / 32, groups, nch), oblock(32, 8);
-    switch (depth) {
-    case 16: dec_lane_kernel<16><<<(P + kRingStride - 1) / kRingStride, kRingStride, 0, st>>>(A); dec_output_kernel<16><<<ogrid, oblock, 0, st>>>(A); break;
-    case 20: dec_lane_kernel<20><<<(P + kRingStride - 1) / kRingStride, kRingStride, 0, st>>>(A); dec_output_kernel<20><<<ogrid, oblock, 0, st>>>(A); break;
-    case 24: dec_lane_kernel<24><<<(P + kRingStride - 1) / kRingStride, kRingStride, 0, st>>>(A); dec_output_kernel<24><<<ogrid, oblock, 0, st>>>(A); break;
-    default: dec_lane_kernel<32><<<(P + kRingStride - 1) / kRingStride, kRingStride, 0, st>>>(A); dec_output_kernel<32><<<ogrid, oblock, 0, st>>>(A); break;
+    for (size_t ci = 0; ci < chunks.size(); ci++) {
+        const Chunk &c = chunks[ci];
+        if (in_host) CU_CHECK(e, cudaStreamWaitEvent(st, h2d_done[ci], 0));
+        A.pkt_base = c.p0;
+        A.num_packets = c.cnt;
+        CU_CHECK(e, cudaMemsetAsync(e->counters.p, 0, 64, st));
+        scan_u32_to_u64_kernel<<<1, 1024, 0, st>>>(d_sizes + c.p0, e->d_pkt_off.as<uint64_t>() + c.p0, c.cnt, nullptr, ci == 0 ? 0 : 1);
+        dec_header_kernel<<<(c.cnt + 127) / 128, 128, 0, st>>>(A);
+        dec_perm_kernel<<<(c.cnt + 127) / 128, 128, 0, st>>>(A);
+        scan_u32_to_u64_kernel<<<1, 1024, 0, st>>>(A.pkt_samples + c.p0, e->d_out_frame.as<uint64_t>() + c.p0, c.cnt, nullptr, ci == 0 ? 0 : 1);
+        e->launches += 4;
+        if (!out_host) {
+            // a caller-owned device buffer: its capacity must be known to hold before anything is written
+            CU_CHECK(e, cudaMemcpyAsync(&e->h_totals[ci], e->d_out_frame.as<uint64_t>() + c.p0 + c.cnt, 8, cudaMemcpyDeviceToHost, st));
+            CU_CHECK(e, cudaStreamSynchronize(st));
+            if (e->h_totals[ci] * bpf > pcm_cap) { e->err = "pcm capacity exceeded"; return ALAC_B200_PARAM_ERROR; }
+        }
+        t_dec.push_back(e->timer());
+        const dim3 ogrid((frame_length + 31) / 32, (c.cnt + 31) / 32, nch), oblock(32, 8);
+        const uint32_t lgrid = (c.cnt + kRingStride - 1) / kRingStride;
+        switch (depth) {
+        case 16: dec_lane_kernel<16><<<lgrid, kRingStride, 0, st>>>(A); dec_output_kernel<16><<<ogrid, oblock, 0, st>>>(A); break;
+        case 20: dec_lane_kernel<20><<<lgrid, kRingStride, 0, st>>>(A); dec_output_kernel<20><<<ogrid, oblock, 0, st>>>(A); break;
+        case 24: dec_lane_kernel<24><<<lgrid, kRingStride, 0, st>>>(A); dec_output_kernel<24><<<ogrid, oblock, 0, st>>>(A); break;
+        default: dec_lane_kernel<32><<<lgrid, kRingStride, 0, st>>>(A); dec_output_kernel<32><<<ogrid, oblock, 0, st>>>(A); break;
+        }
+        t_dec.push_back(e->timer());
+        e->launches += 2;
+        CU_CHECK(e, cudaMemcpyAsync(&e->h_totals[ci], e->d_out_frame.as<uint64_t>() + c.p0 + c.cnt, 8, cudaMemcpyDeviceToHost, st));
+        comp_done.push_back(e->event_on(st));
     }
-    cudaEvent_t t_dec1 = e->timer();
-    e->launches += 2;
-    e->launches++;
     CU_CHECK(e, cudaGetLastError());
     CU_CHECK(e, cudaEventRecord(e->ev[2], st));
 
+    // ---- results (copy-out stream) ----
+    uint64_t copied = 0;
+    bool overflow = false;
+    for (size_t ci = 0; ci < chunks.size(); ci++) {
+        CU_CHECK(e, cudaEventSynchronize(comp_done[ci]));
+        total_frames = e->h_totals[ci];
+        if (out_host) {
+            uint64_t upto = total_frames * bpf;
+            if (upto > pcm_cap) { upto = pcm_cap; overflow = true; }
+            if (upto > copied) {
+                CU_CHECK(e, cudaMemcpyAsync(static_cast<uint8_t *>(pcm_out) + copied, d_pcm + copied, (size_t)(upto - copied),
+                                            cudaMemcpyDeviceToHost, e->copy_out));
+                copied = upto;
+            }
+        }
+    }
     std::vector<int32_t> h_status(P);
-    CU_CHECK(e, cudaMemcpyAsync(h_status.data(), A.pkt_status, (size_t)P * 4, cudaMemcpyDeviceToHost, st));
-    const cudaMemcpyKind to_user = out_mem == ALAC_B200_MEM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
-    if (packet_samples) CU_CHECK(e, cudaMemcpyAsync(packet_samples, A.pkt_samples, (size_t)P * 4, to_user, st));
-    if (packet_status) CU_CHECK(e, cudaMemcpyAsync(packet_status, A.pkt_status, (size_t)P * 4, to_user, st));
-    if (out_mem != ALAC_B200_MEM_DEVICE && total_frames)
-        CU_CHECK(e, cudaMemcpyAsync(pcm_out, d_pcm, (size_t)(total_frames * bpf), cudaMemcpyDeviceToHost, st));
-    CU_CHECK(e, cudaEventRecord(e->ev[3], st));
+    CU_CHECK(e, cudaMemcpyAsync(h_status.data(), A.pkt_status, (size_t)P * 4, cudaMemcpyDeviceToHost, e->copy_out));
+    const cudaMemcpyKind to_user = out_host ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice;
+    if (packet_samples) CU_CHECK(e, cudaMemcpyAsync(packet_samples, A.pkt_samples, (size_t)P * 4, to_user, e->copy_out));
+    if (packet_status) CU_CHECK(e, cudaMemcpyAsync(packet_status, A.pkt_status, (size_t)P * 4, to_user, e->copy_out));
+    CU_CHECK(e, cudaEventRecord(e->ev[3], e->copy_out));
+    CU_CHECK(e, cudaStreamSynchronize(e->copy_out));
     CU_CHECK(e, cudaStreamSynchronize(st));
+    if (overflow) { e->err = "pcm capacity exceeded"; return ALAC_B200_PARAM_ERROR; }
 
     if (out_sample_frames) *out_sample_frames = total_frames;
     int32_t first_err = 0;
@@ -648,10 +758,11 @@ extern "C" int32_t alac_b200_decode(alac_b200_engine *e, const void *cookie, uin
         stats->num_packets = P;
         stats->payload_bytes = total_frames * bpf;
         stats->kernel_launches = e->launches;
-        cudaEventElapsedTime(&stats->ms_h2d, e->ev[0], e->ev[1]);
+        if (in_host) cudaEventElapsedTime(&stats->ms_h2d, e->ev[0], h2d_done.back());
+        else cudaEventElapsedTime(&stats->ms_h2d, e->ev[0], e->ev[1]);
         cudaEventElapsedTime(&stats->ms_kernels, e->ev[1], e->ev[2]);
         cudaEventElapsedTime(&stats->ms_d2h, e->ev[2], e->ev[3]);
-        cudaEventElapsedTime(&stats->ms_decode, t_dec0, t_dec1);
+        for (size_t i = 0; i + 1 < t_dec.size(); i += 2) { float ms = 0; cudaEventElapsedTime(&ms, t_dec[i], t_dec[i + 1]); stats->ms_decode += ms; }
     }
     return first_err;
 }

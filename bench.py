@@ -57,7 +57,7 @@ class ClockSampler:
         try:
             self.f = open(self.path, "w")
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=self.f, stderr=subprocess.DEVNULL)
         except Exception:
             self.proc = None
@@ -236,12 +236,15 @@ def run_cuda(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(max(args.warmup - 1, 0)):
-        step_device()
+    # clocks are sampled from before the warm-up to the end of the timed region (the timed region alone is
+    # only tens of milliseconds, shorter than nvidia-smi's start-up)
     sampler = ClockSampler(local)
-    barrier()
     if rank == 0:
         sampler.start()
+        time.sleep(0.3)
+    for _ in range(max(args.warmup - 1, 0)):
+        step_device()
+    barrier()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     launches = 0
     ms_search = ms_asm = ms_dec = ms_enc_k = ms_dec_k = 0.0
@@ -280,7 +283,7 @@ def run_cuda(args):
 
     e_, d_ = step_host()
     assert np.array_equal(d_.pcm, pcm_np), "host-buffer round trip is not the identity"
-    e2e_steps = max(1, min(args.steps, 3))
+    e2e_steps = max(1, min(args.steps, 5))
     barrier()
     w0 = time.perf_counter()
     for _ in range(e2e_steps):
@@ -361,7 +364,7 @@ def run_cuda(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
     ap.add_argument("--seconds", type=int, default=SECONDS, help="audio seconds per rank (default: the 1-hour workload)")

@@ -13,15 +13,18 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 def _declared():
-    text = open(os.path.join(ROOT, "include", "alac_b200.h")).read()
-    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
-    return sorted(set(re.findall(r"\b(alac_b200_[a-z_0-9]+)\s*\(", text)))
+    names = set()
+    for hdr in ("alac_b200.h", "alac_b200_container.h"):
+        text = open(os.path.join(ROOT, "include", hdr)).read()
+        text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+        names |= set(re.findall(r"\b(alac_b200_[a-z_0-9]+)\s*\(", text))
+    return sorted(names)
 
 
 def test_library_exports_every_declared_symbol():
     lib = alac_b200.load_library()
     names = _declared()
-    assert len(names) >= 9
+    assert len(names) >= 16
     for n in names:
         assert hasattr(lib, n), f"{n} declared in include/alac_b200.h but not exported"
 

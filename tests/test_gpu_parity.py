@@ -227,3 +227,24 @@ def test_class_api_demo(tmp_path, name):
     assert np.array_equal(np.fromfile(prefix + ".sizes", np.uint32), g["sizes"])
     assert np.array_equal(np.fromfile(prefix + ".packets", np.uint8), g["packets"])
     assert np.array_equal(np.fromfile(prefix + ".pcm", np.uint8), g["pcm"])
+
+
+# ---------------------------------------------------------------------------------------------
+# alacconvert CLI: WAV -> CAF -> WAV through the batched ABI, files byte-compared (BASELINE config 1 shape)
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", ["wav05_mono16_k0", "wav50_stereo16_k0", "music_stereo24_k0", "music_5ch16_k0"])
+def test_alacconvert_cli(tmp_path, name):
+    import alac_b200
+    from tests import caf_ref
+    exe = os.path.join(os.path.dirname(alac_b200.library_path()), "alacconvert")
+    if not os.path.exists(exe):
+        subprocess.run(["make", "-C", os.path.dirname(exe), "alacconvert"], check=True)
+    g = np.load(os.path.join(_ROOT, "tests", "golden", name + ".npz"))
+    ch, depth, sr = int(g["channels"]), int(g["depth"]), int(g["sample_rate"])
+    wav, caf, back = str(tmp_path / "in.wav"), str(tmp_path / "out.caf"), str(tmp_path / "back.wav")
+    open(wav, "wb").write(caf_ref.wav_bytes(sr, ch, depth, g["pcm"].tobytes()))
+    subprocess.run([exe, wav, caf], check=True, stdout=subprocess.DEVNULL)
+    want = caf_ref.caf_bytes(sr, ch, depth, bytes(g["cookie"]), int(g["pcm"].nbytes), g["packets"].tobytes(), g["sizes"])
+    assert open(caf, "rb").read() == want
+    subprocess.run([exe, caf, back], check=True, stdout=subprocess.DEVNULL)
+    assert open(back, "rb").read() == open(wav, "rb").read()

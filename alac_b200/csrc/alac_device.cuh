@@ -309,7 +309,10 @@ struct BitPeek {
 // target of a load in flight.  Ring slot s of this lane is ring[s * kRingStride] (bank == lane).
 constexpr uint32_t kRingSlots = 8;
 constexpr uint32_t kRingAhead = 6;
-constexpr uint32_t kRingStride = 128;     // lanes per CTA of the kernels that use BitReader
+#ifndef ALAC_DEC_LANES
+#define ALAC_DEC_LANES 128
+#endif
+constexpr uint32_t kRingStride = ALAC_DEC_LANES;     // lanes per CTA of the kernels that use BitReader
 
 __device__ __forceinline__ void cp_async_word(uint32_t *smem_dst, const uint32_t *gsrc)
 {

@@ -196,7 +196,10 @@ __device__ __forceinline__ void init_coefs_row(int32_t *a, int n)
 
 // 128 chain lanes + one spare warp: the spare warp owns no chain; it only takes final-pass jobs so that
 // the 4-tap and the 8-tap jobs can each start on a warp boundary and no warp ever runs both loops.
-constexpr int kChainThreads = 128;
+#ifndef ALAC_CHAIN_THREADS
+#define ALAC_CHAIN_THREADS 96
+#endif
+constexpr int kChainThreads = ALAC_CHAIN_THREADS;
 #ifndef ALAC_SPARE_WARPS
 #define ALAC_SPARE_WARPS 1
 #endif
@@ -213,7 +216,7 @@ struct FinalJob {
 };
 
 template <int DEPTH, bool STEREO, bool PACKED, bool WRAP>
-__global__ void __launch_bounds__(kSearchThreads, 5)
+__global__ void __launch_bounds__(kSearchThreads, 864 / kSearchThreads)
 enc_search_kernel(EncArgs A, uint32_t elems_of_kind, uint32_t kind_elem0 /* bitmask of element slots of this kind */)
 {
     // Stages A and B keep the U and V chains of a pair on adjacent lanes (they trade bit counts by

@@ -50,6 +50,8 @@ struct alac_b200_engine {
     cudaStream_t stream = nullptr;
     cudaStream_t own_stream = nullptr;
     cudaStream_t copy_in = nullptr, copy_out = nullptr;     // transfer streams of the host-buffer pipeline
+    cudaStream_t lanes[4] = {nullptr, nullptr, nullptr, nullptr};   // compute streams of the host-buffer pipeline
+    cudaStream_t cur = nullptr;                             // stream the launch helpers / timers use right now
     uint64_t *h_totals = nullptr;                           // pinned: running byte / frame totals per chunk
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     std::string err;
@@ -80,7 +82,7 @@ struct alac_b200_engine {
             timers.push_back(ev);
         }
         cudaEvent_t ev = timers[timers_used++];
-        cudaEventRecord(ev, stream);
+        cudaEventRecord(ev, cur ? cur : stream);
         return ev;
     }
 };
@@ -114,8 +116,19 @@ static uint32_t pipeline_chunks()
 {
     static const uint32_t n = [] {
         const char *v = getenv("ALAC_B200_PIPELINE_CHUNKS");
-        const long k = v ? atol(v) : 2;
+        const long k = v ? atol(v) : 4;
         return (uint32_t)(k < 1 ? 1 : k > 64 ? 64 : k);
+    }();
+    return n;
+}
+
+// packets per search launch: bounds the Golomb-slab scratch (ALAC_B200_CHUNK_PACKETS overrides)
+static uint64_t scratch_chunk_packets()
+{
+    static const uint64_t n = [] {
+        const char *v = getenv("ALAC_B200_CHUNK_PACKETS");
+        const long long k = v ? atoll(v) : 0;
+        return (uint64_t)(k <= 0 ? 0 : k < 1024 ? 1024 : k);
     }();
     return n;
 }
@@ -184,7 +197,9 @@ int32_t alac_b200_engine_create(int32_t device, alac_b200_engine **out_engine)
         return ALAC_B200_CUDA_ERROR;
     }
     e->stream = e->own_stream;
-    if (cudaStreamCreateWithFlags(&e->copy_in, cudaStreamNonBlocking) != cudaSuccess ||
+    bool lanes_ok = true;
+    for (auto &ln : e->lanes) lanes_ok = lanes_ok && cudaStreamCreateWithFlags(&ln, cudaStreamNonBlocking) == cudaSuccess;
+    if (!lanes_ok || cudaStreamCreateWithFlags(&e->copy_in, cudaStreamNonBlocking) != cudaSuccess ||
         cudaStreamCreateWithFlags(&e->copy_out, cudaStreamNonBlocking) != cudaSuccess ||
         cudaHostAlloc(&e->h_totals, kMaxChunks * sizeof(uint64_t), cudaHostAllocDefault) != cudaSuccess) {
         delete e;
@@ -214,6 +229,7 @@ void alac_b200_engine_destroy(alac_b200_engine *e)
     for (auto &ev : e->timers) cudaEventDestroy(ev);
     if (e->own_stream) cudaStreamDestroy(e->own_stream);
     if (e->copy_in) cudaStreamDestroy(e->copy_in);
+    for (auto &ln : e->lanes) if (ln) cudaStreamDestroy(ln);
     if (e->copy_out) cudaStreamDestroy(e->copy_out);
     if (e->h_totals) cudaFreeHost(e->h_totals);
     delete e;
@@ -304,13 +320,13 @@ static void launch_search_v(alac_b200_engine *e, const EncArgs &A, uint32_t mono
     if (pairs) {
         const uint64_t threads = (uint64_t)A.num_segments * pairs * 2;
         enc_search_kernel<DEPTH, true, PACKED, WRAP>
-            <<<(uint32_t)((threads + kChainThreads - 1) / kChainThreads), kSearchThreads, 0, e->stream>>>(A, pairs, pair_mask);
+            <<<(uint32_t)((threads + kChainThreads - 1) / kChainThreads), kSearchThreads, 0, e->cur>>>(A, pairs, pair_mask);
         e->launches++;
     }
     if (monos) {
         const uint64_t threads = (uint64_t)A.num_segments * monos;
         enc_search_kernel<DEPTH, false, false, WRAP>
-            <<<(uint32_t)((threads + kChainThreads - 1) / kChainThreads), kSearchThreads, 0, e->stream>>>(A, monos, mono_mask);
+            <<<(uint32_t)((threads + kChainThreads - 1) / kChainThreads), kSearchThreads, 0, e->cur>>>(A, monos, mono_mask);
         e->launches++;
     }
 }
@@ -332,7 +348,7 @@ static void launch_search(alac_b200_engine *e, const EncArgs &A, uint32_t mono_m
 template <int DEPTH>
 static void launch_assemble(alac_b200_engine *e, const AsmArgs &A)
 {
-    enc_assemble_kernel<DEPTH><<<(A.num_packets + kAsmWarps - 1) / kAsmWarps, kAsmWarps * 32, 0, e->stream>>>(A);
+    enc_assemble_kernel<DEPTH><<<(A.num_packets + kAsmWarps - 1) / kAsmWarps, kAsmWarps * 32, 0, e->cur>>>(A);
     e->launches++;
 }
 
@@ -398,8 +414,12 @@ extern "C" int32_t alac_b200_encode(alac_b200_engine *e, const alac_b200_enc_con
     // the kernels of chunk c (compute stream) and the D2H of chunk c-1's packets (copy-out stream).
     const uint32_t cap_words = F + 8;       // >= worst-case Golomb words per channel (<= 32 bits/sample incl. run codes)
     const bool in_host = pcm_mem != ALAC_B200_MEM_DEVICE, out_host = out_mem != ALAC_B200_MEM_DEVICE;
-    uint64_t chunk_target = 65536;
-    if (in_host || out_host) chunk_target = std::min<uint64_t>(65536, std::max<uint64_t>(2048, (P + pipeline_chunks() - 1) / pipeline_chunks()));
+    // default: as many packets as fit an 8 GB slab budget (bigger launches fill the GPU more evenly)
+    uint64_t chunk_target = scratch_chunk_packets();
+    if (!chunk_target) chunk_target = std::max<uint64_t>(4096, (8ull << 30) / ((uint64_t)L.chains_per_packet * cap_words * 4));
+    const bool multi = in_host || out_host;             // host buffers: chunks run on several compute streams
+    const uint32_t nlanes = multi ? 4u : 1u;
+    if (multi) chunk_target = std::min<uint64_t>(chunk_target / nlanes, std::max<uint64_t>(2048, (P + pipeline_chunks() - 1) / pipeline_chunks()));
     struct Chunk { uint32_t s0, s1, p0, cnt; uint64_t f_lo, f_hi; };
     std::vector<Chunk> chunks;
     uint64_t max_chunk = 0;
@@ -426,8 +446,10 @@ extern "C" int32_t alac_b200_encode(alac_b200_engine *e, const alac_b200_enc_con
     CU_CHECK(e, e->seg_first.reserve((size_t)S * 4));
     CU_CHECK(e, e->seg_count.reserve((size_t)S * 4));
     CU_CHECK(e, e->seg_stream.reserve((size_t)S * 4));
-    CU_CHECK(e, e->recs.reserve((size_t)max_chunk * L.elems_per_packet * sizeof(ElemRec)));
-    CU_CHECK(e, e->scratch.reserve((size_t)max_chunk * L.chains_per_packet * cap_words * 4));
+    const size_t recs_per_lane = (size_t)max_chunk * L.elems_per_packet;
+    const size_t slab_words_per_lane = (size_t)max_chunk * L.chains_per_packet * cap_words;
+    CU_CHECK(e, e->recs.reserve(recs_per_lane * nlanes * sizeof(ElemRec)));
+    CU_CHECK(e, e->scratch.reserve(slab_words_per_lane * nlanes * 4));
     CU_CHECK(e, e->sizes.reserve((size_t)P * 4));
     CU_CHECK(e, e->offsets.reserve(((size_t)P + 1) * 8));
     CU_CHECK(e, e->counters.reserve(64));
@@ -448,16 +470,7 @@ extern "C" int32_t alac_b200_encode(alac_b200_engine *e, const alac_b200_enc_con
 
     cudaStream_t st = e->stream;
     CU_CHECK(e, cudaEventRecord(e->ev[0], st));
-    // copy-in stream: PCM chunks, each followed by an event the compute stream waits on
-    std::vector<cudaEvent_t> h2d_done;
-    if (in_host) {
-        CU_CHECK(e, cudaStreamWaitEvent(e->copy_in, e->ev[0], 0));
-        for (const Chunk &c : chunks) {
-            CU_CHECK(e, cudaMemcpyAsync(e->pcm.as<uint8_t>() + c.f_lo * bpf, static_cast<const uint8_t *>(pcm) + c.f_lo * bpf,
-                                        (size_t)((c.f_hi - c.f_lo) * bpf), cudaMemcpyHostToDevice, e->copy_in));
-            h2d_done.push_back(e->event_on(e->copy_in));
-        }
-    }
+    // small tables first: they share the H2D copy engine with the PCM chunks and must not queue behind them
     CU_CHECK(e, cudaMemcpyAsync(e->pkt_frame.p, h_pkt_frame.data(), (size_t)P * 8, cudaMemcpyHostToDevice, st));
     CU_CHECK(e, cudaMemcpyAsync(e->pkt_samples.p, h_pkt_samples.data(), (size_t)P * 4, cudaMemcpyHostToDevice, st));
     CU_CHECK(e, cudaMemcpyAsync(e->seg_first.p, h_seg_first.data(), (size_t)S * 4, cudaMemcpyHostToDevice, st));
@@ -470,19 +483,34 @@ extern "C" int32_t alac_b200_encode(alac_b200_engine *e, const alac_b200_enc_con
         d_state = e->state.as<int16_t>();
     }
     CU_CHECK(e, cudaMemsetAsync(e->counters.p, 0, 64, st));
+    // copy-in stream: PCM chunks, each followed by an event the compute stream waits on
+    std::vector<cudaEvent_t> h2d_done;
+    if (in_host) {
+        CU_CHECK(e, cudaStreamWaitEvent(e->copy_in, e->ev[0], 0));
+        for (const Chunk &c : chunks) {
+            CU_CHECK(e, cudaMemcpyAsync(e->pcm.as<uint8_t>() + c.f_lo * bpf, static_cast<const uint8_t *>(pcm) + c.f_lo * bpf,
+                                        (size_t)((c.f_hi - c.f_lo) * bpf), cudaMemcpyHostToDevice, e->copy_in));
+            h2d_done.push_back(e->event_on(e->copy_in));
+        }
+    }
     CU_CHECK(e, cudaEventRecord(e->ev[1], st));
 
-    // ---- kernels, chunk by chunk (compute stream) ----
+    // ---- kernels, chunk by chunk.  Device-resident calls stay on the caller's stream; with host buffers chunk c
+    //      runs on compute lane c % 4 (own scratch), so its kernels overlap its neighbours' kernels and copies ----
     // coefficients move by at most 1 per predictor step and a frame runs < 2 * frame_size steps on a row:
     // starting from init_coefs (|a| <= 1216) the int16 range cannot be left within K frames if this holds
     const bool wrap = coef_state != nullptr || K == 0 || (uint64_t)K * 2u * F + 1216u > 32767u;
     const bool packed = cfg->channels == 2 && (reinterpret_cast<uintptr_t>(d_pcm) & 7u) == 0;
     unsigned long long *d_escapes = e->counters.as<unsigned long long>();
     uint32_t *d_max = reinterpret_cast<uint32_t *>(e->counters.as<uint8_t>() + 8);
-    std::vector<cudaEvent_t> comp_done;
+    std::vector<cudaEvent_t> comp_done, scan_done;
     for (size_t ci = 0; ci < chunks.size(); ci++) {
         const Chunk &c = chunks[ci];
-        if (in_host) CU_CHECK(e, cudaStreamWaitEvent(st, h2d_done[ci], 0));
+        const uint32_t lane = (uint32_t)(ci % nlanes);
+        cudaStream_t cs = multi ? e->lanes[lane] : st;
+        e->cur = cs;
+        if (multi && ci < nlanes) CU_CHECK(e, cudaStreamWaitEvent(cs, e->ev[1], 0));       // tables are in
+        if (in_host) CU_CHECK(e, cudaStreamWaitEvent(cs, h2d_done[ci], 0));
         EncArgs A;
         A.pcm = d_pcm;
         A.pkt_frame = e->pkt_frame.as<uint64_t>();
@@ -494,8 +522,8 @@ extern "C" int32_t alac_b200_encode(alac_b200_engine *e, const alac_b200_enc_con
         A.num_segments = c.s1 - c.s0;
         A.pkt_base = c.p0;
         A.lay = L;
-        A.recs = e->recs.as<ElemRec>();
-        A.scratch = e->scratch.as<uint32_t>();
+        A.recs = e->recs.as<ElemRec>() + recs_per_lane * lane;
+        A.scratch = e->scratch.as<uint32_t>() + slab_words_per_lane * lane;
         A.cap_words = cap_words;
         A.state = d_state;
         t_search.push_back(e->timer());
@@ -506,10 +534,13 @@ extern "C" int32_t alac_b200_encode(alac_b200_engine *e, const alac_b200_enc_con
         default: launch_search<32>(e, A, mono_mask, pair_mask, packed, wrap); break;
         }
         t_search.push_back(e->timer());
-        enc_size_kernel<<<(c.cnt + 255) / 256, 256, 0, st>>>(A.recs, L, cfg->bit_depth, A.pkt_samples + c.p0, c.cnt,
+        enc_size_kernel<<<(c.cnt + 255) / 256, 256, 0, cs>>>(A.recs, L, cfg->bit_depth, A.pkt_samples + c.p0, c.cnt,
                                                             e->sizes.as<uint32_t>() + c.p0, d_escapes);
-        scan_u32_to_u64_kernel<<<1, 1024, 0, st>>>(e->sizes.as<uint32_t>() + c.p0, e->offsets.as<uint64_t>() + c.p0, c.cnt, d_max,
+        // the scan continues from the previous chunk's total: wait for that chunk's scan
+        if (multi && ci > 0) CU_CHECK(e, cudaStreamWaitEvent(cs, scan_done[ci - 1], 0));
+        scan_u32_to_u64_kernel<<<1, 1024, 0, cs>>>(e->sizes.as<uint32_t>() + c.p0, e->offsets.as<uint64_t>() + c.p0, c.cnt, d_max,
                                                    ci == 0 ? 0 : 1);
+        if (multi) scan_done.push_back(e->event_on(cs));
         e->launches += 2;
 
         AsmArgs B;
@@ -534,10 +565,12 @@ extern "C" int32_t alac_b200_encode(alac_b200_engine *e, const alac_b200_enc_con
         }
         t_asm.push_back(e->timer());
         // running byte total after this chunk -> pinned host word; the host needs it to size the chunk's D2H
-        CU_CHECK(e, cudaMemcpyAsync(&e->h_totals[ci], e->offsets.as<uint64_t>() + c.p0 + c.cnt, 8, cudaMemcpyDeviceToHost, st));
-        comp_done.push_back(e->event_on(st));
+        CU_CHECK(e, cudaMemcpyAsync(&e->h_totals[ci], e->offsets.as<uint64_t>() + c.p0 + c.cnt, 8, cudaMemcpyDeviceToHost, cs));
+        comp_done.push_back(e->event_on(cs));
     }
+    e->cur = nullptr;
     CU_CHECK(e, cudaGetLastError());
+    if (multi) for (cudaEvent_t ev : comp_done) CU_CHECK(e, cudaStreamWaitEvent(st, ev, 0));     // join the lanes
     CU_CHECK(e, cudaEventRecord(e->ev[2], st));
 
     // ---- results (copy-out stream) ----
@@ -615,7 +648,7 @@ extern "C" int32_t alac_b200_decode(alac_b200_engine *e, const void *cookie, uin
     std::vector<Chunk> chunks;
     uint64_t total_bytes = 0;
     {
-        const uint32_t per = out_host ? std::max<uint32_t>(2048, (P + pipeline_chunks() - 1) / pipeline_chunks()) : P;
+        const uint32_t per = out_host ? std::max<uint32_t>(2048, (P + pipeline_chunks() - 1) / pipeline_chunks()) : P;     // see multi below
         for (uint32_t p0 = 0; p0 < P; p0 += per) {
             Chunk c;
             c.p0 = p0; c.cnt = std::min(per, P - p0); c.b0 = total_bytes;
@@ -627,6 +660,9 @@ extern "C" int32_t alac_b200_decode(alac_b200_engine *e, const void *cookie, uin
     if (chunks.size() > kMaxChunks) { e->err = "too many chunks"; return ALAC_B200_PARAM_ERROR; }
     const uint32_t max_cnt = chunks[0].cnt;
     const uint32_t groups = (max_cnt + 31) / 32;
+    const bool multi = out_host;                        // chunks run on several compute streams
+    const uint32_t nlanes = multi ? 4u : 1u;
+    const size_t chan_words_per_lane = (size_t)groups * 32 * nch * frame_length;
 
     CU_CHECK(e, e->d_pkt_off.reserve(((size_t)P + 1) * 8));
     CU_CHECK(e, e->d_pkt_samples.reserve((size_t)P * 4));
@@ -635,9 +671,9 @@ extern "C" int32_t alac_b200_decode(alac_b200_engine *e, const void *cookie, uin
     CU_CHECK(e, e->d_class.reserve((size_t)P * 4));
     CU_CHECK(e, e->d_rank.reserve((size_t)P * 4));
     CU_CHECK(e, e->d_perm.reserve((size_t)P * 4));
-    CU_CHECK(e, e->d_chan.reserve((size_t)groups * 32 * nch * frame_length * 4));
+    CU_CHECK(e, e->d_chan.reserve(chan_words_per_lane * nlanes * 4));
     CU_CHECK(e, e->d_meta.reserve((size_t)P * nch * sizeof(DecChanMeta)));
-    CU_CHECK(e, e->counters.reserve(64));
+    CU_CHECK(e, e->counters.reserve(64 * 4));
 
     CU_CHECK(e, cudaEventRecord(e->ev[0], st));
     const uint32_t *d_sizes;
@@ -648,6 +684,8 @@ extern "C" int32_t alac_b200_decode(alac_b200_engine *e, const void *cookie, uin
         CU_CHECK(e, e->d_packets.reserve((size_t)total_bytes + 64));
         CU_CHECK(e, cudaStreamWaitEvent(e->copy_in, e->ev[0], 0));
         CU_CHECK(e, cudaMemcpyAsync(e->d_sizes.p, packet_sizes, (size_t)P * 4, cudaMemcpyHostToDevice, e->copy_in));
+        CU_CHECK(e, cudaEventRecord(e->ev[3], e->copy_in));
+        CU_CHECK(e, cudaStreamWaitEvent(st, e->ev[3], 0));                 // sizes are in
         for (const Chunk &c : chunks) {
             if (c.b1 > c.b0)
                 CU_CHECK(e, cudaMemcpyAsync(e->d_packets.as<uint8_t>() + c.b0, static_cast<const uint8_t *>(packets) + c.b0,
@@ -667,6 +705,9 @@ extern "C" int32_t alac_b200_decode(alac_b200_engine *e, const void *cookie, uin
     } else {
         d_pcm = static_cast<uint8_t *>(pcm_out);
     }
+    // byte offsets of all packets at once (the sizes are all known up front)
+    scan_u32_to_u64_kernel<<<1, 1024, 0, st>>>(d_sizes, e->d_pkt_off.as<uint64_t>(), P, nullptr, 0);
+    e->launches += 1;
     CU_CHECK(e, cudaEventRecord(e->ev[1], st));
 
     DecArgs A;
@@ -689,40 +730,50 @@ extern "C" int32_t alac_b200_decode(alac_b200_engine *e, const void *cookie, uin
     A.chan_scratch = e->d_chan.as<int32_t>();
     A.chan_meta = e->d_meta.as<DecChanMeta>();
 
-    std::vector<cudaEvent_t> comp_done, t_dec;
+    std::vector<cudaEvent_t> comp_done, scan_done, t_dec;
     uint64_t total_frames = 0;
     for (size_t ci = 0; ci < chunks.size(); ci++) {
         const Chunk &c = chunks[ci];
-        if (in_host) CU_CHECK(e, cudaStreamWaitEvent(st, h2d_done[ci], 0));
+        const uint32_t lane = (uint32_t)(ci % nlanes);
+        cudaStream_t cs = multi ? e->lanes[lane] : st;
+        e->cur = cs;
+        if (multi && ci < nlanes) CU_CHECK(e, cudaStreamWaitEvent(cs, e->ev[1], 0));       // packet offsets are in
+        if (in_host) CU_CHECK(e, cudaStreamWaitEvent(cs, h2d_done[ci], 0));
         A.pkt_base = c.p0;
         A.num_packets = c.cnt;
-        CU_CHECK(e, cudaMemsetAsync(e->counters.p, 0, 64, st));
-        scan_u32_to_u64_kernel<<<1, 1024, 0, st>>>(d_sizes + c.p0, e->d_pkt_off.as<uint64_t>() + c.p0, c.cnt, nullptr, ci == 0 ? 0 : 1);
-        dec_header_kernel<<<(c.cnt + 127) / 128, 128, 0, st>>>(A);
-        dec_perm_kernel<<<(c.cnt + 127) / 128, 128, 0, st>>>(A);
-        scan_u32_to_u64_kernel<<<1, 1024, 0, st>>>(A.pkt_samples + c.p0, e->d_out_frame.as<uint64_t>() + c.p0, c.cnt, nullptr, ci == 0 ? 0 : 1);
-        e->launches += 4;
+        A.class_count = e->counters.as<uint32_t>() + 16 * lane;
+        A.chan_scratch = e->d_chan.as<int32_t>() + chan_words_per_lane * lane;
+        CU_CHECK(e, cudaMemsetAsync(A.class_count, 0, 64, cs));
+        dec_header_kernel<<<(c.cnt + 127) / 128, 128, 0, cs>>>(A);
+        dec_perm_kernel<<<(c.cnt + 127) / 128, 128, 0, cs>>>(A);
+        // output positions continue from the previous chunk's total
+        if (multi && ci > 0) CU_CHECK(e, cudaStreamWaitEvent(cs, scan_done[ci - 1], 0));
+        scan_u32_to_u64_kernel<<<1, 1024, 0, cs>>>(A.pkt_samples + c.p0, e->d_out_frame.as<uint64_t>() + c.p0, c.cnt, nullptr, ci == 0 ? 0 : 1);
+        if (multi) scan_done.push_back(e->event_on(cs));
+        e->launches += 3;
         if (!out_host) {
             // a caller-owned device buffer: its capacity must be known to hold before anything is written
-            CU_CHECK(e, cudaMemcpyAsync(&e->h_totals[ci], e->d_out_frame.as<uint64_t>() + c.p0 + c.cnt, 8, cudaMemcpyDeviceToHost, st));
-            CU_CHECK(e, cudaStreamSynchronize(st));
+            CU_CHECK(e, cudaMemcpyAsync(&e->h_totals[ci], e->d_out_frame.as<uint64_t>() + c.p0 + c.cnt, 8, cudaMemcpyDeviceToHost, cs));
+            CU_CHECK(e, cudaStreamSynchronize(cs));
             if (e->h_totals[ci] * bpf > pcm_cap) { e->err = "pcm capacity exceeded"; return ALAC_B200_PARAM_ERROR; }
         }
         t_dec.push_back(e->timer());
         const dim3 ogrid((frame_length + 31) / 32, (c.cnt + 31) / 32, nch), oblock(32, 8);
         const uint32_t lgrid = (c.cnt + kRingStride - 1) / kRingStride;
         switch (depth) {
-        case 16: dec_lane_kernel<16><<<lgrid, kRingStride, 0, st>>>(A); dec_output_kernel<16><<<ogrid, oblock, 0, st>>>(A); break;
-        case 20: dec_lane_kernel<20><<<lgrid, kRingStride, 0, st>>>(A); dec_output_kernel<20><<<ogrid, oblock, 0, st>>>(A); break;
-        case 24: dec_lane_kernel<24><<<lgrid, kRingStride, 0, st>>>(A); dec_output_kernel<24><<<ogrid, oblock, 0, st>>>(A); break;
-        default: dec_lane_kernel<32><<<lgrid, kRingStride, 0, st>>>(A); dec_output_kernel<32><<<ogrid, oblock, 0, st>>>(A); break;
+        case 16: dec_lane_kernel<16><<<lgrid, kRingStride, 0, cs>>>(A); dec_output_kernel<16><<<ogrid, oblock, 0, cs>>>(A); break;
+        case 20: dec_lane_kernel<20><<<lgrid, kRingStride, 0, cs>>>(A); dec_output_kernel<20><<<ogrid, oblock, 0, cs>>>(A); break;
+        case 24: dec_lane_kernel<24><<<lgrid, kRingStride, 0, cs>>>(A); dec_output_kernel<24><<<ogrid, oblock, 0, cs>>>(A); break;
+        default: dec_lane_kernel<32><<<lgrid, kRingStride, 0, cs>>>(A); dec_output_kernel<32><<<ogrid, oblock, 0, cs>>>(A); break;
         }
         t_dec.push_back(e->timer());
         e->launches += 2;
-        CU_CHECK(e, cudaMemcpyAsync(&e->h_totals[ci], e->d_out_frame.as<uint64_t>() + c.p0 + c.cnt, 8, cudaMemcpyDeviceToHost, st));
-        comp_done.push_back(e->event_on(st));
+        CU_CHECK(e, cudaMemcpyAsync(&e->h_totals[ci], e->d_out_frame.as<uint64_t>() + c.p0 + c.cnt, 8, cudaMemcpyDeviceToHost, cs));
+        comp_done.push_back(e->event_on(cs));
     }
+    e->cur = nullptr;
     CU_CHECK(e, cudaGetLastError());
+    if (multi) for (cudaEvent_t ev : comp_done) CU_CHECK(e, cudaStreamWaitEvent(st, ev, 0));     // join the lanes
     CU_CHECK(e, cudaEventRecord(e->ev[2], st));
 
     // ---- results (copy-out stream) ----

@@ -328,6 +328,14 @@ def run_cuda(args):
     alg_bytes = pcm_d.numel() + payload
     search_ms = ms_search / args.steps
     achieved = alg_bytes / (search_ms / 1e3) / 1e9
+    traffic = None          # DRAM bytes per launch from the committed ncu --set full capture (same workload only)
+    try:
+        if args.seconds == SECONDS:
+            for k in json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))["kernels"]:
+                if "enc_search" in k["kernel"]:
+                    traffic = int(k["dram_read_bytes"] + k["dram_write_bytes"])
+    except Exception:
+        pass
     line = {
         "metric": METRIC, "value": value / 1e6, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -344,8 +352,8 @@ def run_cuda(args):
         "e2e": {"value": e2e_value / 1e6, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                 "ms_per_step": e2e_s * 1e3, "steps": e2e_steps},
         "gpu_launches": int(launches),
-        "roofline": {"bound": "hbm", "kernel": "enc_search_kernel<16,true>", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
-                     "frac": achieved / hbm_peak, "traffic": None, "peak_source": peak_kind,
+        "roofline": {"bound": "hbm", "kernel": "enc_search_kernel<16,stereo,packed,nowrap>", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
+                     "frac": achieved / hbm_peak, "traffic": traffic, "peak_source": peak_kind,
                      "algorithmic_bytes_per_launch": int(alg_bytes),
                      "note": "integer-issue bound, not HBM bound: see DESIGN.md and profiles/ for pipe utilisation"},
         "cpu_baseline": {"value": rtN / 1e6, "unit": UNIT, "cores": threads, "kind": kind,

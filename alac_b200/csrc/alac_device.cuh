@@ -314,31 +314,37 @@ constexpr uint32_t kRingAhead = 6;
 #endif
 constexpr uint32_t kRingStride = ALAC_DEC_LANES;     // lanes per CTA of the kernels that use BitReader
 
-__device__ __forceinline__ void cp_async_word(uint32_t *smem_dst, const uint32_t *gsrc)
+// 4-byte cp.async with a source size: src_bytes = 0 reads nothing and zero-fills the destination
+__device__ __forceinline__ void cp_async_word(uint32_t smem_dst, const uint32_t *gsrc, uint32_t src_bytes)
 {
-    const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d), "l"(gsrc) : "memory");
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(smem_dst), "l"(gsrc), "r"(src_bytes) : "memory");
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ uint32_t lds_u32(uint32_t smem_addr)
+{
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(smem_addr) : "memory");
+    return v;
+}
 
 struct BitReader {
     const uint32_t *base;
-    uint32_t bias, last_word;
-    uint32_t *ring;         // this lane's column of the CTA's ring
+    uint32_t bias;
+    int32_t last_word;      // index of the last word holding packet bytes; -1 for an empty packet
+    uint32_t ring;          // shared-memory address of this lane's ring column
     uint32_t wi;            // word index of w0
     uint32_t w0, w1, w2;    // byte-swapped words wi, wi+1, wi+2
     uint32_t pos;
-    bool valid;
 
+    // branch-free: words past the end are not read, their slot is zero-filled by the copy itself
     __device__ __forceinline__ void issue(uint32_t i)
     {
-        uint32_t *dst = ring + (i & (kRingSlots - 1u)) * kRingStride;
-        if (valid && i <= last_word) cp_async_word(dst, base + i);
-        else *dst = 0u;
+        const bool in = (int32_t)i <= last_word;
+        cp_async_word(ring + (i & (kRingSlots - 1u)) * (kRingStride * 4u), base + (in ? i : 0u), in ? 4u : 0u);
         cp_async_commit();
     }
-    __device__ __forceinline__ uint32_t slot(uint32_t i) const { return bswap32(ring[(i & (kRingSlots - 1u)) * kRingStride]); }
+    __device__ __forceinline__ uint32_t slot(uint32_t i) const { return bswap32(lds_u32(ring + (i & (kRingSlots - 1u)) * (kRingStride * 4u))); }
     __device__ __forceinline__ void fill(uint32_t i)
     {
         wi = i;
@@ -360,9 +366,9 @@ struct BitReader {
         const uintptr_t addr = reinterpret_cast<uintptr_t>(packet);
         base = reinterpret_cast<const uint32_t *>(addr & ~(uintptr_t)3);
         bias = (uint32_t)(addr & 3u) * 8u;
-        valid = nbytes != 0;
-        last_word = valid ? (bias + nbytes * 8u - 1u) >> 5 : 0u;
-        ring = ring_column;
+        last_word = nbytes ? (int32_t)((bias + nbytes * 8u - 1u) >> 5) : -1;
+        if (!nbytes) base = ring_column;        // never dereferenced (every request has size 0), but keep it sane
+        ring = (uint32_t)__cvta_generic_to_shared(ring_column);
         pos = 0;
         fill(0);
     }
@@ -443,8 +449,9 @@ struct AgDec {
     __device__ __forceinline__ int32_t next(BitReader &br, uint32_t cap_bits)
     {
         if (pending_zeros) { pending_zeros--; c++; return 0; }
-        if (status) { c++; return 0; }
-        if (!((br.pos - start_rel) < cap_bits)) { status = -50; c++; return 0; }      // ag_dec.c:302
+        // ag_dec.c:302 "bitPos < maxPos".  An error latches; decoding goes on over zero-filled words (a failed
+        // packet's samples are unspecified) so the hot loop carries no early-out.
+        if (!((br.pos - start_rel) < cap_bits)) status = -50;
         uint32_t k = 31u - (uint32_t)__clz((int)((mb >> kQbShift) + 3u));
         k = min(k, kb);
         const uint32_t m = (1u << k) - 1u;

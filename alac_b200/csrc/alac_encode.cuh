@@ -112,8 +112,18 @@ struct MixSrc {
             else if (DEPTH == 32) { l = (int32_t)r.w[0] >> sh; rr = (int32_t)r.w[1] >> sh; }
             else { l = widen(r.w[0] | (r.w[1] << 8) | (r.w[2] << 16)); rr = widen(r.w[3] | (r.w[4] << 8) | (r.w[5] << 16)); }
         }
-        if (mix_res != 0) return is_v ? (l - rr) : ((mix_res * l + ((1 << kMixBits) - mix_res) * rr) >> kMixBits);
-        return is_v ? rr : l;
+        // u = (mixRes*l + (4-mixRes)*r) >> 2, v = l - r; mixRes 0: u = l, v = r (codec/matrix_enc.cu:72-99).
+        // All four cases are (cl*l + cr*r) >> sh with per-lane constants, so the hot loop has no selects.
+        return (cl * l + cr * rr) >> sh_mix;
+    }
+    int32_t cl, cr;
+    uint32_t sh_mix;
+    __device__ __forceinline__ void set_mix(int32_t res, bool v)
+    {
+        mix_res = res;
+        is_v = v;
+        if (res != 0) { cl = v ? 1 : res; cr = v ? -1 : (1 << kMixBits) - res; sh_mix = v ? 0u : (uint32_t)kMixBits; }
+        else { cl = v ? 0 : 1; cr = v ? 1 : 0; sh_mix = 0u; }
     }
     __device__ __forceinline__ int32_t get(uint32_t j) const
     {
@@ -284,7 +294,8 @@ enc_search_kernel(EncArgs A, uint32_t elems_of_kind, uint32_t kind_elem0 /* bitm
         const uint32_t partial = (n != A.lay.frame_size);
 
         MixSrc<DEPTH, STEREO, PACKED> src;
-        src.base = base; src.stride = stride; src.is_v = is_v; src.mix_res = 0; src.valid = n;
+        src.base = base; src.stride = stride; src.valid = n;
+        src.set_mix(0, is_v);
 
         uint32_t best_res = 0;
         uint32_t num_mine = 8;           // taps chosen for this lane's channel
@@ -298,7 +309,7 @@ enc_search_kernel(EncArgs A, uint32_t elems_of_kind, uint32_t kind_elem0 /* bitm
                 const uint32_t na = n / 8;
                 uint32_t min_bits = 1u << 31;
                 for (int r = 0; r <= kMaxRes; r++) {
-                    src.mix_res = r;
+                    src.set_mix(r, is_v);
                     src.valid = na;
                     CostSink cs;
                     cs.ag.start(na);
@@ -308,7 +319,7 @@ enc_search_kernel(EncArgs A, uint32_t elems_of_kind, uint32_t kind_elem0 /* bitm
                     const uint32_t both = cs.ag.bits + __shfl_xor_sync(pair_mask, cs.ag.bits, 1);
                     if (both < min_bits) { min_bits = both; best_res = (uint32_t)r; }
                 }
-                src.mix_res = (int32_t)best_res;
+                src.set_mix((int32_t)best_res, is_v);
                 src.valid = n;
             }
             // stage B: taps search (:418-452 stereo, :881-905 mono)
@@ -405,7 +416,8 @@ enc_search_kernel(EncArgs A, uint32_t elems_of_kind, uint32_t kind_elem0 /* bitm
         if (threadIdx.x < n4 || (threadIdx.x >= first8 && threadIdx.x < first8 + n8)) {
             FinalJob &J = s_job[threadIdx.x];
             MixSrc<DEPTH, STEREO, PACKED> fs;
-            fs.base = J.base; fs.stride = stride; fs.is_v = (J.flags & 1u) != 0; fs.mix_res = (int32_t)(J.flags >> 1);
+            fs.base = J.base; fs.stride = stride;
+            fs.set_mix((int32_t)(J.flags >> 1), (J.flags & 1u) != 0);
             fs.valid = J.n;
             EmitSink es;
             es.ag.start(J.n);

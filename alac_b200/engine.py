@@ -22,6 +22,9 @@ ALAC_PARAM_ERROR = -50
 ALAC_CUDA_ERROR = -1000
 MEM_HOST, MEM_DEVICE = 0, 1
 STATE_INT16S = 8 * 2 * 2 * 8
+# torch reports its default stream as handle 0, which the C ABI reads as "the engine's own stream"; the explicit
+# handle of CUDA's legacy default stream (cudaStreamLegacy) keeps the call ordered with torch's work
+CUDA_STREAM_LEGACY = 1
 
 
 class AlacError(RuntimeError):
@@ -202,6 +205,13 @@ class Engine:
     def set_stream(self, cuda_stream_ptr: int = 0):
         self.lib.alac_b200_engine_set_stream(self.h, C.c_void_p(cuda_stream_ptr))
 
+    def _follow_torch_stream(self, tensor):
+        """Device-resident torch tensors are produced on torch's current stream: run the call on that stream
+        so it is ordered after whatever filled them (and before whatever reads the results)."""
+        if _is_torch(tensor) and tensor.is_cuda:
+            import torch
+            self.set_stream(torch.cuda.current_stream(tensor.device).cuda_stream or CUDA_STREAM_LEGACY)
+
     # ------------------------------------------------------------------ encode
     def encode(self, pcm, cfg: EncoderConfig, streams: Optional[Sequence[Tuple[int, int]]] = None,
                coef_state: Optional[np.ndarray] = None, out=None, out_sizes=None) -> EncodeResult:
@@ -212,6 +222,7 @@ class Engine:
         out / out_sizes: optional preallocated outputs (same memory kind as pcm).
         """
         ptr, nbytes, mem = _buf(pcm)
+        self._follow_torch_stream(pcm)
         bpf = cfg.bytes_per_frame
         if nbytes % bpf:
             raise ValueError("pcm size is not a whole number of sample-frames")
@@ -261,6 +272,7 @@ class Engine:
         cfgd = parse_cookie(cookie)
         bpf = {16: 2, 20: 3, 24: 3, 32: 4}[cfgd["bit_depth"]] * cfgd["num_channels"]
         pptr, pbytes, mem = _buf(packets)
+        self._follow_torch_stream(packets)
         sptr, sbytes, smem = _buf(sizes)
         if smem != mem:
             raise ValueError("packets and sizes must live in the same memory kind")

@@ -203,7 +203,6 @@ def run_cuda(args):
     cfg = alac_b200.EncoderConfig(channels=CHANNELS, bit_depth=DEPTH, sample_rate=SAMPLE_RATE, frame_size=FRAME,
                                   frames_per_segment=K_SEGMENT)
     eng = alac_b200.Engine(local)
-    eng.set_stream(torch.cuda.current_stream().cuda_stream)
 
     # ---- corpus: rank r owns frame range [r*T, (r+1)*T) of the global synthetic stream -------------
     parts = []

@@ -82,7 +82,9 @@ int32_t     alac_b200_engine_create(int32_t device, alac_b200_engine **out_engin
 void        alac_b200_engine_destroy(alac_b200_engine *engine);
 const char *alac_b200_last_error(const alac_b200_engine *engine);
 const char *alac_b200_version(void);
-/* make later calls run on `cuda_stream` (a cudaStream_t) instead of the engine's own stream */
+/* make later calls run on `cuda_stream` (a cudaStream_t) instead of the engine's own non-blocking stream; NULL
+   selects the engine's own stream again.  Device buffers must be ready on the stream the call runs on: pass the
+   producer's stream (cudaStreamLegacy for work issued on the legacy default stream). */
 int32_t     alac_b200_engine_set_stream(alac_b200_engine *engine, void *cuda_stream);
 
 /* ---- magic cookie: ALACEncoder::GetMagicCookie, codec/ALACEncoder.cu:1109-1140 ------------- */

@@ -248,3 +248,25 @@ def test_alacconvert_cli(tmp_path, name):
     assert open(caf, "rb").read() == want
     subprocess.run([exe, caf, back], check=True, stdout=subprocess.DEVNULL)
     assert open(back, "rb").read() == open(wav, "rb").read()
+
+
+def test_host_pipeline_matches_device_path(engine, oracle):
+    """Host buffers large enough for several pipelined chunks on several compute streams: same bytes as
+    the single-stream device-resident path, and decode is the identity (K = 1 and K = 3)."""
+    import torch
+    import alac_b200
+    dev = torch.device("cuda", 0)
+    for ch, depth, K in [(1, 16, 1), (2, 24, 3)]:
+        frames = 4096 * 12000 + 777
+        pcm_t = torch.cat([synth.corpus_torch(a, min(1 << 24, frames - a), ch, depth, dev, seed=3) for a in range(0, frames, 1 << 24)])
+        cfg = alac_b200.EncoderConfig(channels=ch, bit_depth=depth, frames_per_segment=K)
+        ref = engine.encode(pcm_t, cfg)
+        pcm_h = pcm_t.cpu().numpy()
+        got = engine.encode(pcm_h, cfg)
+        assert got.num_packets == ref.num_packets > 8192
+        assert np.array_equal(np.asarray(got.sizes, np.uint32), ref.sizes.cpu().numpy().astype(np.uint32))
+        assert np.array_equal(got.packets, ref.packets.cpu().numpy())
+        dec = engine.decode(got.cookie, got.packets, got.sizes)
+        assert dec.status == 0 and np.array_equal(dec.pcm, pcm_h)
+        _check = oracle.Encoder(ch, depth).encode_stream(pcm_h[: 4096 * 6 * cfg.bytes_per_frame], K)
+        assert np.array_equal(got.packets[: _check.packets.nbytes], _check.packets)

@@ -411,4 +411,40 @@ __global__ void __launch_bounds__(256) dec_output_kernel(DecArgs A)
     }
 }
 
+
+// ---- CAF packet table on the device -------------------------------------------------------
+// The 'pakt' chunk stores each packet size as a BER integer (7 bits per byte, high bit = "more",
+// convert-utility/CAFFileALAC.cpp:189-258).  ber_flag_kernel marks the last byte of every entry; an exclusive
+// scan of the marks numbers the entries; ber_value_kernel assembles each entry from the <= 5 bytes that end at
+// its mark; ber_count_kernel finds where the reference's decode loop would stop (a zero size, or a packet that
+// no longer fits the data chunk, convert-utility/main.cu:717).
+__global__ void ber_flag_kernel(const uint8_t *table, uint64_t nbytes, uint32_t *flags)
+{
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < nbytes) flags[i] = (table[i] & 0x80u) ? 0u : 1u;
+}
+
+__global__ void ber_value_kernel(const uint8_t *table, uint64_t nbytes, const uint64_t *entry_of_byte, uint32_t *sizes, uint64_t cap)
+{
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nbytes || (table[i] & 0x80u)) return;
+    const uint64_t k = entry_of_byte[i];
+    if (k >= cap) return;
+    uint32_t v = table[i] & 0x7fu, shift = 7, len = 1;
+    for (uint64_t j = i; j > 0 && (table[j - 1] & 0x80u); j--) {
+        if (++len > 5) { v = 0; break; }                    // ReadBERInteger gives up after 5 bytes (:246-250)
+        v |= (uint32_t)(table[j - 1] & 0x7fu) << shift;
+        shift += 7;
+    }
+    sizes[k] = v;
+}
+
+__global__ void ber_count_kernel(const uint32_t *sizes, const uint64_t *offsets, uint64_t entries, uint64_t data_bytes,
+                                 unsigned long long *first_bad)
+{
+    const uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= entries) return;
+    if (sizes[k] == 0 || offsets[k] + sizes[k] > data_bytes) atomicMin(first_bad, (unsigned long long)k);
+}
+
 }  // namespace alacb

@@ -817,3 +817,63 @@ extern "C" int32_t alac_b200_decode(alac_b200_engine *e, const void *cookie, uin
     }
     return first_err;
 }
+
+// ------------------------------------------------------------------------------------------------
+// CAF packet table -> packet sizes, on the device
+// ------------------------------------------------------------------------------------------------
+extern "C" int32_t alac_b200_ber_table_sizes(alac_b200_engine *e, const void *table, uint64_t table_bytes, int32_t table_mem,
+                                             uint64_t data_bytes, uint32_t *sizes_out, uint64_t sizes_cap, int32_t out_mem,
+                                             uint64_t *out_num_packets)
+{
+    if (!e || !out_num_packets || (!table && table_bytes) || (!sizes_out && sizes_cap)) return ALAC_B200_PARAM_ERROR;
+    e->err.clear();
+    *out_num_packets = 0;
+    if (table_bytes == 0) return ALAC_B200_OK;
+    if (table_bytes > 0x7fffffffull) return ALAC_B200_PARAM_ERROR;
+    CU_CHECK(e, cudaSetDevice(e->device));
+    cudaStream_t st = e->stream;
+    const uint8_t *d_table;
+    if (table_mem == ALAC_B200_MEM_DEVICE) {
+        d_table = static_cast<const uint8_t *>(table);
+    } else {
+        CU_CHECK(e, e->d_packets.reserve((size_t)table_bytes + 64));
+        CU_CHECK(e, cudaMemcpyAsync(e->d_packets.p, table, (size_t)table_bytes, cudaMemcpyHostToDevice, st));
+        d_table = e->d_packets.as<uint8_t>();
+    }
+    // every entry is at least one byte, so there are at most table_bytes entries
+    CU_CHECK(e, e->d_class.reserve((size_t)table_bytes * 4));                 // end-of-entry marks
+    CU_CHECK(e, e->d_pkt_off.reserve(((size_t)table_bytes + 1) * 8));         // entry index of every byte
+    CU_CHECK(e, e->d_sizes.reserve((size_t)table_bytes * 4));                 // decoded sizes
+    CU_CHECK(e, e->d_out_frame.reserve(((size_t)table_bytes + 1) * 8));       // byte offsets of the packets
+    CU_CHECK(e, e->counters.reserve(256));
+    const uint32_t blocks = (uint32_t)((table_bytes + 255) / 256);
+    ber_flag_kernel<<<blocks, 256, 0, st>>>(d_table, table_bytes, e->d_class.as<uint32_t>());
+    scan_u32_to_u64_kernel<<<1, 1024, 0, st>>>(e->d_class.as<uint32_t>(), e->d_pkt_off.as<uint64_t>(), table_bytes, nullptr, 0);
+    CU_CHECK(e, cudaMemsetAsync(e->d_sizes.p, 0, (size_t)table_bytes * 4, st));
+    ber_value_kernel<<<blocks, 256, 0, st>>>(d_table, table_bytes, e->d_pkt_off.as<uint64_t>(), e->d_sizes.as<uint32_t>(), table_bytes);
+    uint64_t entries = 0;
+    CU_CHECK(e, cudaMemcpyAsync(&entries, e->d_pkt_off.as<uint64_t>() + table_bytes, 8, cudaMemcpyDeviceToHost, st));
+    CU_CHECK(e, cudaStreamSynchronize(st));
+    uint64_t n = entries;
+    if (entries) {
+        unsigned long long *d_first = e->counters.as<unsigned long long>() + 16;
+        const unsigned long long init = entries;
+        CU_CHECK(e, cudaMemcpyAsync(d_first, &init, 8, cudaMemcpyHostToDevice, st));
+        scan_u32_to_u64_kernel<<<1, 1024, 0, st>>>(e->d_sizes.as<uint32_t>(), e->d_out_frame.as<uint64_t>(), entries, nullptr, 0);
+        ber_count_kernel<<<(uint32_t)((entries + 255) / 256), 256, 0, st>>>(e->d_sizes.as<uint32_t>(), e->d_out_frame.as<uint64_t>(), entries,
+                                                                          data_bytes, d_first);
+        unsigned long long first = 0;
+        CU_CHECK(e, cudaMemcpyAsync(&first, d_first, 8, cudaMemcpyDeviceToHost, st));
+        CU_CHECK(e, cudaStreamSynchronize(st));
+        n = first;
+    }
+    CU_CHECK(e, cudaGetLastError());
+    if (n > sizes_cap) { e->err = "sizes capacity exceeded"; return ALAC_B200_PARAM_ERROR; }
+    if (n) {
+        CU_CHECK(e, cudaMemcpyAsync(sizes_out, e->d_sizes.p, (size_t)n * 4,
+                                    out_mem == ALAC_B200_MEM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, st));
+        CU_CHECK(e, cudaStreamSynchronize(st));
+    }
+    *out_num_packets = n;
+    return ALAC_B200_OK;
+}

@@ -91,6 +91,8 @@ def load_library():
     lib.alac_b200_encode.restype = i32
     lib.alac_b200_decode.argtypes = [vp, vp, u32, vp, vp, u64, i32, vp, u64, vp, vp, i32, C.POINTER(u64), C.POINTER(Stats)]
     lib.alac_b200_decode.restype = i32
+    lib.alac_b200_ber_table_sizes.argtypes = [vp, vp, u64, i32, u64, vp, u64, i32, C.POINTER(u64)]
+    lib.alac_b200_ber_table_sizes.restype = i32
     _lib = lib
     return lib
 
@@ -265,6 +267,24 @@ class Engine:
         if st:
             raise AlacError(st, self._err())
         return EncodeResult(magic_cookie(cfg), out[:nb.value], out_sizes[:npk.value], npk.value, nb.value, stats.as_dict())
+
+    # ------------------------------------------------------------------ CAF packet table
+    def ber_table_sizes(self, table, data_bytes: int):
+        """BER packet table of a CAF 'pakt' chunk (uint8 numpy array or torch CUDA tensor) -> packet sizes,
+        parsed on the GPU.  Output lives where the table lives."""
+        tptr, tbytes, mem = _buf(table)
+        self._follow_torch_stream(table)
+        if mem == MEM_DEVICE:
+            import torch
+            out = torch.empty(max(tbytes, 1), dtype=torch.int32, device=table.device)
+        else:
+            out = np.empty(max(tbytes, 1), np.uint32)
+        n = C.c_uint64(0)
+        st = self.lib.alac_b200_ber_table_sizes(self.h, C.c_void_p(tptr), tbytes, mem, data_bytes, C.c_void_p(_buf(out)[0]),
+                                                max(tbytes, 1), mem, C.byref(n))
+        if st:
+            raise AlacError(st, self._err())
+        return out[:n.value]
 
     # ------------------------------------------------------------------ decode
     def decode(self, cookie: bytes, packets, sizes, out=None, raise_on_error: bool = True) -> DecodeResult:

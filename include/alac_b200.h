@@ -134,6 +134,17 @@ int32_t alac_b200_decode(alac_b200_engine *engine, const void *cookie, uint32_t 
                          uint64_t *out_sample_frames,
                          alac_b200_stats *stats);
 
+/* ---- CAF packet table on the device ------------------------------------------------ */
+/*
+ * Turns the BER-coded size table of a CAF 'pakt' chunk (convert-utility/CAFFileALAC.cpp:189-258) into
+ * packet_sizes[] with GPU kernels (mark entry ends, scan, assemble), stopping where the reference's decode
+ * loop stops (convert-utility/main.cu:717: a zero size, or a packet that no longer fits data_bytes).
+ * The result can be passed straight to alac_b200_decode(..., in_mem = ALAC_B200_MEM_DEVICE).
+ */
+int32_t alac_b200_ber_table_sizes(alac_b200_engine *engine, const void *table, uint64_t table_bytes, int32_t table_mem,
+                                  uint64_t data_bytes, uint32_t *sizes_out, uint64_t sizes_cap, int32_t out_mem,
+                                  uint64_t *out_num_packets);
+
 /* parse a cookie on the host (no GPU work): fills the 11 ALACSpecificConfig fields in order
    frameLength, compatibleVersion, bitDepth, pb, mb, kb, numChannels, maxRun, maxFrameBytes,
    avgBitRate, sampleRate (codec/ALACAudioTypes.h:162-176) */

@@ -270,3 +270,36 @@ def test_host_pipeline_matches_device_path(engine, oracle):
         assert dec.status == 0 and np.array_equal(dec.pcm, pcm_h)
         _check = oracle.Encoder(ch, depth).encode_stream(pcm_h[: 4096 * 6 * cfg.bytes_per_frame], K)
         assert np.array_equal(got.packets[: _check.packets.nbytes], _check.packets)
+
+
+def test_ber_table_on_device(engine):
+    """Device-side parse of a CAF packet table (N3): sizes, stop at a zero entry, stop when the data runs out."""
+    import torch
+    from tests import caf_ref
+    rng = np.random.default_rng(1)
+    sizes = np.concatenate([rng.integers(1, 128, 300), rng.integers(128, 16384, 3000), rng.integers(16384, 200000, 500),
+                            [127, 128, 16383, 16384, 2097151, 2097152]]).astype(np.uint32)
+    rng.shuffle(sizes)
+    table = np.frombuffer(b"".join(caf_ref.ber(int(s)) for s in sizes), np.uint8).copy()
+    total = int(sizes.astype(np.int64).sum())
+    got = engine.ber_table_sizes(table, total)
+    assert np.array_equal(got, sizes)
+    got_d = engine.ber_table_sizes(torch.from_numpy(table).cuda(), total)
+    assert np.array_equal(got_d.cpu().numpy().astype(np.uint32), sizes)
+    # trailing zero padding (the worst-case sized table of the writer) ends the list
+    assert np.array_equal(engine.ber_table_sizes(np.concatenate([table, np.zeros(40, np.uint8)]), total), sizes)
+    # data chunk shorter than the table claims: stop at the first packet that does not fit
+    cut = int(sizes[:1000].astype(np.int64).sum()) + 5
+    assert np.array_equal(engine.ber_table_sizes(table, cut), sizes[:1000])
+
+
+def test_decode_from_caf_table(engine):
+    """Config-5 path: packets addressed through the BER table of a CAF file, all on the device."""
+    import torch
+    from tests import caf_ref
+    g = np.load([p for p in _GOLDEN if "music_stereo32_k1" in p][0])
+    table = np.frombuffer(b"".join(caf_ref.ber(int(s)) for s in g["sizes"]), np.uint8).copy()
+    t_table, t_data = torch.from_numpy(table).cuda(), torch.from_numpy(g["packets"]).cuda()
+    sizes = engine.ber_table_sizes(t_table, t_data.numel())
+    dec = engine.decode(bytes(g["cookie"]), t_data, sizes)
+    assert dec.status == 0 and np.array_equal(dec.pcm.cpu().numpy(), g["pcm"])

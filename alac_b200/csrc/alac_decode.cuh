@@ -4,16 +4,18 @@
 //                       packet's sample count (partial-frame field), so output offsets can be scanned.
 //                       Also classifies the packet by predictor orders; dec_perm_kernel turns the
 //                       classes into a lane -> packet permutation so warps run uniform tap counts.
-//   dec_lane_kernel     one lane per packet: the serial part of ALACDecoder::Decode
-//                       (codec/ALACDecoder.cu:571-1002): element loop, header parse, dyn_decomp and
-//                       unpc_block fused per sample.  Each channel's int32 samples (u / v / mono) go
-//                       to a scratch laid out [group of 32 packets][channel][sample][lane], so every
-//                       store of a warp is one 128-byte line; a DecChanMeta per channel says how to
-//                       finish it.  The bitstream arrives through a cp.async shared-memory ring.
-//   dec_output_kernel   the data-parallel part (codec/ALACDecoder.cu:193-495 unmixNN /
-//                       copyPredictorToNN): 32 packets x 32 samples tiles are transposed through
-//                       shared memory, un-mixed, merged with the shift bytes read straight from the
-//                       packet, packed and stored with coalesced writes.
+//   dec_entropy_kernel  one lane per packet: the serial walk through the packet's bits
+//                       (codec/ALACDecoder.cu:571-1002): element loop, header parse, dyn_decomp, escape
+//                       samples.  Each channel's residuals go to a scratch laid out
+//                       [group of 32 packets][channel][sample][lane], so every store of a warp is one
+//                       128-byte line; a DecChanMeta / DecChanHdr per channel says how to finish it.  The
+//                       bitstream arrives through a cp.async shared-memory ring read by a branch-free window.
+//   dec_finish_kernel   one lane per (packet, element): unpc_block, then the data-parallel tail
+//                       (codec/ALACDecoder.cu:193-495 unmixNN / copyPredictorToNN).  Residual tiles of 32 samples x
+//                       32 packets stream through shared memory (cp.async, one tile ahead); the predictor runs down
+//                       each lane's column in place, then the warp flips roles (lane = sample) to un-mix, merge
+//                       the shift bytes read straight from the packet, pack and store each packet's 32
+//                       sample-frames as one contiguous run.
 #pragma once
 #include "alac_device.cuh"
 
@@ -34,9 +36,10 @@ struct DecArgs {
     uint32_t *pkt_class, *pkt_rank, *class_count, *perm;
     int32_t *chan_scratch;        // [group][channel][frame_length][32]
     struct DecChanMeta *chan_meta; // [packet][channel]
+    struct DecChanHdr *chan_hdr;   // [packet][channel]
 };
 
-// how dec_output_kernel finishes one channel of one packet
+// how dec_finish_kernel finishes one channel of one packet
 enum : uint32_t { CH_ZERO = 0, CH_MONO = 1, CH_PAIR_U = 2, CH_PAIR_V = 3 };
 struct DecChanMeta {
     uint32_t n;             // samples
@@ -108,12 +111,19 @@ __global__ void dec_perm_kernel(DecArgs A)
     A.perm[A.pkt_base + first + A.pkt_rank[p]] = p;
 }
 
+// what the entropy kernel hands to the predictor kernel for one channel of one packet
+struct DecChanHdr {
+    uint8_t mode, den_shift, num, chan_bits;    // num = kRawChannel: samples are final (escape element), no predictor
+    int16_t coefs[32];
+};
+constexpr uint32_t kRawChannel = 0xffu;
+
 struct ChanHeader {
     uint32_t mode, den_shift, pb_factor, num;
     int16_t coefs[32];
 };
 
-__device__ __forceinline__ void read_chan_header(BitReader &br, ChanHeader &h)
+__device__ __forceinline__ void read_chan_header(BitPeek &br, ChanHeader &h)
 {
     uint32_t hb = br.get(8);                        // codec/ALACDecoder.cu:660-669
     h.mode = hb >> 4;
@@ -124,40 +134,201 @@ __device__ __forceinline__ void read_chan_header(BitReader &br, ChanHeader &h)
     for (uint32_t i = 0; i < h.num; i++) h.coefs[i] = (int16_t)br.get(16);
 }
 
-// dyn_decomp + unpc_block for one channel, streamed; out(j, sample) receives the n samples.
-template <int TAPS, bool WRAP, class Out>
-__device__ __forceinline__ void decode_channel_fast(BitReader &br, uint32_t cap_bits, AgDec &ag, uint32_t n,
-                                                    const ChanHeader &h, uint32_t chanshift, Out &out)
+__device__ __forceinline__ void store_chan_hdr(DecChanHdr *dst, const ChanHeader &h, uint32_t chan_bits)
+{
+    dst->mode = (uint8_t)h.mode;
+    dst->den_shift = (uint8_t)h.den_shift;
+    dst->num = (uint8_t)h.num;
+    dst->chan_bits = (uint8_t)chan_bits;
+    for (uint32_t i = 0; i < h.num; i++) dst->coefs[i] = h.coefs[i];
+}
+
+// dyn_decomp for one channel (codec/ag_dec.c:272-362): n residuals -> this lane's column of the channel tile
+__device__ __forceinline__ int32_t entropy_channel(BitReader &br, BitPeek &bp, uint32_t cap_bits, const DecArgs &A, uint32_t n,
+                                                   uint32_t chan_bits, const ChanHeader &h, int32_t *dst)
+{
+    br.seek(bp.pos);
+    AgDec ag;
+    ag.start(br, n, A.mb, (A.pb * h.pb_factor) / 4, A.kb, chan_bits);       // codec/ALACDecoder.cu:682
+    for (uint32_t j = 0; j < n; j++) {
+        dst[(size_t)j * 32u] = ag.next(br, cap_bits);
+        if ((j & (kTopUpEvery - 1u)) == kTopUpEvery - 1u) br.top_up();
+    }
+    // dyn_decomp's exit check "cur <= end" (codec/ag_dec.c:359)
+    if (!ag.status && (br.pos >> 3) > (cap_bits >> 3)) ag.status = -50;
+    bp.pos = br.pos;
+    return ag.status;
+}
+
+// ---- entropy kernel: one lane per packet ---------------------------------------------------------------------
+// The serial walk through the packet's bits (codec/ALACDecoder.cu:571-1002): element loop, headers, Golomb
+// streams, escape samples.  Residuals go to the channel tiles, headers to chan_hdr / chan_meta.
+template <int DEPTH>
+__global__ void __launch_bounds__(kRingStride) dec_entropy_kernel(DecArgs A)
+{
+    __shared__ uint32_t s_ring[kRingSlots][kRingStride];
+    const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
+    if (tid >= A.num_packets) return;
+    const uint32_t pkt = A.perm[A.pkt_base + tid];
+    const uint32_t nch = A.num_channels;
+    const uint32_t size = A.pkt_size[pkt];
+    const uint32_t cap_bits = size * 8u;
+    const uint32_t slot_samples = A.pkt_samples[pkt];
+    const uint32_t F = A.frame_length;
+    int32_t *tile0 = A.chan_scratch + ((size_t)(tid >> 5) * nch * F) * 32u + (tid & 31u);
+    DecChanMeta *meta = A.chan_meta + (size_t)pkt * nch;
+    DecChanHdr *hdrs = A.chan_hdr + (size_t)pkt * nch;
+    for (uint32_t c = 0; c < nch; c++) {            // channels that never arrive are zero-filled (:972-998)
+        DecChanMeta z;
+        z.n = slot_samples; z.shift_pos = 0; z.kind = CH_ZERO; z.shift = 0; z.mix_res = 0; z.mix_bits = 0;
+        meta[c] = z;
+    }
+    BitPeek br;             // headers, escape samples
+    br.start(A.packets + A.pkt_off[pkt], size);
+    BitReader gr;           // Golomb streams
+    gr.start(A.packets + A.pkt_off[pkt], size, &s_ring[0][threadIdx.x]);
+
+    uint32_t n = F;
+    uint32_t channel_index = 0;
+    int32_t status = 0;
+    ChanHeader hu, hv;
+
+    while (status == 0) {
+        if (!((br.pos >> 3) < size)) { status = -50; break; }                   // :615
+        const uint32_t tag = br.get(3);
+        if (tag == ID_SCE || tag == ID_LFE || tag == ID_CPE) {
+            const bool pair = (tag == ID_CPE);
+            if (pair && channel_index + 2 > nch) break;                         // :759-760
+            if (!pair && channel_index >= nch) { status = -50; break; }
+            br.pos += 4;                                                         // element instance tag
+            if (br.get(12) != 0) { status = -50; break; }                       // :633
+            const uint32_t hb = br.get(4);
+            const uint32_t partial = hb >> 3;
+            const uint32_t bytes_shifted = (hb >> 1) & 3u;
+            if (bytes_shifted == 3) { status = -50; break; }                    // :641
+            const uint32_t escape = hb & 1u;
+            if (partial) { n = br.get(16) << 16; n |= br.get(16); }             // :650-654
+            if (n > slot_samples) { status = -50; break; }
+            DecChanMeta mu;
+            mu.n = n; mu.shift_pos = 0; mu.kind = pair ? CH_PAIR_U : CH_MONO; mu.shift = 0; mu.mix_res = 0; mu.mix_bits = 0;
+            int32_t *du = tile0 + (size_t)channel_index * F * 32u;
+            int32_t *dv = du + (size_t)F * 32u;
+            if (!escape) {
+                const uint32_t chan_bits = DEPTH - bytes_shifted * 8 + (pair ? 1u : 0u);
+                mu.mix_bits = (uint8_t)br.get(8);
+                mu.mix_res = (int8_t)br.get(8);
+                read_chan_header(br, hu);
+                if (pair) read_chan_header(br, hv);
+                if (bytes_shifted) {                                            // :675-679, :818-822
+                    mu.shift = (uint8_t)(bytes_shifted * 8);
+                    mu.shift_pos = br.pos;
+                    br.pos += mu.shift * (pair ? 2u : 1u) * n;
+                }
+                store_chan_hdr(&hdrs[channel_index], hu, chan_bits);
+                status = entropy_channel(gr, br, cap_bits, A, n, chan_bits, hu, du);
+                if (status == 0 && pair) {
+                    store_chan_hdr(&hdrs[channel_index + 1], hv, chan_bits);
+                    status = entropy_channel(gr, br, cap_bits, A, n, chan_bits, hv, dv);
+                }
+            } else {
+                // uncompressed element (:697-727, :856-896): raw samples, pairs interleaved
+                const uint32_t sh = 32u - DEPTH;
+                hdrs[channel_index].num = (uint8_t)kRawChannel;
+                if (pair) hdrs[channel_index + 1].num = (uint8_t)kRawChannel;
+                for (uint32_t j = 0; j < n; j++) {
+                    du[(size_t)j * 32u] = (int32_t)(br.get(DEPTH) << sh) >> sh;
+                    if (pair) dv[(size_t)j * 32u] = (int32_t)(br.get(DEPTH) << sh) >> sh;
+                }
+            }
+            if (status) break;
+            meta[channel_index] = mu;
+            if (pair) { mu.kind = CH_PAIR_V; meta[channel_index + 1] = mu; }
+            channel_index += pair ? 2u : 1u;
+        } else if (tag == ID_CCE || tag == ID_PCE) {
+            status = -50;                                                       // :932-939
+        } else if (tag == ID_DSE) {                                             // :1033-1059
+            br.pos += 4;
+            const uint32_t align = br.get(1);
+            uint32_t count = br.get(8);
+            if (count == 255) count += br.get(8);
+            if (align && (br.pos & 7u)) br.pos += 8u - (br.pos & 7u);
+            br.pos += count * 8;
+            if ((br.pos >> 3) > size) status = -50;
+        } else if (tag == ID_FIL) {                                             // :1012-1027
+            int32_t count = (int32_t)br.get(4);
+            if (count == 15) count += (int32_t)br.get(8) - 1;
+            br.pos += (uint32_t)count * 8;
+            if ((br.pos >> 3) > size) status = -50;
+        } else {
+            break;                                                              // ID_END :955-961
+        }
+        if (channel_index >= nch) break;                                        // :966-967
+    }
+    cp_async_wait<0>();
+    A.pkt_status[pkt] = status;
+}
+
+// ---- finish kernel: predictor + un-mix + output, one lane per (packet, element) -------------------------------------
+// unpc_block (codec/dp_dec.c:55-381), then unmixNN / copyPredictorToNN (codec/ALACDecoder.cu:193-495).
+// A warp is one (group of 32 packets, channel slot c); lane = packet.  A lane whose slot c is the U of a pair also
+// owns the V channel (slot c + 1); lanes whose slot is a V have nothing to do (warps of pure-V slots exit at once).
+// The frame is walked in tiles of 32 samples:
+//   1. the tile's residual rows (128 B each: 32 lanes) arrive in shared memory by 16-byte cp.async, one tile
+//      ahead of the arithmetic (a whole tile of predictor work hides the HBM latency);
+//   2. serial phase: every lane runs the predictor down its own column, in place (conflict-free: bank == lane);
+//   3. parallel phase: the roles flip -- lane = sample, loop over the 32 packets -- so each packet's 32 finished
+//      sample-frames are un-mixed, merged with their shift bytes, packed and stored as one contiguous run.
+// The class permutation makes the lanes of a warp run the same tap counts.
+constexpr uint32_t kFinWarps = 1;      // one-warp CTAs: warps of V-only slots exit at once and hold no shared memory
+constexpr uint32_t kTileRows = 32;
+constexpr uint32_t kTilePitch = 36;     // words per row: 32 lanes + 4 pad keeps rows 16-byte aligned and the
+                                        // transposed read of phase 3 at 4-way bank conflicts at most
+constexpr uint32_t kTileWords = kTileRows * kTilePitch;
+
+enum : uint32_t { PM_PASS = 0, PM_FAST4 = 1, PM_FAST8 = 2, PM_WRAP = 4 };
+struct PredState { int32_t a[8]; int32_t hist[9]; };
+
+// rows [r0, r1) of the lane's tile column; absolute sample index of row r is j0 + r
+template <int TAPS, bool WRAP>
+__device__ __forceinline__ void unpc_rows(PredState &s, int32_t *col, uint32_t j0, uint32_t r0, uint32_t r1, uint32_t chanshift)
 {
     int32_t a[TAPS], hist[TAPS + 1];
 #pragma unroll
-    for (int k = 0; k < TAPS; k++) a[k] = h.coefs[k];
+    for (int k = 0; k < TAPS; k++) a[k] = s.a[k];
 #pragma unroll
-    for (int k = 0; k <= TAPS; k++) hist[k] = 0;
-    int32_t prev = 0;
-    const uint32_t warm = min(n, (uint32_t)TAPS + 1u);
-    for (uint32_t j = 0; j < warm; j++) {           // codec/dp_dec.c:65, :97-101
-        const int32_t r = ag.next(br, cap_bits);
-        const int32_t x = j ? sext_bits(r + prev, chanshift) : r;
-        out(j, x);
+    for (int k = 0; k <= TAPS; k++) hist[k] = s.hist[k];
+    uint32_t r = r0;
+    // warm-up samples 0..TAPS: first differences (codec/dp_dec.c:65, :97-101)
+    for (; r < r1 && j0 + r <= (uint32_t)TAPS; r++) {
+        const int32_t res = col[r * kTilePitch];
+        const int32_t x = (j0 + r) ? sext_bits(res + hist[0], chanshift) : res;
+        col[r * kTilePitch] = x;
 #pragma unroll
         for (int k = TAPS; k > 0; k--) hist[k] = hist[k - 1];
         hist[0] = x;
-        prev = x;
     }
-    for (uint32_t j = TAPS + 1; j < n; j++) {
-        const int32_t r = ag.next(br, cap_bits);
-        out(j, predict_dec_step<TAPS, WRAP>(r, hist, a, chanshift));
+#pragma unroll 2
+    for (; r < r1; r++) col[r * kTilePitch] = predict_dec_step<TAPS, WRAP>(col[r * kTilePitch], hist, a, chanshift);
+#pragma unroll
+    for (int k = 0; k < TAPS; k++) s.a[k] = a[k];
+#pragma unroll
+    for (int k = 0; k <= TAPS; k++) s.hist[k] = hist[k];
+}
+
+__device__ __forceinline__ void unpc_rows_any(uint32_t mode, PredState &s, int32_t *col, uint32_t j0, uint32_t r0, uint32_t r1, uint32_t chanshift)
+{
+    switch (mode) {
+    case PM_FAST4: unpc_rows<4, false>(s, col, j0, r0, r1, chanshift); break;
+    case PM_FAST8: unpc_rows<8, false>(s, col, j0, r0, r1, chanshift); break;
+    case PM_FAST4 | PM_WRAP: unpc_rows<4, true>(s, col, j0, r0, r1, chanshift); break;
+    case PM_FAST8 | PM_WRAP: unpc_rows<8, true>(s, col, j0, r0, r1, chanshift); break;
+    default: break;
     }
 }
 
-// any numactive 0..31, any denShift, mode != 0 (codec/dp_dec.c:67-95, :335-380; codec/ALACDecoder.cu:686-694)
-// Everything is taken BY VALUE (and the reader / coder state handed back) so that this rarely-run,
-// out-of-line routine does not force the hot objects of the fast paths into local memory.
-struct GeneralState { BitReader br; AgDec ag; };
-template <class Out>
-__device__ __noinline__ GeneralState decode_channel_general(BitReader br, uint32_t cap_bits, AgDec ag, uint32_t n,
-                                                            ChanHeader h, uint32_t chanshift, Out out)
+// any numactive 0..31, any denShift, mode != 0 (codec/dp_dec.c:67-95, :335-380; codec/ALACDecoder.cu:686-694):
+// in place on the lane's column of the channel tile in global memory
+__device__ __noinline__ void unpc_general(int32_t *col, uint32_t n, DecChanHdr h, uint32_t chanshift)
 {
     int32_t ring[32];
     for (int k = 0; k < 32; k++) ring[k] = 0;
@@ -167,7 +338,7 @@ __device__ __noinline__ GeneralState decode_channel_general(BitReader br, uint32
     int32_t pre = 0;        // running value of the mode != 0 first-difference pass
     int32_t prev = 0;
     for (uint32_t j = 0; j < n; j++) {
-        int32_t r = ag.next(br, cap_bits);
+        int32_t r = col[(size_t)j * 32u];
         if (h.mode != 0) {                          // unpc_block(pred, pred, n, nil, 31, chanBits, 0)
             r = j ? sext_bits(r + pre, chanshift) : r;
             pre = r;
@@ -203,214 +374,171 @@ __device__ __noinline__ GeneralState decode_channel_general(BitReader br, uint32
         }
         ring[j & 31u] = x;
         prev = x;
-        out(j, x);
+        col[(size_t)j * 32u] = x;
     }
-    GeneralState gs;
-    gs.br = br;
-    gs.ag = ag;
-    return gs;
 }
 
-template <class Out>
-__device__ __forceinline__ int32_t decode_channel(BitReader &br, uint32_t cap_bits, const DecArgs &A, uint32_t n,
-                                                  uint32_t chan_bits, ChanHeader &h, Out &out)
+// per-lane predictor set-up for one channel; returns the PM_* mode.  Channels the register paths do not cover
+// are finished right here, in place in global memory, and then pass through the tiles untouched.
+__device__ __forceinline__ uint32_t pred_setup(const DecChanHdr *hp, uint32_t n, int32_t *gcol, PredState &s)
 {
-    AgDec ag;
-    ag.start(br, n, A.mb, (A.pb * h.pb_factor) / 4, A.kb, chan_bits);       // codec/ALACDecoder.cu:682
-    const uint32_t chanshift = 32u - chan_bits;
-    // coefficients move by at most 1 per sample: if max|a| + n stays inside int16 no update can wrap and
-    // the cheaper no-wrap step is exact
-    int32_t amax = 0;
-    for (uint32_t i = 0; i < h.num; i++) amax = max(amax, abs((int32_t)h.coefs[i]));
-    const bool safe = (uint32_t)amax + n <= 32767u;
-    const bool fast = h.mode == 0 && h.den_shift == kDenShift;
-    if (fast && h.num == 4) {
-        if (safe) decode_channel_fast<4, false>(br, cap_bits, ag, n, h, chanshift, out);
-        else decode_channel_fast<4, true>(br, cap_bits, ag, n, h, chanshift, out);
-    } else if (fast && h.num == 8) {
-        if (safe) decode_channel_fast<8, false>(br, cap_bits, ag, n, h, chanshift, out);
-        else decode_channel_fast<8, true>(br, cap_bits, ag, n, h, chanshift, out);
-    } else {
-        const GeneralState gs = decode_channel_general(br, cap_bits, ag, n, h, chanshift, out);
-        br = gs.br;
-        ag = gs.ag;
+    const uint32_t num = hp->num;
+#pragma unroll
+    for (int k = 0; k < 9; k++) s.hist[k] = 0;
+#pragma unroll
+    for (int k = 0; k < 8; k++) s.a[k] = 0;
+    if (num == kRawChannel) return PM_PASS;
+    const uint32_t chanshift = 32u - hp->chan_bits;
+    if (hp->mode == 0 && hp->den_shift == kDenShift && (num == 4 || num == 8)) {
+        // coefficients move by at most 1 per sample: if max|a| + n stays inside int16 no update can wrap and
+        // the cheaper no-wrap step is exact
+        int32_t amax = 0;
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            if ((uint32_t)k < num) { s.a[k] = hp->coefs[k]; amax = max(amax, abs(s.a[k])); }
+        }
+        const bool safe = (uint32_t)amax + n <= 32767u;
+        return (num == 4 ? PM_FAST4 : PM_FAST8) | (safe ? 0u : (uint32_t)PM_WRAP);
     }
-    // dyn_decomp's exit check "cur <= end" (codec/ag_dec.c:359)
-    if (!ag.status && (br.pos >> 3) > (cap_bits >> 3)) ag.status = -50;
-    return ag.status;
+    unpc_general(gcol, n, *hp, chanshift);
+    __threadfence();        // other lanes of the warp copy these words into the tiles
+    return PM_PASS;
 }
 
-// channel samples -> scratch [sample][lane]: one coalesced line per warp store
-struct ScratchOut {
-    int32_t *dst;           // this lane's column of the channel's [frame_length][32] tile
-    __device__ __forceinline__ void operator()(uint32_t j, int32_t v) { dst[(size_t)j * 32u] = v; }
+struct FinMeta {
+    uint64_t out_frame;
+    const uint8_t *pkt;
+    uint32_t pkt_size, n, shift_pos;
+    uint8_t kind, shift, mix_bits;
+    int8_t mix_res;
 };
 
-template <int DEPTH>
-__global__ void __launch_bounds__(kRingStride) dec_lane_kernel(DecArgs A)
+// 16-byte cp.async with zero-fill (src_bytes = 0 reads nothing)
+__device__ __forceinline__ void cp_async_16(uint32_t smem_dst, const void *gsrc, uint32_t src_bytes)
 {
-    __shared__ uint32_t s_ring[kRingSlots][kRingStride];
-    const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
-    if (tid >= A.num_packets) return;
-    const uint32_t pkt = A.perm[A.pkt_base + tid];
-    const uint32_t nch = A.num_channels;
-    const uint32_t size = A.pkt_size[pkt];
-    const uint32_t cap_bits = size * 8u;
-    const uint32_t slot_samples = A.pkt_samples[pkt];
-    const uint32_t F = A.frame_length;
-    int32_t *tile0 = A.chan_scratch + ((size_t)(tid >> 5) * nch * F) * 32u + (tid & 31u);
-    DecChanMeta *meta = A.chan_meta + (size_t)pkt * nch;
-    for (uint32_t c = 0; c < nch; c++) {            // channels that never arrive are zero-filled (:972-998)
-        DecChanMeta z;
-        z.n = slot_samples; z.shift_pos = 0; z.kind = CH_ZERO; z.shift = 0; z.mix_res = 0; z.mix_bits = 0;
-        meta[c] = z;
-    }
-    BitReader br;
-    br.start(A.packets + A.pkt_off[pkt], size, &s_ring[0][threadIdx.x]);
-
-    uint32_t n = F;
-    uint32_t channel_index = 0;
-    int32_t status = 0;
-    ChanHeader hu, hv;
-
-    while (status == 0) {
-        if (!((br.pos >> 3) < size)) { status = -50; break; }                   // :615
-        const uint32_t tag = br.get(3);
-        if (tag == ID_SCE || tag == ID_LFE || tag == ID_CPE) {
-            const bool pair = (tag == ID_CPE);
-            if (pair && channel_index + 2 > nch) break;                         // :759-760
-            if (!pair && channel_index >= nch) { status = -50; break; }
-            br.pos += 4;                                                        // element instance tag
-            if (br.get(12) != 0) { status = -50; break; }                       // :633
-            const uint32_t hb = br.get(4);
-            const uint32_t partial = hb >> 3;
-            const uint32_t bytes_shifted = (hb >> 1) & 3u;
-            if (bytes_shifted == 3) { status = -50; break; }                    // :641
-            const uint32_t escape = hb & 1u;
-            if (partial) { n = br.get(16) << 16; n |= br.get(16); }             // :650-654
-            if (n > slot_samples) { status = -50; break; }
-            DecChanMeta mu;
-            mu.n = n; mu.shift_pos = 0; mu.kind = pair ? CH_PAIR_U : CH_MONO; mu.shift = 0; mu.mix_res = 0; mu.mix_bits = 0;
-            ScratchOut ou, ov;
-            ou.dst = tile0 + (size_t)channel_index * F * 32u;
-            ov.dst = ou.dst + (size_t)F * 32u;
-            if (!escape) {
-                const uint32_t chan_bits = DEPTH - bytes_shifted * 8 + (pair ? 1u : 0u);
-                mu.mix_bits = (uint8_t)br.get(8);
-                mu.mix_res = (int8_t)br.get(8);
-                read_chan_header(br, hu);
-                if (pair) read_chan_header(br, hv);
-                if (bytes_shifted) {                                            // :675-679, :818-822
-                    mu.shift = (uint8_t)(bytes_shifted * 8);
-                    mu.shift_pos = br.pos;
-                    br.pos += mu.shift * (pair ? 2u : 1u) * n;
-                }
-                status = decode_channel(br, cap_bits, A, n, chan_bits, hu, ou);
-                if (status == 0 && pair) status = decode_channel(br, cap_bits, A, n, chan_bits, hv, ov);
-            } else {
-                // uncompressed element (:697-727, :856-896): raw samples, pairs interleaved
-                const uint32_t sh = 32u - DEPTH;
-                for (uint32_t j = 0; j < n; j++) {
-                    ou(j, (int32_t)(br.get(DEPTH) << sh) >> sh);
-                    if (pair) ov(j, (int32_t)(br.get(DEPTH) << sh) >> sh);
-                }
-            }
-            if (status) break;
-            meta[channel_index] = mu;
-            if (pair) { mu.kind = CH_PAIR_V; meta[channel_index + 1] = mu; }
-            channel_index += pair ? 2u : 1u;
-        } else if (tag == ID_CCE || tag == ID_PCE) {
-            status = -50;                                                       // :932-939
-        } else if (tag == ID_DSE) {                                             // :1033-1059
-            br.pos += 4;
-            const uint32_t align = br.get(1);
-            uint32_t count = br.get(8);
-            if (count == 255) count += br.get(8);
-            if (align && (br.pos & 7u)) br.pos += 8u - (br.pos & 7u);
-            br.pos += count * 8;
-            if ((br.pos >> 3) > size) status = -50;
-        } else if (tag == ID_FIL) {                                             // :1012-1027
-            int32_t count = (int32_t)br.get(4);
-            if (count == 15) count += (int32_t)br.get(8) - 1;
-            br.pos += (uint32_t)count * 8;
-            if ((br.pos >> 3) > size) status = -50;
-        } else {
-            break;                                                              // ID_END :955-961
-        }
-        if (channel_index >= nch) break;                                        // :966-967
-    }
-    A.pkt_status[pkt] = status;
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_dst), "l"(gsrc), "r"(src_bytes) : "memory");
 }
 
-// grid: x = 32-sample tiles of a frame, y = groups of 32 packets (permuted order), z = channel
 template <int DEPTH>
-__global__ void __launch_bounds__(256) dec_output_kernel(DecArgs A)
+__global__ void __launch_bounds__(kFinWarps * 32) dec_finish_kernel(DecArgs A)
 {
-    __shared__ int32_t su[32][33], sv[32][33];
+    __shared__ __align__(16) int32_t s_tile[kFinWarps][2][2][kTileWords];      // [warp][buffer][U / V][row * pitch + lane]
+    __shared__ FinMeta s_meta[kFinWarps][32];
     constexpr uint32_t bps = DepthTraits<DEPTH>::kBytes;
     const uint32_t nch = A.num_channels, F = A.frame_length;
-    const uint32_t group = blockIdx.y, c = blockIdx.z, j0 = blockIdx.x * 32u;
-    const uint32_t tx = threadIdx.x, ty = threadIdx.y;
+    const uint32_t wid = threadIdx.x >> 5, lane = threadIdx.x & 31u;
+    const uint32_t warp = blockIdx.x * kFinWarps + wid;
+    const uint32_t group = warp / nch, c = warp - group * nch;
+    const uint32_t slot = group * 32u + lane;
     const uint32_t stride = nch * bps;
+    // 16-bit stereo: one 32-bit store per sample-frame when the output is 4-byte aligned
+    const bool out_pair32 = (nch == 2) && ((reinterpret_cast<uintptr_t>(A.pcm_out) & 3u) == 0);
+    if (group * 32u >= A.num_packets) return;
 
-    // does any packet of the group need this channel slot written from here? (CH_PAIR_V is written by its U)
-    const uint32_t my_slot = group * 32u + tx;
-    uint32_t kind_x = CH_PAIR_V;
-    if (my_slot < A.num_packets && ty == 0) {
-        const DecChanMeta &m = A.chan_meta[(size_t)A.perm[A.pkt_base + my_slot] * nch + c];
-        kind_x = (j0 < m.n) ? m.kind : (uint32_t)CH_PAIR_V;
-    }
-    const int any = __syncthreads_or(kind_x != CH_PAIR_V);
-    if (!any) return;
-
-    const int32_t *tile_u = A.chan_scratch + ((size_t)(group * nch + c) * F) * 32u;
-    const int32_t *tile_v = tile_u + (size_t)F * 32u;
-    const bool have_v = (c + 1 < nch);
-    for (uint32_t r = ty; r < 32; r += 8) {
-        const uint32_t j = j0 + r;
-        su[r][tx] = j < F ? tile_u[(size_t)j * 32u + tx] : 0;
-        sv[r][tx] = (have_v && j < F) ? tile_v[(size_t)j * 32u + tx] : 0;
-    }
-    __syncthreads();
-
-    const uint32_t j = j0 + tx;
-    for (uint32_t pr = ty; pr < 32; pr += 8) {
-        const uint32_t slot = group * 32u + pr;
-        if (slot >= A.num_packets) break;
-        const uint32_t pkt = A.perm[A.pkt_base + slot];
+    // ---- this lane's packet: what is channel slot c?
+    FinMeta M;
+    M.kind = CH_PAIR_V; M.n = 0; M.out_frame = 0; M.pkt = nullptr; M.pkt_size = 0; M.shift_pos = 0; M.shift = 0; M.mix_bits = 0; M.mix_res = 0;
+    uint32_t pkt = 0;
+    if (slot < A.num_packets) {
+        pkt = A.perm[A.pkt_base + slot];
         const DecChanMeta m = A.chan_meta[(size_t)pkt * nch + c];
-        if (j >= m.n || m.kind == CH_PAIR_V) continue;
-        uint8_t *out = A.pcm_out + (A.out_frame[pkt] + j) * stride + (size_t)c * bps;
-        int32_t l = su[tx][pr];
-        if (m.kind == CH_ZERO) {
-            store_sample<DEPTH>(out, 0);
-            continue;
-        }
-        BitPeek bp;
-        if (m.shift) bp.start(A.packets + A.pkt_off[pkt], A.pkt_size[pkt]);
-        if (m.kind == CH_MONO) {
-            if (m.shift) l = (int32_t)(((uint32_t)l << m.shift) | bp.bits_at(m.shift_pos + j * m.shift, m.shift));   // :436-495
-            store_sample<DEPTH>(out, l);
-        } else {
-            const int32_t v = sv[tx][pr];
-            int32_t r;
-            if (m.mix_res != 0) {                       // :193-223
-                l = l + v - (((int32_t)m.mix_res * v) >> m.mix_bits);
-                r = l - v;
-            } else {
-                r = v;
-            }
-            if (m.shift) {                              // :282-383
-                const uint32_t both = bp.bits_at(m.shift_pos + j * 2u * m.shift, 2u * m.shift);
-                l = (int32_t)(((uint32_t)l << m.shift) | (both >> m.shift));
-                r = (int32_t)(((uint32_t)r << m.shift) | (both & ((1u << m.shift) - 1u)));
-            }
-            store_sample<DEPTH>(out, l);
-            store_sample<DEPTH>(out + bps, r);
-        }
+        M.kind = m.kind; M.n = m.n; M.shift_pos = m.shift_pos; M.shift = m.shift; M.mix_bits = m.mix_bits; M.mix_res = m.mix_res;
+        M.out_frame = A.out_frame[pkt];
+        M.pkt = A.packets + A.pkt_off[pkt];
+        M.pkt_size = A.pkt_size[pkt];
     }
-}
+    if (!__any_sync(0xffffffffu, M.kind != CH_PAIR_V)) return;     // a slot that is a V everywhere: done by its U's warp
+    s_meta[wid][lane] = M;
 
+    int32_t *gtile_u = A.chan_scratch + ((size_t)(group * nch + c) * F) * 32u;
+    int32_t *gtile_v = gtile_u + (size_t)F * 32u;
+    const bool is_pair = (M.kind == CH_PAIR_U);
+    const bool any_pair = __any_sync(0xffffffffu, is_pair);
+    PredState su, sv;
+    uint32_t mode_u = PM_PASS, mode_v = PM_PASS, chanshift = 0;
+    if (M.kind == CH_MONO || is_pair) {
+        const DecChanHdr *hp = A.chan_hdr + (size_t)pkt * nch + c;
+        chanshift = 32u - hp->chan_bits;
+        mode_u = pred_setup(hp, M.n, gtile_u + lane, su);
+        if (is_pair) mode_v = pred_setup(hp + 1, M.n, gtile_v + lane, sv);
+    }
+    const uint32_t n_lane = (M.kind == CH_PAIR_V) ? 0u : M.n;
+    const uint32_t n_max = __reduce_max_sync(0xffffffffu, n_lane);
+    const uint32_t tiles = (n_max + kTileRows - 1) / kTileRows;
+    __syncwarp();
+
+    // a tile = 32 rows x 8 chunks of 16 bytes per channel; lane i takes chunks i, i + 32, ...
+    auto request = [&](uint32_t t) {
+        int32_t *bu = s_tile[wid][t & 1u][0], *bv = s_tile[wid][t & 1u][1];
+#pragma unroll
+        for (uint32_t i = 0; i < 8; i++) {
+            const uint32_t ch = i * 32u + lane, row = ch >> 3, part = ch & 7u;
+            const uint32_t j = t * kTileRows + row;
+            const bool in = j < F && t < tiles;
+            const size_t goff = (size_t)(in ? j : 0u) * 32u + part * 4u;
+            cp_async_16((uint32_t)__cvta_generic_to_shared(bu + row * kTilePitch + part * 4u), gtile_u + goff, in ? 16u : 0u);
+            if (any_pair)
+                cp_async_16((uint32_t)__cvta_generic_to_shared(bv + row * kTilePitch + part * 4u), gtile_v + goff, in ? 16u : 0u);
+        }
+        cp_async_commit();
+    };
+    request(0);
+    request(1);
+    for (uint32_t t = 0; t < tiles; t++) {
+        cp_async_wait<1>();             // tile t is in (only tile t + 1 may still be in flight)
+        __syncwarp();
+        int32_t *bu = s_tile[wid][t & 1u][0], *bv = s_tile[wid][t & 1u][1];
+        const uint32_t j0 = t * kTileRows;
+        // ---- serial phase: lane = packet
+        if (j0 < n_lane) {
+            const uint32_t r1 = min(n_lane - j0, kTileRows);
+            unpc_rows_any(mode_u, su, bu + lane, j0, 0, r1, chanshift);
+            if (is_pair) unpc_rows_any(mode_v, sv, bv + lane, j0, 0, r1, chanshift);
+        }
+        __syncwarp();
+        // ---- parallel phase: lane = sample
+        const uint32_t j = j0 + lane;
+        for (uint32_t pr = 0; pr < 32; pr++) {
+            const FinMeta &m = s_meta[wid][pr];
+            if (m.kind == CH_PAIR_V || j >= m.n) continue;
+            uint8_t *out = A.pcm_out + (m.out_frame + j) * stride + (size_t)c * bps;
+            if (m.kind == CH_ZERO) {
+                store_sample<DEPTH>(out, 0);
+                continue;
+            }
+            int32_t l = bu[lane * kTilePitch + pr];
+            BitPeek bp;
+            if (m.shift) bp.start(m.pkt, m.pkt_size);
+            if (m.kind == CH_MONO) {
+                if (m.shift) l = (int32_t)(((uint32_t)l << m.shift) | bp.bits_at(m.shift_pos + j * m.shift, m.shift));   // :436-495
+                store_sample<DEPTH>(out, l);
+            } else {
+                const int32_t v = bv[lane * kTilePitch + pr];
+                int32_t r;
+                if (m.mix_res != 0) {                       // :193-223
+                    l = l + v - (((int32_t)m.mix_res * v) >> m.mix_bits);
+                    r = l - v;
+                } else {
+                    r = v;
+                }
+                if (m.shift) {                              // :282-383
+                    const uint32_t both = bp.bits_at(m.shift_pos + j * 2u * m.shift, 2u * m.shift);
+                    l = (int32_t)(((uint32_t)l << m.shift) | (both >> m.shift));
+                    r = (int32_t)(((uint32_t)r << m.shift) | (both & ((1u << m.shift) - 1u)));
+                }
+                if (DEPTH == 16 && out_pair32) {
+                    *reinterpret_cast<uint32_t *>(out) = ((uint32_t)l & 0xffffu) | ((uint32_t)r << 16);
+                } else {
+                    store_sample<DEPTH>(out, l);
+                    store_sample<DEPTH>(out + bps, r);
+                }
+            }
+        }
+        __syncwarp();
+        request(t + 2);                 // refills the buffer just drained (an empty group past the last tile)
+    }
+    cp_async_wait<0>();
+}
 
 // ---- CAF packet table on the device -------------------------------------------------------
 // The 'pakt' chunk stores each packet size as a BER integer (7 bits per byte, high bit = "more",

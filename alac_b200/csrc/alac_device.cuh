@@ -303,16 +303,27 @@ struct BitPeek {
     }
 };
 
-// Sequential reader for the serial Golomb decode: the packet's words stream through a private
-// shared-memory ring filled by cp.async (LDGSTS) kAhead words in front of the read position, so the
-// global-load latency never sits on the decode's dependency chain and no register is ever the
-// target of a load in flight.  Ring slot s of this lane is ring[s * kRingStride] (bank == lane).
-constexpr uint32_t kRingSlots = 8;
-constexpr uint32_t kRingAhead = 6;
+// Sequential reader for the serial Golomb decode.  The reader is BRANCH-FREE on the per-symbol path, because the
+// lanes of a warp cross word boundaries at different symbols and any "refill if needed" branch would be taken by a
+// few lanes at almost every symbol (the warp then pays for it every time):
+//   * a 64-bit MSB-first window (hi:lo) with `navail` valid bits; consume() is two funnel shifts;
+//   * refill() tops the window up with the pre-loaded word `nxt` when navail <= 32 -- selects and one predicated
+//     LDS, no branch -- so hi always holds 32 valid bits;
+//   * the packet's words stream through a private shared-memory ring (slot s of this lane is
+//     ring[s * kRingStride], bank == lane) filled by cp.async (LDGSTS).  The ring is topped up at a WARP-UNIFORM
+//     cadence (every kTopUpEvery symbols, top_up()); what one top-up requests is only assumed to have landed after
+//     the NEXT top-up (wait_group 1), so the global-load latency never sits on the decode's dependency chain.
+//     One symbol step consumes at most 9 + 32 bits plus a 25-bit run code = 66 bits, so two periods consume at most
+//     2 * kTopUpEvery * 66 bits = 33 words, well inside the kRingSlots = 64 words requested ahead.
+//   * headers and escape samples are sparse reads and go through BitPeek instead; seek() (synchronous) positions
+//     this reader at the first bit of a Golomb stream.
+constexpr uint32_t kRingSlots = 64;
+constexpr uint32_t kTopUpEvery = 8;
 #ifndef ALAC_DEC_LANES
 #define ALAC_DEC_LANES 128
 #endif
 constexpr uint32_t kRingStride = ALAC_DEC_LANES;     // lanes per CTA of the kernels that use BitReader
+static_assert(2 * kTopUpEvery * 66 + 4 * 32 <= kRingSlots * 32, "ring too small for the top-up cadence");
 
 // 4-byte cp.async with a source size: src_bytes = 0 reads nothing and zero-fills the destination
 __device__ __forceinline__ void cp_async_word(uint32_t smem_dst, const uint32_t *gsrc, uint32_t src_bytes)
@@ -327,39 +338,98 @@ __device__ __forceinline__ uint32_t lds_u32(uint32_t smem_addr)
     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(smem_addr) : "memory");
     return v;
 }
+// v = take ? shared[addr] : v, as a predicated load (never a branch)
+__device__ __forceinline__ void lds_u32_if(uint32_t &v, uint32_t smem_addr, bool take)
+{
+    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %2, 0;\n\t@q ld.shared.u32 %0, [%1];\n\t}"
+                 : "+r"(v) : "r"(smem_addr), "r"((uint32_t)take) : "memory");
+}
+__device__ __forceinline__ uint32_t bfind_u32(uint32_t v)     // index of the highest set bit = 31 - clz(v), v != 0
+{
+    uint32_t r;
+    asm("bfind.u32 %0, %1;" : "=r"(r) : "r"(v));
+    return r;
+}
 
 struct BitReader {
-    const uint32_t *base;
-    uint32_t bias;
+    const uint32_t *base;   // 4-byte aligned address at or before the packet
+    uint32_t bias;          // bit offset of the packet's first bit inside base[0]
     int32_t last_word;      // index of the last word holding packet bytes; -1 for an empty packet
     uint32_t ring;          // shared-memory address of this lane's ring column
-    uint32_t wi;            // word index of w0
-    uint32_t w0, w1, w2;    // byte-swapped words wi, wi+1, wi+2
-    uint32_t pos;
+    uint32_t rd;            // index of the word held in nxt (the next one to enter the window)
+    uint32_t wr;            // next word index to request
+    uint32_t landed;        // words below this index are known to be in the ring
+    uint32_t hi, lo;        // window: the next unread bit is the MSB of hi
+    uint32_t navail;        // valid bits in hi:lo (>= 32 after refill())
+    uint32_t nxt;           // word rd, byte-swapped
+    uint32_t pos;           // bits consumed since the start of the packet
 
+    __device__ __forceinline__ uint32_t slot_addr(uint32_t i) const { return ring + (i & (kRingSlots - 1u)) * (kRingStride * 4u); }
     // branch-free: words past the end are not read, their slot is zero-filled by the copy itself
     __device__ __forceinline__ void issue(uint32_t i)
     {
         const bool in = (int32_t)i <= last_word;
-        cp_async_word(ring + (i & (kRingSlots - 1u)) * (kRingStride * 4u), base + (in ? i : 0u), in ? 4u : 0u);
+        cp_async_word(slot_addr(i), base + (in ? i : 0u), in ? 4u : 0u);
+    }
+    // request everything up to kRingSlots words past the read position (slots of words < rd are free)
+    __device__ __forceinline__ uint32_t request_ahead()
+    {
+        const uint32_t old = wr, limit = rd + kRingSlots;
+        while ((int32_t)(limit - wr) > 0) issue(wr++);
         cp_async_commit();
+        return old;
     }
-    __device__ __forceinline__ uint32_t slot(uint32_t i) const { return bswap32(lds_u32(ring + (i & (kRingSlots - 1u)) * (kRingStride * 4u))); }
-    __device__ __forceinline__ void fill(uint32_t i)
+    // asynchronous top-up: what THIS call requests is only usable after the next one
+    __device__ __forceinline__ void top_up()
     {
-        wi = i;
-#pragma unroll
-        for (uint32_t d = 0; d <= kRingAhead; d++) issue(i + d);
-        cp_async_wait<kRingAhead - 2>();        // all but the 4 newest requests done: words i, i+1, i+2 are in
-        w0 = slot(i); w1 = slot(i + 1); w2 = slot(i + 2);
+        const uint32_t old = request_ahead();
+        cp_async_wait<1>();
+        landed = old;
     }
-    __device__ __forceinline__ void advance()
+    // synchronous top-up: everything requested so far is in
+    __device__ __forceinline__ void prime()
     {
-        wi++;
-        w0 = w1; w1 = w2;
-        issue(wi + kRingAhead);                 // reuses the slot of word wi - 2
-        cp_async_wait<kRingAhead - 2>();        // word wi + 2 is in
-        w2 = slot(wi + 2);
+        request_ahead();
+        cp_async_wait<0>();
+        landed = wr;
+    }
+    __device__ __forceinline__ void consume(uint32_t nbits)     // 0..32 (<= navail)
+    {
+        hi = __funnelshift_lc(lo, hi, nbits);
+        lo = __funnelshift_lc(0u, lo, nbits);
+        navail -= nbits;
+        pos += nbits;
+    }
+    __device__ __forceinline__ void refill()
+    {
+        const bool take = navail <= 32u;
+        // insert nxt below the navail valid bits (lo holds none of them when navail <= 32)
+        const uint32_t add_hi = __funnelshift_rc(nxt, 0u, navail);      // nxt >> navail, 0 at navail = 32
+        const uint32_t new_lo = __funnelshift_rc(0u, nxt, navail);      // low half of (nxt:0) >> navail
+        hi |= take ? add_hi : 0u;
+        lo = take ? new_lo : lo;
+        navail += take ? 32u : 0u;
+        rd += take ? 1u : 0u;
+        lds_u32_if(nxt, slot_addr(rd), take);
+        nxt = take ? bswap32(nxt) : nxt;
+    }
+    // jump to bit position p of the packet (synchronous)
+    __device__ __forceinline__ void seek(uint32_t p)
+    {
+        const uint32_t abs_bit = bias + p, w = abs_bit >> 5;
+        cp_async_wait<0>();         // nothing older may still be writing ring slots
+        pos = p;
+        rd = w;
+        wr = w;
+        prime();
+        hi = bswap32(lds_u32(slot_addr(w)));
+        lo = bswap32(lds_u32(slot_addr(w + 1)));
+        nxt = bswap32(lds_u32(slot_addr(w + 2)));
+        rd = w + 2;
+        navail = 64;
+        consume(abs_bit & 31u);
+        pos = p;
+        refill();
     }
     __device__ __forceinline__ void start(const uint8_t *packet, uint32_t nbytes, uint32_t *ring_column)
     {
@@ -370,69 +440,13 @@ struct BitReader {
         if (!nbytes) base = ring_column;        // never dereferenced (every request has size 0), but keep it sane
         ring = (uint32_t)__cvta_generic_to_shared(ring_column);
         pos = 0;
-        fill(0);
     }
-    __device__ __forceinline__ uint32_t peek32_at(uint32_t p)
-    {
-        const uint32_t abs_bit = bias + p;
-        const uint32_t i = abs_bit >> 5;
-        if (i != wi) {
-            if (i - wi <= 2u) { while (wi != i) advance(); }
-            else fill(i);
-        }
-        return __funnelshift_l(w1, w0, abs_bit & 31u);
-    }
-    __device__ __forceinline__ uint32_t peek32() { return peek32_at(pos); }
-    __device__ __forceinline__ uint32_t get(uint32_t nbits)   // 0..32
-    {
-        if (nbits == 0) return 0;
-        const uint32_t v = peek32() >> (32u - nbits);
-        pos += nbits;
-        return v;
-    }
+    __device__ __forceinline__ uint32_t peek32() const { return hi; }
 };
 
-// codec/ag_dec.c:220-270 dyn_get_32bit
-__device__ __forceinline__ uint32_t ag_get_sample(BitReader &br, uint32_t m, uint32_t k, uint32_t maxbits)
-{
-    const uint32_t window = br.peek32();
-    const uint32_t pre = (uint32_t)__clz((int)~window);
-    uint32_t result;
-    if (pre >= kMaxPrefix) {
-        br.pos += kMaxPrefix;
-        result = br.get(maxbits);
-    } else {
-        result = pre;
-        br.pos += pre + 1;
-        if (k != 1) {
-            const uint32_t v = (window << (pre + 1)) >> (32u - k);
-            br.pos += k - 1;
-            result = pre * m;
-            if (v >= 2) { result += v - 1; br.pos += 1; }
-        }
-    }
-    return result;
-}
-
-// codec/ag_dec.c:171-217 dyn_get
-__device__ __forceinline__ uint32_t ag_get_run(BitReader &br, uint32_t m, uint32_t k)
-{
-    const uint32_t window = br.peek32();
-    const uint32_t pre = (uint32_t)__clz((int)~window);
-    uint32_t result;
-    if (pre >= kMaxPrefix) {
-        result = (window << kMaxPrefix) >> (32u - kRunRawBits);
-        br.pos += kMaxPrefix + kRunRawBits;
-    } else {
-        const uint32_t v = (window << (pre + 1)) >> (32u - k);
-        br.pos += pre + 1 + k;
-        result = pre * m + v - 1;
-        if (v < 2) { result -= (v - 1); br.pos -= 1; }
-    }
-    return result;
-}
-
-// streaming dyn_decomp (codec/ag_dec.c:272-362): next() yields one residual per call
+// streaming dyn_decomp (codec/ag_dec.c:272-362): next() yields one residual per call.  The common symbol
+// (codec/ag_dec.c:220-270 dyn_get_32bit, prefix < 9) is straight-line code; the escape code and the zero-run
+// code (codec/ag_dec.c:171-217 dyn_get) are the only branches.
 struct AgDec {
     uint32_t mb, zmode, pending_zeros, c, count;
     uint32_t pb, kb, wb, max_size;
@@ -441,7 +455,7 @@ struct AgDec {
     __device__ __forceinline__ void start(const BitReader &br, uint32_t n, uint32_t mb0, uint32_t pb_, uint32_t kb_, uint32_t max_size_)
     {
         mb = mb0; zmode = 0; pending_zeros = 0; c = 0; count = n;
-        pb = pb_; kb = kb_; wb = (1u << kb_) - 1u; max_size = max_size_;
+        pb = pb_; kb = kb_; wb = (1u << kb_) - 1u; max_size = min(max_size_, 32u);
         start_rel = br.pos & ~7u;
         status = 0;
     }
@@ -452,22 +466,49 @@ struct AgDec {
         // ag_dec.c:302 "bitPos < maxPos".  An error latches; decoding goes on over zero-filled words (a failed
         // packet's samples are unspecified) so the hot loop carries no early-out.
         if (!((br.pos - start_rel) < cap_bits)) status = -50;
-        uint32_t k = 31u - (uint32_t)__clz((int)((mb >> kQbShift) + 3u));
-        k = min(k, kb);
+        const uint32_t k = min(bfind_u32((mb >> kQbShift) + 3u), kb);
         const uint32_t m = (1u << k) - 1u;
-        const uint32_t n = ag_get_sample(br, m, k, max_size);
+        const uint32_t window = br.peek32();
+        const uint32_t pre = (uint32_t)__clz((int)~window);
+        uint32_t n;
+        if (pre >= kMaxPrefix) {
+            br.consume(kMaxPrefix);
+            br.refill();
+            n = br.peek32() >> (32u - max_size);
+            br.consume(max_size);
+        } else {
+            // k low bits after the prefix's terminating zero; v < 2 means the code was one bit shorter
+            const uint32_t v = (window << (pre + 1u)) >> (32u - k);
+            const uint32_t big = (v >= 2u) ? 1u : 0u;
+            n = pre * m + (big ? v - 1u : 0u);
+            br.consume(pre + k + big);
+        }
+        br.refill();
         const uint32_t nd = n + zmode;
         const int32_t mult = (-(int32_t)(nd & 1u)) | 1;
         const int32_t del = (int32_t)(((nd + 1u) >> 1) * (uint32_t)mult);              // ag_dec.c:313-319
         c++;
-        mb = pb * (n + zmode) + mb - ((pb * mb) >> kQbShift);
+        mb = pb * nd + mb - ((pb * mb) >> kQbShift);
         if (n > kMeanClamp) mb = kMeanClamp;
         zmode = 0;
         if (((mb << 2) < kQb) && (c < count)) {                                          // ag_dec.c:334
             zmode = 1;
-            k = (uint32_t)__clz((int)mb) - 24u + ((mb + 16u) >> 6);
-            const uint32_t mz = ((1u << k) - 1u) & wb;
-            const uint32_t run = ag_get_run(br, mz, k);
+            const uint32_t kz = (uint32_t)__clz((int)mb) - 24u + ((mb + 16u) >> 6);
+            const uint32_t mz = ((1u << kz) - 1u) & wb;
+            const uint32_t w2 = br.peek32();
+            const uint32_t pz = (uint32_t)__clz((int)~w2);
+            uint32_t run;
+            if (pz >= kMaxPrefix) {
+                run = (w2 << kMaxPrefix) >> (32u - kRunRawBits);
+                br.consume(kMaxPrefix + kRunRawBits);
+            } else {
+                const uint32_t v = (w2 << (pz + 1u)) >> (32u - kz);
+                uint32_t nb = pz + 1u + kz;
+                run = pz * mz + v - 1u;
+                if (v < 2u) { run -= (v - 1u); nb -= 1u; }
+                br.consume(nb);
+            }
+            br.refill();
             if (!(c + run <= count)) { status = -50; }                                   // ag_dec.c:341
             else pending_zeros = run;
             if (run >= 65535u) zmode = 0;

@@ -58,7 +58,7 @@ struct alac_b200_engine {
     // encode
     DevBuf pcm, pkt_frame, pkt_samples, seg_first, seg_count, seg_stream, recs, scratch, sizes, offsets, out, state, counters;
     // decode
-    DevBuf d_packets, d_sizes, d_pkt_off, d_pkt_samples, d_out_frame, d_status, d_pcm, d_class, d_rank, d_perm, d_chan, d_meta;
+    DevBuf d_packets, d_sizes, d_pkt_off, d_pkt_samples, d_out_frame, d_status, d_pcm, d_class, d_rank, d_perm, d_chan, d_meta, d_hdr;
     uint32_t launches = 0;
     // per-kernel timers: (start, stop) event pairs, grown on demand, reused across calls
     std::vector<cudaEvent_t> timers;
@@ -222,7 +222,7 @@ void alac_b200_engine_destroy(alac_b200_engine *e)
     cudaStreamSynchronize(e->stream);
     DevBuf *bufs[] = {&e->pcm, &e->pkt_frame, &e->pkt_samples, &e->seg_first, &e->seg_count, &e->seg_stream, &e->recs,
                       &e->scratch, &e->sizes, &e->offsets, &e->out, &e->state, &e->counters, &e->d_packets, &e->d_sizes,
-                      &e->d_pkt_off, &e->d_pkt_samples, &e->d_out_frame, &e->d_status, &e->d_pcm, &e->d_class, &e->d_rank, &e->d_perm, &e->d_chan, &e->d_meta};
+                      &e->d_pkt_off, &e->d_pkt_samples, &e->d_out_frame, &e->d_status, &e->d_pcm, &e->d_class, &e->d_rank, &e->d_perm, &e->d_chan, &e->d_meta, &e->d_hdr};
     for (DevBuf *b : bufs) b->release();
     for (auto &ev : e->ev)
         if (ev) cudaEventDestroy(ev);
@@ -673,6 +673,7 @@ extern "C" int32_t alac_b200_decode(alac_b200_engine *e, const void *cookie, uin
     CU_CHECK(e, e->d_perm.reserve((size_t)P * 4));
     CU_CHECK(e, e->d_chan.reserve(chan_words_per_lane * nlanes * 4));
     CU_CHECK(e, e->d_meta.reserve((size_t)P * nch * sizeof(DecChanMeta)));
+    CU_CHECK(e, e->d_hdr.reserve((size_t)P * nch * sizeof(DecChanHdr)));
     CU_CHECK(e, e->counters.reserve(64 * 4));
 
     CU_CHECK(e, cudaEventRecord(e->ev[0], st));
@@ -729,6 +730,7 @@ extern "C" int32_t alac_b200_decode(alac_b200_engine *e, const void *cookie, uin
     A.perm = e->d_perm.as<uint32_t>();
     A.chan_scratch = e->d_chan.as<int32_t>();
     A.chan_meta = e->d_meta.as<DecChanMeta>();
+    A.chan_hdr = e->d_hdr.as<DecChanHdr>();
 
     std::vector<cudaEvent_t> comp_done, scan_done, t_dec;
     uint64_t total_frames = 0;
@@ -758,13 +760,19 @@ extern "C" int32_t alac_b200_decode(alac_b200_engine *e, const void *cookie, uin
             if (e->h_totals[ci] * bpf > pcm_cap) { e->err = "pcm capacity exceeded"; return ALAC_B200_PARAM_ERROR; }
         }
         t_dec.push_back(e->timer());
-        const dim3 ogrid((frame_length + 31) / 32, (c.cnt + 31) / 32, nch), oblock(32, 8);
         const uint32_t lgrid = (c.cnt + kRingStride - 1) / kRingStride;
+        const uint32_t fgrid = (((c.cnt + 31) / 32) * nch + kFinWarps - 1) / kFinWarps;
         switch (depth) {
-        case 16: dec_lane_kernel<16><<<lgrid, kRingStride, 0, cs>>>(A); dec_output_kernel<16><<<ogrid, oblock, 0, cs>>>(A); break;
-        case 20: dec_lane_kernel<20><<<lgrid, kRingStride, 0, cs>>>(A); dec_output_kernel<20><<<ogrid, oblock, 0, cs>>>(A); break;
-        case 24: dec_lane_kernel<24><<<lgrid, kRingStride, 0, cs>>>(A); dec_output_kernel<24><<<ogrid, oblock, 0, cs>>>(A); break;
-        default: dec_lane_kernel<32><<<lgrid, kRingStride, 0, cs>>>(A); dec_output_kernel<32><<<ogrid, oblock, 0, cs>>>(A); break;
+        case 16: dec_entropy_kernel<16><<<lgrid, kRingStride, 0, cs>>>(A); break;
+        case 20: dec_entropy_kernel<20><<<lgrid, kRingStride, 0, cs>>>(A); break;
+        case 24: dec_entropy_kernel<24><<<lgrid, kRingStride, 0, cs>>>(A); break;
+        default: dec_entropy_kernel<32><<<lgrid, kRingStride, 0, cs>>>(A); break;
+        }
+        switch (depth) {
+        case 16: dec_finish_kernel<16><<<fgrid, kFinWarps * 32, 0, cs>>>(A); break;
+        case 20: dec_finish_kernel<20><<<fgrid, kFinWarps * 32, 0, cs>>>(A); break;
+        case 24: dec_finish_kernel<24><<<fgrid, kFinWarps * 32, 0, cs>>>(A); break;
+        default: dec_finish_kernel<32><<<fgrid, kFinWarps * 32, 0, cs>>>(A); break;
         }
         t_dec.push_back(e->timer());
         e->launches += 2;

@@ -270,16 +270,17 @@ __global__ void __launch_bounds__(kRingStride) dec_entropy_kernel(DecArgs A)
 
 // ---- finish kernel: predictor + un-mix + output, one lane per (packet, element) -------------------------------------
 // unpc_block (codec/dp_dec.c:55-381), then unmixNN / copyPredictorToNN (codec/ALACDecoder.cu:193-495).
-// A warp is one (group of 32 packets, channel slot c); lane = packet.  A lane whose slot c is the U of a pair also
-// owns the V channel (slot c + 1); lanes whose slot is a V have nothing to do (warps of pure-V slots exit at once).
+// A CTA is one (group of 32 packets, channel slot c) and has two warps, lane = packet: warp 0 predicts slot c (a mono
+// channel or the U of a pair), warp 1 the V of the pair in slot c + 1.  CTAs of slots that are a V in every packet
+// exit at once (their U's CTA does the work).
 // The frame is walked in tiles of 32 samples:
 //   1. the tile's residual rows (128 B each: 32 lanes) arrive in shared memory by 16-byte cp.async, one tile
 //      ahead of the arithmetic (a whole tile of predictor work hides the HBM latency);
 //   2. serial phase: every lane runs the predictor down its own column, in place (conflict-free: bank == lane);
-//   3. parallel phase: the roles flip -- lane = sample, loop over the 32 packets -- so each packet's 32 finished
-//      sample-frames are un-mixed, merged with their shift bytes, packed and stored as one contiguous run.
+//   3. parallel phase: the roles flip -- lane = sample, each warp loops over half of the 32 packets -- so a
+//      packet's 32 finished sample-frames are un-mixed, merged with their shift bytes, packed and stored as one
+//      contiguous run.
 // The class permutation makes the lanes of a warp run the same tap counts.
-constexpr uint32_t kFinWarps = 1;      // one-warp CTAs: warps of V-only slots exit at once and hold no shared memory
 constexpr uint32_t kTileRows = 32;
 constexpr uint32_t kTilePitch = 36;     // words per row: 32 lanes + 4 pad keeps rows 16-byte aligned and the
                                         // transposed read of phase 3 at 4-way bank conflicts at most
@@ -420,22 +421,20 @@ __device__ __forceinline__ void cp_async_16(uint32_t smem_dst, const void *gsrc,
 }
 
 template <int DEPTH>
-__global__ void __launch_bounds__(kFinWarps * 32) dec_finish_kernel(DecArgs A)
+__global__ void __launch_bounds__(64) dec_finish_kernel(DecArgs A)
 {
-    __shared__ __align__(16) int32_t s_tile[kFinWarps][2][2][kTileWords];      // [warp][buffer][U / V][row * pitch + lane]
-    __shared__ FinMeta s_meta[kFinWarps][32];
+    __shared__ __align__(16) int32_t s_tile[2][2][kTileWords];     // [buffer][channel c / c + 1][row * pitch + lane]
+    __shared__ FinMeta s_meta[32];
     constexpr uint32_t bps = DepthTraits<DEPTH>::kBytes;
     const uint32_t nch = A.num_channels, F = A.frame_length;
-    const uint32_t wid = threadIdx.x >> 5, lane = threadIdx.x & 31u;
-    const uint32_t warp = blockIdx.x * kFinWarps + wid;
-    const uint32_t group = warp / nch, c = warp - group * nch;
+    const uint32_t w = threadIdx.x >> 5, lane = threadIdx.x & 31u;      // warp w owns channel slot c + w
+    const uint32_t group = blockIdx.x / nch, c = blockIdx.x - group * nch;
     const uint32_t slot = group * 32u + lane;
     const uint32_t stride = nch * bps;
     // 16-bit stereo: one 32-bit store per sample-frame when the output is 4-byte aligned
     const bool out_pair32 = (nch == 2) && ((reinterpret_cast<uintptr_t>(A.pcm_out) & 3u) == 0);
-    if (group * 32u >= A.num_packets) return;
 
-    // ---- this lane's packet: what is channel slot c?
+    // ---- this lane's packet: what is channel slot c?  (both warps read the same records)
     FinMeta M;
     M.kind = CH_PAIR_V; M.n = 0; M.out_frame = 0; M.pkt = nullptr; M.pkt_size = 0; M.shift_pos = 0; M.shift = 0; M.mix_bits = 0; M.mix_res = 0;
     uint32_t pkt = 0;
@@ -447,38 +446,37 @@ __global__ void __launch_bounds__(kFinWarps * 32) dec_finish_kernel(DecArgs A)
         M.pkt = A.packets + A.pkt_off[pkt];
         M.pkt_size = A.pkt_size[pkt];
     }
-    if (!__any_sync(0xffffffffu, M.kind != CH_PAIR_V)) return;     // a slot that is a V everywhere: done by its U's warp
-    s_meta[wid][lane] = M;
+    if (!__any_sync(0xffffffffu, M.kind != CH_PAIR_V)) return;     // a slot that is a V everywhere: done by its U's CTA (both warps agree)
+    if (w == 0) s_meta[lane] = M;
 
-    int32_t *gtile_u = A.chan_scratch + ((size_t)(group * nch + c) * F) * 32u;
-    int32_t *gtile_v = gtile_u + (size_t)F * 32u;
-    const bool is_pair = (M.kind == CH_PAIR_U);
-    const bool any_pair = __any_sync(0xffffffffu, is_pair);
-    PredState su, sv;
-    uint32_t mode_u = PM_PASS, mode_v = PM_PASS, chanshift = 0;
-    if (M.kind == CH_MONO || is_pair) {
-        const DecChanHdr *hp = A.chan_hdr + (size_t)pkt * nch + c;
+    // which channel does this lane predict?  warp 0: slot c (mono or U), warp 1: slot c + 1 (V of a pair)
+    const bool mine = (w == 0) ? (M.kind == CH_MONO || M.kind == CH_PAIR_U) : (M.kind == CH_PAIR_U);
+    int32_t *gtile = A.chan_scratch + ((size_t)(group * nch + c + w) * F) * 32u;
+    PredState st;
+    uint32_t mode = PM_PASS, chanshift = 0;
+    if (mine) {
+        const DecChanHdr *hp = A.chan_hdr + (size_t)pkt * nch + c + w;
         chanshift = 32u - hp->chan_bits;
-        mode_u = pred_setup(hp, M.n, gtile_u + lane, su);
-        if (is_pair) mode_v = pred_setup(hp + 1, M.n, gtile_v + lane, sv);
+        mode = pred_setup(hp, M.n, gtile + lane, st);
     }
-    const uint32_t n_lane = (M.kind == CH_PAIR_V) ? 0u : M.n;
-    const uint32_t n_max = __reduce_max_sync(0xffffffffu, n_lane);
+    const bool warp_has_tiles = __any_sync(0xffffffffu, mine || (w == 0 && M.kind != CH_PAIR_V));
+    const uint32_t n_pred = mine ? M.n : 0u;
+    const uint32_t n_max = __reduce_max_sync(0xffffffffu, (M.kind == CH_PAIR_V) ? 0u : M.n);      // same in both warps
     const uint32_t tiles = (n_max + kTileRows - 1) / kTileRows;
-    __syncwarp();
+    __syncthreads();
 
-    // a tile = 32 rows x 8 chunks of 16 bytes per channel; lane i takes chunks i, i + 32, ...
+    // a tile = 32 rows x 8 chunks of 16 bytes; lane i takes chunks i, i + 32, ...
     auto request = [&](uint32_t t) {
-        int32_t *bu = s_tile[wid][t & 1u][0], *bv = s_tile[wid][t & 1u][1];
+        int32_t *buf = s_tile[t & 1u][w];
+        if (warp_has_tiles) {
 #pragma unroll
-        for (uint32_t i = 0; i < 8; i++) {
-            const uint32_t ch = i * 32u + lane, row = ch >> 3, part = ch & 7u;
-            const uint32_t j = t * kTileRows + row;
-            const bool in = j < F && t < tiles;
-            const size_t goff = (size_t)(in ? j : 0u) * 32u + part * 4u;
-            cp_async_16((uint32_t)__cvta_generic_to_shared(bu + row * kTilePitch + part * 4u), gtile_u + goff, in ? 16u : 0u);
-            if (any_pair)
-                cp_async_16((uint32_t)__cvta_generic_to_shared(bv + row * kTilePitch + part * 4u), gtile_v + goff, in ? 16u : 0u);
+            for (uint32_t i = 0; i < 8; i++) {
+                const uint32_t ch = i * 32u + lane, row = ch >> 3, part = ch & 7u;
+                const uint32_t j = t * kTileRows + row;
+                const bool in = j < F && t < tiles;
+                const size_t goff = (size_t)(in ? j : 0u) * 32u + part * 4u;
+                cp_async_16((uint32_t)__cvta_generic_to_shared(buf + row * kTilePitch + part * 4u), gtile + goff, in ? 16u : 0u);
+            }
         }
         cp_async_commit();
     };
@@ -487,19 +485,15 @@ __global__ void __launch_bounds__(kFinWarps * 32) dec_finish_kernel(DecArgs A)
     for (uint32_t t = 0; t < tiles; t++) {
         cp_async_wait<1>();             // tile t is in (only tile t + 1 may still be in flight)
         __syncwarp();
-        int32_t *bu = s_tile[wid][t & 1u][0], *bv = s_tile[wid][t & 1u][1];
+        int32_t *bu = s_tile[t & 1u][0], *bv = s_tile[t & 1u][1];
         const uint32_t j0 = t * kTileRows;
-        // ---- serial phase: lane = packet
-        if (j0 < n_lane) {
-            const uint32_t r1 = min(n_lane - j0, kTileRows);
-            unpc_rows_any(mode_u, su, bu + lane, j0, 0, r1, chanshift);
-            if (is_pair) unpc_rows_any(mode_v, sv, bv + lane, j0, 0, r1, chanshift);
-        }
-        __syncwarp();
-        // ---- parallel phase: lane = sample
+        // ---- serial phase: lane = packet, each warp on its own channel
+        if (j0 < n_pred) unpc_rows_any(mode, st, s_tile[t & 1u][w] + lane, j0, 0, min(n_pred - j0, kTileRows), chanshift);
+        __syncthreads();
+        // ---- parallel phase: lane = sample; warp w takes the packets of its parity
         const uint32_t j = j0 + lane;
-        for (uint32_t pr = 0; pr < 32; pr++) {
-            const FinMeta &m = s_meta[wid][pr];
+        for (uint32_t pr = w; pr < 32; pr += 2) {
+            const FinMeta &m = s_meta[pr];
             if (m.kind == CH_PAIR_V || j >= m.n) continue;
             uint8_t *out = A.pcm_out + (m.out_frame + j) * stride + (size_t)c * bps;
             if (m.kind == CH_ZERO) {
@@ -534,7 +528,7 @@ __global__ void __launch_bounds__(kFinWarps * 32) dec_finish_kernel(DecArgs A)
                 }
             }
         }
-        __syncwarp();
+        __syncthreads();
         request(t + 2);                 // refills the buffer just drained (an empty group past the last tile)
     }
     cp_async_wait<0>();

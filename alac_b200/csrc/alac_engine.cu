@@ -761,7 +761,7 @@ extern "C" int32_t alac_b200_decode(alac_b200_engine *e, const void *cookie, uin
         }
         t_dec.push_back(e->timer());
         const uint32_t lgrid = (c.cnt + kRingStride - 1) / kRingStride;
-        const uint32_t fgrid = (((c.cnt + 31) / 32) * nch + kFinWarps - 1) / kFinWarps;
+        const uint32_t fgrid = ((c.cnt + 31) / 32) * nch;
         switch (depth) {
         case 16: dec_entropy_kernel<16><<<lgrid, kRingStride, 0, cs>>>(A); break;
         case 20: dec_entropy_kernel<20><<<lgrid, kRingStride, 0, cs>>>(A); break;
@@ -769,10 +769,10 @@ extern "C" int32_t alac_b200_decode(alac_b200_engine *e, const void *cookie, uin
         default: dec_entropy_kernel<32><<<lgrid, kRingStride, 0, cs>>>(A); break;
         }
         switch (depth) {
-        case 16: dec_finish_kernel<16><<<fgrid, kFinWarps * 32, 0, cs>>>(A); break;
-        case 20: dec_finish_kernel<20><<<fgrid, kFinWarps * 32, 0, cs>>>(A); break;
-        case 24: dec_finish_kernel<24><<<fgrid, kFinWarps * 32, 0, cs>>>(A); break;
-        default: dec_finish_kernel<32><<<fgrid, kFinWarps * 32, 0, cs>>>(A); break;
+        case 16: dec_finish_kernel<16><<<fgrid, 64, 0, cs>>>(A); break;
+        case 20: dec_finish_kernel<20><<<fgrid, 64, 0, cs>>>(A); break;
+        case 24: dec_finish_kernel<24><<<fgrid, 64, 0, cs>>>(A); break;
+        default: dec_finish_kernel<32><<<fgrid, 64, 0, cs>>>(A); break;
         }
         t_dec.push_back(e->timer());
         e->launches += 2;

@@ -204,6 +204,89 @@ __device__ __forceinline__ void init_coefs_row(int32_t *a, int n)
     a[2] = (-2 * 512) >> 4;
 }
 
+// Stages A and B of one frame for one chain lane (U and V of a pair on adjacent lanes): the mixRes search, the
+// taps search and the escape estimate of EncodeStereo / EncodeMono.  c4 / c8 are the lane's coefficient rows.
+struct SearchOut { uint32_t best_res, num_mine; int do_escape; };
+
+template <int DEPTH, bool STEREO, bool PACKED, bool WRAP>
+__device__ __forceinline__ SearchOut search_stages(MixSrc<DEPTH, STEREO, PACKED> &src, const EncArgs &A, bool valid, bool is_v, uint32_t n,
+                                                   uint32_t partial, uint32_t pair_mask, uint32_t chan_bits, uint32_t chanshift,
+                                                   uint32_t *slab, int32_t (&c4)[4], int32_t (&c8)[8])
+{
+    constexpr uint32_t shift = DepthTraits<DEPTH>::kShift;
+    uint32_t best_res = 0;
+    uint32_t num_mine = 8;           // taps chosen for this lane's channel
+    uint32_t metric_mine = 0;
+    int do_escape = 0;
+
+    const bool fast = STEREO && A.lay.fast_mode;   // EncodeMono has no fast variant
+    if (!fast && valid) {
+        if (STEREO) {
+            // stage A: mixRes search, first n/8 samples, chained on row 7 (:353-379)
+            const uint32_t na = n / 8;
+            uint32_t min_bits = 1u << 31;
+            for (int r = 0; r <= kMaxRes; r++) {
+                src.set_mix(r, is_v);
+                src.valid = na;
+                CostSink cs;
+                cs.ag.start(na);
+                cs.bit_size = chan_bits;
+                cs.keep = (r == kMaxRes) ? reinterpret_cast<int32_t *>(slab) : nullptr;
+                predict_pass<8, WRAP>(src, na, c8, chanshift, cs);
+                const uint32_t both = cs.ag.bits + __shfl_xor_sync(pair_mask, cs.ag.bits, 1);
+                if (both < min_bits) { min_bits = both; best_res = (uint32_t)r; }
+            }
+            src.set_mix((int32_t)best_res, is_v);
+            src.valid = n;
+        }
+        // stage B: taps search (:418-452 stereo, :881-905 mono)
+        uint32_t best_metric = 1u << 31;
+        num_mine = 4;
+        const uint32_t nb = n / 32, nc = n / 8;
+#pragma unroll 1
+        for (uint32_t taps = 4; taps <= 8; taps += 4) {
+            CostSink cs;
+            cs.ag.start(nc);
+            cs.bit_size = chan_bits;
+            cs.keep = nullptr;
+            NullSink null_sink;
+            if (taps == 4) {
+                for (int pass = 0; pass < 7; pass++) predict_pass<4, WRAP>(src, nb, c4, chanshift, null_sink);
+                predict_pass<4, WRAP>(src, STEREO ? nb : nc, c4, chanshift, cs);
+            } else {
+                for (int pass = 0; pass < 7; pass++) predict_pass<8, WRAP>(src, nb, c8, chanshift, null_sink);
+                predict_pass<8, WRAP>(src, STEREO ? nb : nc, c8, chanshift, cs);
+            }
+            if (STEREO) {
+                // residuals [max(n/32, taps+1), n/8) are what the mixRes=4 trial left behind (F4)
+                const int32_t *stale = reinterpret_cast<const int32_t *>(slab);
+                NoSink ns;
+                for (uint32_t j = max(nb, taps + 1); j < nc; j++) ag_put<false>(cs.ag, stale[j], chan_bits, ns);
+            }
+            const uint32_t metric = cs.ag.bits * 8 + 16 * taps;
+            if (metric < best_metric) { best_metric = metric; num_mine = taps; }
+        }
+        metric_mine = best_metric;
+        // escape estimate (:455-461 stereo, :909-915 mono)
+        if (STEREO) {
+            const uint32_t other = __shfl_xor_sync(pair_mask, metric_mine, 1);
+            uint32_t min_bits = metric_mine + other + 64 + (partial ? 32u : 0u);
+            if (shift) min_bits += n * shift * 2;
+            const uint32_t escape_bits = n * DEPTH * 2 + (partial ? 32u : 0u) + 16;
+            do_escape = (min_bits >= escape_bits);
+        } else {
+            uint32_t min_bits = metric_mine + 32 + (partial ? 32u : 0u);
+            if (shift) min_bits += n * shift;
+            const uint32_t escape_bits = n * DEPTH + (partial ? 32u : 0u) + 16;
+            do_escape = (min_bits >= escape_bits);
+        }
+    }
+
+    SearchOut o;
+    o.best_res = best_res; o.num_mine = num_mine; o.do_escape = do_escape;
+    return o;
+}
+
 // 128 chain lanes + one spare warp: the spare warp owns no chain; it only takes final-pass jobs so that
 // the 4-tap and the 8-tap jobs can each start on a warp boundary and no warp ever runs both loops.
 #ifndef ALAC_CHAIN_THREADS
@@ -297,73 +380,9 @@ enc_search_kernel(EncArgs A, uint32_t elems_of_kind, uint32_t kind_elem0 /* bitm
         src.base = base; src.stride = stride; src.valid = n;
         src.set_mix(0, is_v);
 
-        uint32_t best_res = 0;
-        uint32_t num_mine = 8;           // taps chosen for this lane's channel
-        uint32_t metric_mine = 0;
-        int do_escape = 0;
-
-        const bool fast = STEREO && A.lay.fast_mode;   // EncodeMono has no fast variant
-        if (!fast && valid) {
-            if (STEREO) {
-                // stage A: mixRes search, first n/8 samples, chained on row 7 (:353-379)
-                const uint32_t na = n / 8;
-                uint32_t min_bits = 1u << 31;
-                for (int r = 0; r <= kMaxRes; r++) {
-                    src.set_mix(r, is_v);
-                    src.valid = na;
-                    CostSink cs;
-                    cs.ag.start(na);
-                    cs.bit_size = chan_bits;
-                    cs.keep = (r == kMaxRes) ? reinterpret_cast<int32_t *>(slab) : nullptr;
-                    predict_pass<8, WRAP>(src, na, c8, chanshift, cs);
-                    const uint32_t both = cs.ag.bits + __shfl_xor_sync(pair_mask, cs.ag.bits, 1);
-                    if (both < min_bits) { min_bits = both; best_res = (uint32_t)r; }
-                }
-                src.set_mix((int32_t)best_res, is_v);
-                src.valid = n;
-            }
-            // stage B: taps search (:418-452 stereo, :881-905 mono)
-            uint32_t best_metric = 1u << 31;
-            num_mine = 4;
-            const uint32_t nb = n / 32, nc = n / 8;
-#pragma unroll 1
-            for (uint32_t taps = 4; taps <= 8; taps += 4) {
-                CostSink cs;
-                cs.ag.start(nc);
-                cs.bit_size = chan_bits;
-                cs.keep = nullptr;
-                NullSink null_sink;
-                if (taps == 4) {
-                    for (int pass = 0; pass < 7; pass++) predict_pass<4, WRAP>(src, nb, c4, chanshift, null_sink);
-                    predict_pass<4, WRAP>(src, STEREO ? nb : nc, c4, chanshift, cs);
-                } else {
-                    for (int pass = 0; pass < 7; pass++) predict_pass<8, WRAP>(src, nb, c8, chanshift, null_sink);
-                    predict_pass<8, WRAP>(src, STEREO ? nb : nc, c8, chanshift, cs);
-                }
-                if (STEREO) {
-                    // residuals [max(n/32, taps+1), n/8) are what the mixRes=4 trial left behind (F4)
-                    const int32_t *stale = reinterpret_cast<const int32_t *>(slab);
-                    NoSink ns;
-                    for (uint32_t j = max(nb, taps + 1); j < nc; j++) ag_put<false>(cs.ag, stale[j], chan_bits, ns);
-                }
-                const uint32_t metric = cs.ag.bits * 8 + 16 * taps;
-                if (metric < best_metric) { best_metric = metric; num_mine = taps; }
-            }
-            metric_mine = best_metric;
-            // escape estimate (:455-461 stereo, :909-915 mono)
-            if (STEREO) {
-                const uint32_t other = __shfl_xor_sync(pair_mask, metric_mine, 1);
-                uint32_t min_bits = metric_mine + other + 64 + (partial ? 32u : 0u);
-                if (shift) min_bits += n * shift * 2;
-                const uint32_t escape_bits = n * DEPTH * 2 + (partial ? 32u : 0u) + 16;
-                do_escape = (min_bits >= escape_bits);
-            } else {
-                uint32_t min_bits = metric_mine + 32 + (partial ? 32u : 0u);
-                if (shift) min_bits += n * shift;
-                const uint32_t escape_bits = n * DEPTH + (partial ? 32u : 0u) + 16;
-                do_escape = (min_bits >= escape_bits);
-            }
-        }
+        const SearchOut so = search_stages<DEPTH, STEREO, PACKED, WRAP>(src, A, valid, is_v, n, partial, pair_mask, chan_bits, chanshift, slab, c4, c8);
+        const uint32_t best_res = so.best_res, num_mine = so.num_mine;
+        const int do_escape = so.do_escape;
 
         // header coefficients are the post-search, pre-final-pass values (:479-485)
         ElemRec *rec = A.recs + (size_t)(pkt - A.pkt_base) * A.lay.elems_per_packet + slot;
@@ -454,6 +473,141 @@ enc_search_kernel(EncArgs A, uint32_t elems_of_kind, uint32_t kind_elem0 /* bitm
         for (int k = 4; k < 8; k++) st[k] = 0;
         for (int k = 0; k < 8; k++) st[8 + k] = (int16_t)c8[k];
     }
+}
+
+// ---- split form of the search kernel (every segment is one frame: frames_per_segment = 1, no state hand-off) -------
+// Nothing chains from one frame to the next, so the final pass need not stay on the lane (or even in the CTA) that
+// did the search.  enc_search_split_kernel runs stages A and B with one-warp CTAs (the grid then spreads over the
+// 148 SMs to within one warp) and files each channel's final-pass job under its tap count in a global list;
+// enc_final_kernel runs stage C with every warp full and uniform -- no in-CTA regrouping, no barriers, no spare warp.
+struct JobLists {
+    FinalJob *jobs;         // [2][max_jobs]: 4-tap jobs, then 8-tap jobs
+    uint32_t *counts;       // [2]
+    uint32_t max_jobs;
+};
+
+template <int DEPTH, bool STEREO, bool PACKED, bool WRAP>
+__global__ void __launch_bounds__(32, 20)
+enc_search_split_kernel(EncArgs A, uint32_t elems_of_kind, uint32_t kind_elem0, JobLists Q)
+{
+    constexpr uint32_t kLanesPerJob = STEREO ? 2 : 1;
+    const uint32_t tid = blockIdx.x * 32u + threadIdx.x;
+    const uint32_t lane = threadIdx.x;
+    const uint32_t job = tid / kLanesPerJob;
+    const bool is_v = STEREO && (tid & 1u);
+    const uint32_t total_jobs = A.num_segments * elems_of_kind;
+    const bool valid = job < total_jobs;              // lanes of a pair are both in or both out
+    const uint32_t pair_mask = STEREO ? (3u << (lane & ~1u)) : 0u;
+
+    uint32_t slot = 0, seg = A.seg_base;
+    if (valid) {
+        seg = A.seg_base + job / elems_of_kind;
+        uint32_t which = job % elems_of_kind;
+        for (uint32_t s = 0, m = kind_elem0; s < 8; s++, m >>= 1) {
+            if (m & 1u) { if (which == 0) { slot = s; break; } which--; }
+        }
+    }
+    const uint32_t chan = A.lay.elem_chan[slot];
+    const uint32_t chain = A.lay.elem_chain[slot] + (is_v ? 1u : 0u);
+    constexpr uint32_t bps = DepthTraits<DEPTH>::kBytes;
+    constexpr uint32_t shift = DepthTraits<DEPTH>::kShift;
+    const uint32_t stride = A.lay.channels * bps;
+    const uint32_t chan_bits = DEPTH - shift + (STEREO ? 1u : 0u);                 // :334 / :857
+    const uint32_t chanshift = 32u - chan_bits;
+
+    int32_t c4[4], c8[8];
+    init_coefs_row(c4, 4);
+    init_coefs_row(c8, 8);
+
+    const uint32_t pkt = valid ? A.seg_first[seg] : A.pkt_base;
+    const uint32_t n = valid ? A.pkt_samples[pkt] : 0u;
+    const uint8_t *base = A.pcm + (A.pkt_frame[pkt] * A.lay.channels + chan) * bps;
+    uint32_t *slab = A.scratch + ((size_t)(pkt - A.pkt_base) * A.lay.chains_per_packet + chain) * A.cap_words;
+    const uint32_t partial = (n != A.lay.frame_size);
+
+    MixSrc<DEPTH, STEREO, PACKED> src;
+    src.base = base; src.stride = stride; src.valid = n;
+    src.set_mix(0, is_v);
+    const SearchOut so = search_stages<DEPTH, STEREO, PACKED, WRAP>(src, A, valid, is_v, n, partial, pair_mask, chan_bits, chanshift, slab, c4, c8);
+    const uint32_t best_res = so.best_res, num_mine = so.num_mine;
+    const int do_escape = so.do_escape;
+
+    // header coefficients are the post-search, pre-final-pass values (:479-485)
+    ElemRec *rec = A.recs + (size_t)(pkt - A.pkt_base) * A.lay.elems_per_packet + slot;
+    const uint32_t other_num = STEREO ? __shfl_xor_sync(0xffffffffu, num_mine, 1) : 0u;
+    if (valid) {
+        int16_t *hc = is_v ? rec->coef_v : rec->coef_u;
+        if (num_mine == 4) { for (int k = 0; k < 4; k++) hc[k] = (int16_t)c4[k]; for (int k = 4; k < 8; k++) hc[k] = 0; }
+        else { for (int k = 0; k < 8; k++) hc[k] = (int16_t)c8[k]; }
+        if (is_v) {
+            rec->bits_v = 0;
+        } else {
+            rec->escape = (uint8_t)do_escape;
+            rec->mix_res = (uint8_t)best_res;
+            rec->num_u = (uint8_t)num_mine;
+            rec->num_v = (uint8_t)other_num;
+            rec->bits_u = 0;
+            if (!STEREO) rec->bits_v = 0;
+        }
+    }
+
+    // file the final-pass job under its tap count (one atomic per warp and list)
+    const uint32_t key = (valid && !do_escape) ? (num_mine == 8 ? 1u : 0u) : 2u;
+    const uint32_t b4 = __ballot_sync(0xffffffffu, key == 0), b8 = __ballot_sync(0xffffffffu, key == 1);
+    uint32_t first4 = 0, first8 = 0;
+    if (lane == 0) {
+        if (b4) first4 = atomicAdd(&Q.counts[0], (uint32_t)__popc(b4));
+        if (b8) first8 = atomicAdd(&Q.counts[1], (uint32_t)__popc(b8));
+    }
+    first4 = __shfl_sync(0xffffffffu, first4, 0);
+    first8 = __shfl_sync(0xffffffffu, first8, 0);
+    if (key < 2) {
+        const uint32_t lt = (1u << lane) - 1u;
+        FinalJob J;
+        J.base = base;
+        J.slab = slab;
+        J.bits_out = is_v ? &rec->bits_v : &rec->bits_u;
+        J.n = n;
+        J.flags = (is_v ? 1u : 0u) | (best_res << 1);
+#pragma unroll
+        for (int k = 0; k < 8; k++) J.coef[k] = (key == 0) ? (k < 4 ? c4[k] : 0) : c8[k];
+        Q.jobs[(size_t)key * Q.max_jobs + (key == 0 ? first4 + __popc(b4 & lt) : first8 + __popc(b8 & lt))] = J;
+    }
+}
+
+// stage C: final predictor + Golomb pass over the whole frame (:507-531, :941-945), one lane per listed job.
+// The first half of the grid takes the 8-tap list (the longer jobs start first), the second half the 4-tap list.
+template <int DEPTH, bool STEREO, bool PACKED, bool WRAP>
+__global__ void __launch_bounds__(32, 24)
+enc_final_kernel(EncArgs A, JobLists Q, uint32_t ctas_per_list)
+{
+    const uint32_t list = blockIdx.x < ctas_per_list ? 1u : 0u;
+    const uint32_t idx = (blockIdx.x - (list ? 0u : ctas_per_list)) * 32u + threadIdx.x;
+    if (idx >= Q.counts[list]) return;
+    const FinalJob J = Q.jobs[(size_t)list * Q.max_jobs + idx];
+    constexpr uint32_t bps = DepthTraits<DEPTH>::kBytes;
+    constexpr uint32_t shift = DepthTraits<DEPTH>::kShift;
+    const uint32_t chan_bits = DEPTH - shift + (STEREO ? 1u : 0u);
+    const uint32_t chanshift = 32u - chan_bits;
+    MixSrc<DEPTH, STEREO, PACKED> fs;
+    fs.base = J.base; fs.stride = A.lay.channels * bps;
+    fs.set_mix((int32_t)(J.flags >> 1), (J.flags & 1u) != 0);
+    fs.valid = J.n;
+    EmitSink es;
+    es.ag.start(J.n);
+    es.bit_size = chan_bits;
+    es.bits.start(J.slab, A.cap_words);
+    if (list == 0) {
+        int32_t a[4];
+        for (int k = 0; k < 4; k++) a[k] = J.coef[k];
+        predict_pass<4, WRAP>(fs, J.n, a, chanshift, es);
+    } else {
+        int32_t a[8];
+        for (int k = 0; k < 8; k++) a[k] = J.coef[k];
+        predict_pass<8, WRAP>(fs, J.n, a, chanshift, es);
+    }
+    es.bits.finish();
+    *J.bits_out = es.ag.bits;
 }
 
 // ---- packet sizes ------------------------------------------------------------------------------------

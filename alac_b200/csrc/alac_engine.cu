@@ -58,7 +58,7 @@ struct alac_b200_engine {
     // encode
     DevBuf pcm, pkt_frame, pkt_samples, seg_first, seg_count, seg_stream, recs, scratch, sizes, offsets, out, state, counters;
     // decode
-    DevBuf d_packets, d_sizes, d_pkt_off, d_pkt_samples, d_out_frame, d_status, d_pcm, d_class, d_rank, d_perm, d_chan, d_meta, d_hdr;
+    DevBuf d_packets, d_sizes, d_pkt_off, d_pkt_samples, d_out_frame, d_status, d_pcm, d_class, d_rank, d_perm, d_chan, d_meta, d_hdr, jobs, job_counts;
     uint32_t launches = 0;
     // per-kernel timers: (start, stop) event pairs, grown on demand, reused across calls
     std::vector<cudaEvent_t> timers;
@@ -222,7 +222,7 @@ void alac_b200_engine_destroy(alac_b200_engine *e)
     cudaStreamSynchronize(e->stream);
     DevBuf *bufs[] = {&e->pcm, &e->pkt_frame, &e->pkt_samples, &e->seg_first, &e->seg_count, &e->seg_stream, &e->recs,
                       &e->scratch, &e->sizes, &e->offsets, &e->out, &e->state, &e->counters, &e->d_packets, &e->d_sizes,
-                      &e->d_pkt_off, &e->d_pkt_samples, &e->d_out_frame, &e->d_status, &e->d_pcm, &e->d_class, &e->d_rank, &e->d_perm, &e->d_chan, &e->d_meta, &e->d_hdr};
+                      &e->d_pkt_off, &e->d_pkt_samples, &e->d_out_frame, &e->d_status, &e->d_pcm, &e->d_class, &e->d_rank, &e->d_perm, &e->d_chan, &e->d_meta, &e->d_hdr, &e->jobs, &e->job_counts};
     for (DevBuf *b : bufs) b->release();
     for (auto &ev : e->ev)
         if (ev) cudaEventDestroy(ev);
@@ -314,19 +314,35 @@ int32_t alac_b200_copy_to_device(void *dst, const void *src, uint64_t bytes)
 // encode
 // ------------------------------------------------------------------------------------------------
 template <int DEPTH, bool PACKED, bool WRAP>
-static void launch_search_v(alac_b200_engine *e, const EncArgs &A, uint32_t mono_mask, uint32_t pair_mask)
+static void launch_search_v(alac_b200_engine *e, const EncArgs &A, uint32_t mono_mask, uint32_t pair_mask, const JobLists *split)
 {
     const uint32_t pairs = __builtin_popcount(pair_mask), monos = __builtin_popcount(mono_mask);
     if (pairs) {
         const uint64_t threads = (uint64_t)A.num_segments * pairs * 2;
-        enc_search_kernel<DEPTH, true, PACKED, WRAP>
-            <<<(uint32_t)((threads + kChainThreads - 1) / kChainThreads), kSearchThreads, 0, e->cur>>>(A, pairs, pair_mask);
+        if (split) {
+            const uint32_t ctas = (uint32_t)((threads + 31) / 32);
+            cudaMemsetAsync(split->counts, 0, 8, e->cur);
+            enc_search_split_kernel<DEPTH, true, PACKED, WRAP><<<ctas, 32, 0, e->cur>>>(A, pairs, pair_mask, *split);
+            enc_final_kernel<DEPTH, true, PACKED, WRAP><<<2 * ctas, 32, 0, e->cur>>>(A, *split, ctas);
+            e->launches++;
+        } else {
+            enc_search_kernel<DEPTH, true, PACKED, WRAP>
+                <<<(uint32_t)((threads + kChainThreads - 1) / kChainThreads), kSearchThreads, 0, e->cur>>>(A, pairs, pair_mask);
+        }
         e->launches++;
     }
     if (monos) {
         const uint64_t threads = (uint64_t)A.num_segments * monos;
-        enc_search_kernel<DEPTH, false, false, WRAP>
-            <<<(uint32_t)((threads + kChainThreads - 1) / kChainThreads), kSearchThreads, 0, e->cur>>>(A, monos, mono_mask);
+        if (split) {
+            const uint32_t ctas = (uint32_t)((threads + 31) / 32);
+            cudaMemsetAsync(split->counts, 0, 8, e->cur);
+            enc_search_split_kernel<DEPTH, false, false, WRAP><<<ctas, 32, 0, e->cur>>>(A, monos, mono_mask, *split);
+            enc_final_kernel<DEPTH, false, false, WRAP><<<2 * ctas, 32, 0, e->cur>>>(A, *split, ctas);
+            e->launches++;
+        } else {
+            enc_search_kernel<DEPTH, false, false, WRAP>
+                <<<(uint32_t)((threads + kChainThreads - 1) / kChainThreads), kSearchThreads, 0, e->cur>>>(A, monos, mono_mask);
+        }
         e->launches++;
     }
 }
@@ -334,14 +350,15 @@ static void launch_search_v(alac_b200_engine *e, const EncArgs &A, uint32_t mono
 // packed: pure stereo PCM at 8-byte alignment (one wide load per sample-frame);
 // wrap: the int16 coefficient range could be left during a segment, so every update re-wraps
 template <int DEPTH>
-static void launch_search(alac_b200_engine *e, const EncArgs &A, uint32_t mono_mask, uint32_t pair_mask, bool packed, bool wrap)
+static void launch_search(alac_b200_engine *e, const EncArgs &A, uint32_t mono_mask, uint32_t pair_mask, bool packed, bool wrap,
+                          const JobLists *split)
 {
     if (packed) {
-        if (wrap) launch_search_v<DEPTH, true, true>(e, A, mono_mask, pair_mask);
-        else launch_search_v<DEPTH, true, false>(e, A, mono_mask, pair_mask);
+        if (wrap) launch_search_v<DEPTH, true, true>(e, A, mono_mask, pair_mask, split);
+        else launch_search_v<DEPTH, true, false>(e, A, mono_mask, pair_mask, split);
     } else {
-        if (wrap) launch_search_v<DEPTH, false, true>(e, A, mono_mask, pair_mask);
-        else launch_search_v<DEPTH, false, false>(e, A, mono_mask, pair_mask);
+        if (wrap) launch_search_v<DEPTH, false, true>(e, A, mono_mask, pair_mask, split);
+        else launch_search_v<DEPTH, false, false>(e, A, mono_mask, pair_mask, split);
     }
 }
 
@@ -453,6 +470,13 @@ extern "C" int32_t alac_b200_encode(alac_b200_engine *e, const alac_b200_enc_con
     CU_CHECK(e, e->sizes.reserve((size_t)P * 4));
     CU_CHECK(e, e->offsets.reserve(((size_t)P + 1) * 8));
     CU_CHECK(e, e->counters.reserve(64));
+    // every segment is a single frame and no state is handed over: search and final pass run as two kernels
+    const bool split = K == 1 && coef_state == nullptr;
+    const size_t jobs_per_lane = (size_t)max_chunk * L.chains_per_packet;
+    if (split) {
+        CU_CHECK(e, e->jobs.reserve(2 * jobs_per_lane * nlanes * sizeof(FinalJob)));
+        CU_CHECK(e, e->job_counts.reserve(64));
+    }
     const uint8_t *d_pcm;
     if (in_host) {
         CU_CHECK(e, e->pcm.reserve((size_t)(num_sample_frames * bpf) + 64));
@@ -526,12 +550,16 @@ extern "C" int32_t alac_b200_encode(alac_b200_engine *e, const alac_b200_enc_con
         A.scratch = e->scratch.as<uint32_t>() + slab_words_per_lane * lane;
         A.cap_words = cap_words;
         A.state = d_state;
+        JobLists Q;
+        Q.max_jobs = (uint32_t)jobs_per_lane;
+        Q.jobs = split ? e->jobs.as<FinalJob>() + 2 * jobs_per_lane * lane : nullptr;
+        Q.counts = split ? e->job_counts.as<uint32_t>() + 2 * lane : nullptr;
         t_search.push_back(e->timer());
         switch (cfg->bit_depth) {
-        case 16: launch_search<16>(e, A, mono_mask, pair_mask, packed, wrap); break;
-        case 20: launch_search<20>(e, A, mono_mask, pair_mask, packed, wrap); break;
-        case 24: launch_search<24>(e, A, mono_mask, pair_mask, packed, wrap); break;
-        default: launch_search<32>(e, A, mono_mask, pair_mask, packed, wrap); break;
+        case 16: launch_search<16>(e, A, mono_mask, pair_mask, packed, wrap, split ? &Q : nullptr); break;
+        case 20: launch_search<20>(e, A, mono_mask, pair_mask, packed, wrap, split ? &Q : nullptr); break;
+        case 24: launch_search<24>(e, A, mono_mask, pair_mask, packed, wrap, split ? &Q : nullptr); break;
+        default: launch_search<32>(e, A, mono_mask, pair_mask, packed, wrap, split ? &Q : nullptr); break;
         }
         t_search.push_back(e->timer());
         enc_size_kernel<<<(c.cnt + 255) / 256, 256, 0, cs>>>(A.recs, L, cfg->bit_depth, A.pkt_samples + c.p0, c.cnt,

@@ -650,7 +650,8 @@ __global__ void enc_size_kernel(ElemRec *recs, EncLayout lay, uint32_t depth, co
 
 // ---- exclusive scan (single block, sequential tiles) -------------------------------------------------------
 // offsets[i] = sum_{j<i} sizes[j]; offsets[n] = total.  One 1024-thread block walks the array in tiles.
-__global__ void __launch_bounds__(1024) scan_u32_to_u64_kernel(const uint32_t *in, uint64_t *out, uint64_t n, uint32_t *max_out, int chain_base)
+__global__ void __launch_bounds__(1024) scan_u32_to_u64_kernel(const uint32_t *in, uint64_t *out, uint64_t n, uint32_t *max_out, int chain_base,
+                                                               uint64_t *host_total = nullptr)
 {
     __shared__ uint64_t warp_sums[32];
     __shared__ uint64_t carry_s;
@@ -689,7 +690,11 @@ __global__ void __launch_bounds__(1024) scan_u32_to_u64_kernel(const uint32_t *i
         if (threadIdx.x == 1023) carry_s = incl;
         __syncthreads();
     }
-    if (threadIdx.x == 0) out[n] = carry_s;
+    if (threadIdx.x == 0) {
+        out[n] = carry_s;
+        // pinned host word (UVA): the host reads it after the chunk's completion event, no copy-engine op needed
+        if (host_total) { *host_total = carry_s; __threadfence_system(); }
+    }
     if (max_out) {
         for (int d = 16; d; d >>= 1) my_max = max(my_max, __shfl_xor_sync(0xffffffffu, my_max, d));
         if (lane == 0) warp_max[wid] = my_max;

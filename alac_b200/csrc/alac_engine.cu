@@ -12,6 +12,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <chrono>
 #include <vector>
 
 using namespace alacb;
@@ -50,7 +51,7 @@ struct alac_b200_engine {
     cudaStream_t stream = nullptr;
     cudaStream_t own_stream = nullptr;
     cudaStream_t copy_in = nullptr, copy_out = nullptr;     // transfer streams of the host-buffer pipeline
-    cudaStream_t lanes[4] = {nullptr, nullptr, nullptr, nullptr};   // compute streams of the host-buffer pipeline
+    cudaStream_t lanes[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   // compute streams of the host-buffer pipeline
     cudaStream_t cur = nullptr;                             // stream the launch helpers / timers use right now
     uint64_t *h_totals = nullptr;                           // pinned: running byte / frame totals per chunk
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
@@ -116,10 +117,41 @@ static uint32_t pipeline_chunks()
 {
     static const uint32_t n = [] {
         const char *v = getenv("ALAC_B200_PIPELINE_CHUNKS");
-        const long k = v ? atol(v) : 4;
+        const long k = v ? atol(v) : 5;
         return (uint32_t)(k < 1 ? 1 : k > 64 ? 64 : k);
     }();
     return n;
+}
+
+// Share of the packets that pipeline chunk i of n gets.  Every kernel here is latency-bound (a packet is one serial
+// chain), so a chunk's kernels take about as long however small it is; what the pipeline cannot hide is the
+// kernel time of the LAST chunk on encode (after the last PCM byte arrived) and of the FIRST chunk on decode
+// (before the first PCM byte can leave).  Those chunks are therefore the small ones: linear weights n, n-1, .. 1.
+static uint64_t tapered_chunk(uint64_t total, uint32_t n, uint32_t i, bool small_last)
+{
+    // ALAC_B200_PIPELINE_WEIGHTS="w0,w1,..." (encode order; decode uses it reversed) overrides the linear taper
+    static const std::vector<uint64_t> custom = [] {
+        std::vector<uint64_t> w;
+        const char *v = getenv("ALAC_B200_PIPELINE_WEIGHTS");
+        while (v && *v) {
+            char *end = nullptr;
+            const long long k = strtoll(v, &end, 10);
+            if (end == v) break;
+            w.push_back((uint64_t)std::max<long long>(1, k));
+            v = (*end == ',') ? end + 1 : end;
+        }
+        return w;
+    }();
+    if (!custom.empty()) {
+        const uint32_t m = (uint32_t)custom.size();
+        uint64_t wsum = 0;
+        for (uint64_t w : custom) wsum += w;
+        const uint32_t k = std::min(i, m - 1);
+        return std::max<uint64_t>(1, (total * custom[small_last ? k : m - 1 - k] + wsum - 1) / wsum);
+    }
+    const uint64_t wsum = (uint64_t)n * (n + 1) / 2;
+    const uint64_t w = small_last ? (n - i) : (i + 1);
+    return std::max<uint64_t>(1, (total * w + wsum - 1) / wsum);
 }
 
 // packets per search launch: bounds the Golomb-slab scratch (ALAC_B200_CHUNK_PACKETS overrides)
@@ -321,7 +353,6 @@ static void launch_search_v(alac_b200_engine *e, const EncArgs &A, uint32_t mono
         const uint64_t threads = (uint64_t)A.num_segments * pairs * 2;
         if (split) {
             const uint32_t ctas = (uint32_t)((threads + 31) / 32);
-            cudaMemsetAsync(split->counts, 0, 8, e->cur);
             enc_search_split_kernel<DEPTH, true, PACKED, WRAP><<<ctas, 32, 0, e->cur>>>(A, pairs, pair_mask, *split);
             enc_final_kernel<DEPTH, true, PACKED, WRAP><<<2 * ctas, 32, 0, e->cur>>>(A, *split, ctas);
             e->launches++;
@@ -335,9 +366,10 @@ static void launch_search_v(alac_b200_engine *e, const EncArgs &A, uint32_t mono
         const uint64_t threads = (uint64_t)A.num_segments * monos;
         if (split) {
             const uint32_t ctas = (uint32_t)((threads + 31) / 32);
-            cudaMemsetAsync(split->counts, 0, 8, e->cur);
-            enc_search_split_kernel<DEPTH, false, false, WRAP><<<ctas, 32, 0, e->cur>>>(A, monos, mono_mask, *split);
-            enc_final_kernel<DEPTH, false, false, WRAP><<<2 * ctas, 32, 0, e->cur>>>(A, *split, ctas);
+            JobLists Qm = *split;
+            Qm.counts += 2;     // the mono launch has its own pair of counters
+            enc_search_split_kernel<DEPTH, false, false, WRAP><<<ctas, 32, 0, e->cur>>>(A, monos, mono_mask, Qm);
+            enc_final_kernel<DEPTH, false, false, WRAP><<<2 * ctas, 32, 0, e->cur>>>(A, Qm, ctas);
             e->launches++;
         } else {
             enc_search_kernel<DEPTH, false, false, WRAP>
@@ -435,15 +467,19 @@ extern "C" int32_t alac_b200_encode(alac_b200_engine *e, const alac_b200_enc_con
     uint64_t chunk_target = scratch_chunk_packets();
     if (!chunk_target) chunk_target = std::max<uint64_t>(4096, (8ull << 30) / ((uint64_t)L.chains_per_packet * cap_words * 4));
     const bool multi = in_host || out_host;             // host buffers: chunks run on several compute streams
-    const uint32_t nlanes = multi ? 4u : 1u;
-    if (multi) chunk_target = std::min<uint64_t>(chunk_target / nlanes, std::max<uint64_t>(2048, (P + pipeline_chunks() - 1) / pipeline_chunks()));
+    const uint32_t nlanes = multi ? 8u : 1u;
+    if (multi) chunk_target /= nlanes;
+    const bool taper = multi && P >= 4096;
     struct Chunk { uint32_t s0, s1, p0, cnt; uint64_t f_lo, f_hi; };
     std::vector<Chunk> chunks;
     uint64_t max_chunk = 0;
     for (uint32_t s0 = 0; s0 < S;) {
         uint32_t s1 = s0;
         uint64_t cnt = 0;
-        while (s1 < S && (cnt == 0 || cnt + h_seg_count[s1] <= chunk_target)) cnt += h_seg_count[s1++];
+        uint64_t target = chunk_target;
+        if (taper) target = std::min<uint64_t>(target, std::max<uint64_t>(512, tapered_chunk(P, pipeline_chunks(), (uint32_t)std::min<size_t>(chunks.size(), pipeline_chunks() - 1), true)));
+        else if (multi) target = std::min<uint64_t>(target, std::max<uint64_t>(2048, (P + pipeline_chunks() - 1) / pipeline_chunks()));
+        while (s1 < S && (cnt == 0 || cnt + h_seg_count[s1] <= target)) cnt += h_seg_count[s1++];
         Chunk c;
         c.s0 = s0; c.s1 = s1; c.p0 = h_seg_first[s0]; c.cnt = (uint32_t)cnt;
         c.f_lo = ~0ull; c.f_hi = 0;
@@ -475,7 +511,7 @@ extern "C" int32_t alac_b200_encode(alac_b200_engine *e, const alac_b200_enc_con
     const size_t jobs_per_lane = (size_t)max_chunk * L.chains_per_packet;
     if (split) {
         CU_CHECK(e, e->jobs.reserve(2 * jobs_per_lane * nlanes * sizeof(FinalJob)));
-        CU_CHECK(e, e->job_counts.reserve(64));
+        CU_CHECK(e, e->job_counts.reserve(chunks.size() * 16));        // per chunk: {4-tap, 8-tap} x {pair, mono launch}
     }
     const uint8_t *d_pcm;
     if (in_host) {
@@ -507,6 +543,7 @@ extern "C" int32_t alac_b200_encode(alac_b200_engine *e, const alac_b200_enc_con
         d_state = e->state.as<int16_t>();
     }
     CU_CHECK(e, cudaMemsetAsync(e->counters.p, 0, 64, st));
+    if (split) CU_CHECK(e, cudaMemsetAsync(e->job_counts.p, 0, chunks.size() * 16, st));
     // copy-in stream: PCM chunks, each followed by an event the compute stream waits on
     std::vector<cudaEvent_t> h2d_done;
     if (in_host) {
@@ -528,11 +565,15 @@ extern "C" int32_t alac_b200_encode(alac_b200_engine *e, const alac_b200_enc_con
     unsigned long long *d_escapes = e->counters.as<unsigned long long>();
     uint32_t *d_max = reinterpret_cast<uint32_t *>(e->counters.as<uint8_t>() + 8);
     std::vector<cudaEvent_t> comp_done, scan_done;
+    const bool trace = getenv("ALAC_B200_TRACE") != nullptr;
+    const auto host_t0 = std::chrono::steady_clock::now();
     for (size_t ci = 0; ci < chunks.size(); ci++) {
         const Chunk &c = chunks[ci];
         const uint32_t lane = (uint32_t)(ci % nlanes);
         cudaStream_t cs = multi ? e->lanes[lane] : st;
         e->cur = cs;
+        if (trace) fprintf(stderr, "[alac_b200] host submits enc chunk %zu at +%.2f ms\n", ci,
+                           std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - host_t0).count());
         if (multi && ci < nlanes) CU_CHECK(e, cudaStreamWaitEvent(cs, e->ev[1], 0));       // tables are in
         if (in_host) CU_CHECK(e, cudaStreamWaitEvent(cs, h2d_done[ci], 0));
         EncArgs A;
@@ -553,7 +594,7 @@ extern "C" int32_t alac_b200_encode(alac_b200_engine *e, const alac_b200_enc_con
         JobLists Q;
         Q.max_jobs = (uint32_t)jobs_per_lane;
         Q.jobs = split ? e->jobs.as<FinalJob>() + 2 * jobs_per_lane * lane : nullptr;
-        Q.counts = split ? e->job_counts.as<uint32_t>() + 2 * lane : nullptr;
+        Q.counts = split ? e->job_counts.as<uint32_t>() + 4 * ci : nullptr;
         t_search.push_back(e->timer());
         switch (cfg->bit_depth) {
         case 16: launch_search<16>(e, A, mono_mask, pair_mask, packed, wrap, split ? &Q : nullptr); break;
@@ -567,7 +608,7 @@ extern "C" int32_t alac_b200_encode(alac_b200_engine *e, const alac_b200_enc_con
         // the scan continues from the previous chunk's total: wait for that chunk's scan
         if (multi && ci > 0) CU_CHECK(e, cudaStreamWaitEvent(cs, scan_done[ci - 1], 0));
         scan_u32_to_u64_kernel<<<1, 1024, 0, cs>>>(e->sizes.as<uint32_t>() + c.p0, e->offsets.as<uint64_t>() + c.p0, c.cnt, d_max,
-                                                   ci == 0 ? 0 : 1);
+                                                   ci == 0 ? 0 : 1, &e->h_totals[ci]);
         if (multi) scan_done.push_back(e->event_on(cs));
         e->launches += 2;
 
@@ -593,7 +634,6 @@ extern "C" int32_t alac_b200_encode(alac_b200_engine *e, const alac_b200_enc_con
         }
         t_asm.push_back(e->timer());
         // running byte total after this chunk -> pinned host word; the host needs it to size the chunk's D2H
-        CU_CHECK(e, cudaMemcpyAsync(&e->h_totals[ci], e->offsets.as<uint64_t>() + c.p0 + c.cnt, 8, cudaMemcpyDeviceToHost, cs));
         comp_done.push_back(e->event_on(cs));
     }
     e->cur = nullptr;
@@ -622,6 +662,15 @@ extern "C" int32_t alac_b200_encode(alac_b200_engine *e, const alac_b200_enc_con
     CU_CHECK(e, cudaStreamSynchronize(e->copy_out));
     CU_CHECK(e, cudaStreamSynchronize(st));
 
+    if (getenv("ALAC_B200_TRACE")) {        // developer aid: per-chunk timeline in ms since the call started
+        for (size_t ci = 0; ci < chunks.size(); ci++) {
+            float a = 0, b = 0, c = 0, d = 0;
+            if (in_host) cudaEventElapsedTime(&a, e->ev[0], h2d_done[ci]);
+            if (2 * ci + 1 < t_search.size()) { cudaEventElapsedTime(&b, e->ev[0], t_search[2 * ci]); cudaEventElapsedTime(&c, e->ev[0], t_search[2 * ci + 1]); }
+            cudaEventElapsedTime(&d, e->ev[0], comp_done[ci]);
+            fprintf(stderr, "[alac_b200] enc chunk %zu: %u packets, h2d done %.2f, search %.2f..%.2f, done %.2f\n", ci, chunks[ci].cnt, a, b, c, d);
+        }
+    }
     if (out_num_packets) *out_num_packets = P;
     if (out_bytes) *out_bytes = total;
     if (stats) {
@@ -676,20 +725,25 @@ extern "C" int32_t alac_b200_decode(alac_b200_engine *e, const void *cookie, uin
     std::vector<Chunk> chunks;
     uint64_t total_bytes = 0;
     {
-        const uint32_t per = out_host ? std::max<uint32_t>(2048, (P + pipeline_chunks() - 1) / pipeline_chunks()) : P;     // see multi below
-        for (uint32_t p0 = 0; p0 < P; p0 += per) {
+        const bool taper = out_host && P >= 4096;
+        for (uint32_t p0 = 0; p0 < P;) {
+            uint32_t per = P;
+            if (taper) per = (uint32_t)std::max<uint64_t>(512, tapered_chunk(P, pipeline_chunks(), (uint32_t)std::min<size_t>(chunks.size(), pipeline_chunks() - 1), false));
+            else if (out_host) per = std::max<uint32_t>(2048, (P + pipeline_chunks() - 1) / pipeline_chunks());     // see multi below
             Chunk c;
             c.p0 = p0; c.cnt = std::min(per, P - p0); c.b0 = total_bytes;
             if (in_host) for (uint32_t i = p0; i < p0 + c.cnt; i++) total_bytes += packet_sizes[i];
             c.b1 = total_bytes;
             chunks.push_back(c);
+            p0 += c.cnt;
         }
     }
     if (chunks.size() > kMaxChunks) { e->err = "too many chunks"; return ALAC_B200_PARAM_ERROR; }
-    const uint32_t max_cnt = chunks[0].cnt;
+    uint32_t max_cnt = 0;
+    for (const Chunk &c : chunks) max_cnt = std::max(max_cnt, c.cnt);
     const uint32_t groups = (max_cnt + 31) / 32;
     const bool multi = out_host;                        // chunks run on several compute streams
-    const uint32_t nlanes = multi ? 4u : 1u;
+    const uint32_t nlanes = multi ? 8u : 1u;
     const size_t chan_words_per_lane = (size_t)groups * 32 * nch * frame_length;
 
     CU_CHECK(e, e->d_pkt_off.reserve(((size_t)P + 1) * 8));
@@ -702,7 +756,7 @@ extern "C" int32_t alac_b200_decode(alac_b200_engine *e, const void *cookie, uin
     CU_CHECK(e, e->d_chan.reserve(chan_words_per_lane * nlanes * 4));
     CU_CHECK(e, e->d_meta.reserve((size_t)P * nch * sizeof(DecChanMeta)));
     CU_CHECK(e, e->d_hdr.reserve((size_t)P * nch * sizeof(DecChanHdr)));
-    CU_CHECK(e, e->counters.reserve(64 * 4));
+    CU_CHECK(e, e->counters.reserve(64 * chunks.size()));
 
     CU_CHECK(e, cudaEventRecord(e->ev[0], st));
     const uint32_t *d_sizes;
@@ -734,6 +788,7 @@ extern "C" int32_t alac_b200_decode(alac_b200_engine *e, const void *cookie, uin
     } else {
         d_pcm = static_cast<uint8_t *>(pcm_out);
     }
+    CU_CHECK(e, cudaMemsetAsync(e->counters.p, 0, 64 * chunks.size(), st));     // class counters of every chunk
     // byte offsets of all packets at once (the sizes are all known up front)
     scan_u32_to_u64_kernel<<<1, 1024, 0, st>>>(d_sizes, e->d_pkt_off.as<uint64_t>(), P, nullptr, 0);
     e->launches += 1;
@@ -771,19 +826,17 @@ extern "C" int32_t alac_b200_decode(alac_b200_engine *e, const void *cookie, uin
         if (in_host) CU_CHECK(e, cudaStreamWaitEvent(cs, h2d_done[ci], 0));
         A.pkt_base = c.p0;
         A.num_packets = c.cnt;
-        A.class_count = e->counters.as<uint32_t>() + 16 * lane;
+        A.class_count = e->counters.as<uint32_t>() + 16 * ci;
         A.chan_scratch = e->d_chan.as<int32_t>() + chan_words_per_lane * lane;
-        CU_CHECK(e, cudaMemsetAsync(A.class_count, 0, 64, cs));
         dec_header_kernel<<<(c.cnt + 127) / 128, 128, 0, cs>>>(A);
         dec_perm_kernel<<<(c.cnt + 127) / 128, 128, 0, cs>>>(A);
         // output positions continue from the previous chunk's total
         if (multi && ci > 0) CU_CHECK(e, cudaStreamWaitEvent(cs, scan_done[ci - 1], 0));
-        scan_u32_to_u64_kernel<<<1, 1024, 0, cs>>>(A.pkt_samples + c.p0, e->d_out_frame.as<uint64_t>() + c.p0, c.cnt, nullptr, ci == 0 ? 0 : 1);
+        scan_u32_to_u64_kernel<<<1, 1024, 0, cs>>>(A.pkt_samples + c.p0, e->d_out_frame.as<uint64_t>() + c.p0, c.cnt, nullptr, ci == 0 ? 0 : 1, &e->h_totals[ci]);
         if (multi) scan_done.push_back(e->event_on(cs));
         e->launches += 3;
         if (!out_host) {
             // a caller-owned device buffer: its capacity must be known to hold before anything is written
-            CU_CHECK(e, cudaMemcpyAsync(&e->h_totals[ci], e->d_out_frame.as<uint64_t>() + c.p0 + c.cnt, 8, cudaMemcpyDeviceToHost, cs));
             CU_CHECK(e, cudaStreamSynchronize(cs));
             if (e->h_totals[ci] * bpf > pcm_cap) { e->err = "pcm capacity exceeded"; return ALAC_B200_PARAM_ERROR; }
         }
@@ -804,7 +857,6 @@ extern "C" int32_t alac_b200_decode(alac_b200_engine *e, const void *cookie, uin
         }
         t_dec.push_back(e->timer());
         e->launches += 2;
-        CU_CHECK(e, cudaMemcpyAsync(&e->h_totals[ci], e->d_out_frame.as<uint64_t>() + c.p0 + c.cnt, 8, cudaMemcpyDeviceToHost, cs));
         comp_done.push_back(e->event_on(cs));
     }
     e->cur = nullptr;

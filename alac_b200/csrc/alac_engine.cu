@@ -64,6 +64,7 @@ struct alac_b200_engine {
     // per-kernel timers: (start, stop) event pairs, grown on demand, reused across calls
     std::vector<cudaEvent_t> timers;
     size_t timers_used = 0;
+    std::vector<cudaEvent_t> t_mid;     // (before, between, after) of every two-kernel launch: search | final, entropy | finish
     cudaEvent_t event_on(cudaStream_t s)
     {
         if (timers_used == timers.size()) {
@@ -353,8 +354,11 @@ static void launch_search_v(alac_b200_engine *e, const EncArgs &A, uint32_t mono
         const uint64_t threads = (uint64_t)A.num_segments * pairs * 2;
         if (split) {
             const uint32_t ctas = (uint32_t)((threads + 31) / 32);
+            e->t_mid.push_back(e->timer());
             enc_search_split_kernel<DEPTH, true, PACKED, WRAP><<<ctas, 32, 0, e->cur>>>(A, pairs, pair_mask, *split);
+            e->t_mid.push_back(e->timer());
             enc_final_kernel<DEPTH, true, PACKED, WRAP><<<2 * ctas, 32, 0, e->cur>>>(A, *split, ctas);
+            e->t_mid.push_back(e->timer());
             e->launches++;
         } else {
             enc_search_kernel<DEPTH, true, PACKED, WRAP>
@@ -368,8 +372,11 @@ static void launch_search_v(alac_b200_engine *e, const EncArgs &A, uint32_t mono
             const uint32_t ctas = (uint32_t)((threads + 31) / 32);
             JobLists Qm = *split;
             Qm.counts += 2;     // the mono launch has its own pair of counters
+            e->t_mid.push_back(e->timer());
             enc_search_split_kernel<DEPTH, false, false, WRAP><<<ctas, 32, 0, e->cur>>>(A, monos, mono_mask, Qm);
+            e->t_mid.push_back(e->timer());
             enc_final_kernel<DEPTH, false, false, WRAP><<<2 * ctas, 32, 0, e->cur>>>(A, Qm, ctas);
+            e->t_mid.push_back(e->timer());
             e->launches++;
         } else {
             enc_search_kernel<DEPTH, false, false, WRAP>
@@ -416,6 +423,7 @@ extern "C" int32_t alac_b200_encode(alac_b200_engine *e, const alac_b200_enc_con
     CU_CHECK(e, cudaSetDevice(e->device));
     e->launches = 0;
     e->timers_used = 0;
+    e->t_mid.clear();
     std::vector<cudaEvent_t> t_search, t_asm;
 
     alac_b200_stream whole = {0, num_sample_frames};
@@ -687,6 +695,8 @@ extern "C" int32_t alac_b200_encode(alac_b200_engine *e, const alac_b200_enc_con
         cudaEventElapsedTime(&stats->ms_d2h, e->ev[2], e->ev[3]);
         for (size_t i = 0; i + 1 < t_search.size(); i += 2) { float ms = 0; cudaEventElapsedTime(&ms, t_search[i], t_search[i + 1]); stats->ms_search += ms; }
         for (size_t i = 0; i + 1 < t_asm.size(); i += 2) { float ms = 0; cudaEventElapsedTime(&ms, t_asm[i], t_asm[i + 1]); stats->ms_assemble += ms; }
+        for (size_t i = 0; i + 2 < e->t_mid.size(); i += 3) { float ms = 0; cudaEventElapsedTime(&ms, e->t_mid[i + 1], e->t_mid[i + 2]); stats->ms_final += ms; }
+        stats->ms_search -= stats->ms_final;
     }
     return ALAC_B200_OK;
 }
@@ -714,6 +724,7 @@ extern "C" int32_t alac_b200_decode(alac_b200_engine *e, const void *cookie, uin
     CU_CHECK(e, cudaSetDevice(e->device));
     e->launches = 0;
     e->timers_used = 0;
+    e->t_mid.clear();
     const uint32_t P = (uint32_t)num_packets;
     const uint64_t bpf = (uint64_t)bytes_per_sample(depth) * nch;
     cudaStream_t st = e->stream;
@@ -849,6 +860,7 @@ extern "C" int32_t alac_b200_decode(alac_b200_engine *e, const void *cookie, uin
         case 24: dec_entropy_kernel<24><<<lgrid, kRingStride, 0, cs>>>(A); break;
         default: dec_entropy_kernel<32><<<lgrid, kRingStride, 0, cs>>>(A); break;
         }
+        e->t_mid.push_back(e->timer());
         switch (depth) {
         case 16: dec_finish_kernel<16><<<fgrid, 64, 0, cs>>>(A); break;
         case 20: dec_finish_kernel<20><<<fgrid, 64, 0, cs>>>(A); break;
@@ -901,7 +913,12 @@ extern "C" int32_t alac_b200_decode(alac_b200_engine *e, const void *cookie, uin
         else cudaEventElapsedTime(&stats->ms_h2d, e->ev[0], e->ev[1]);
         cudaEventElapsedTime(&stats->ms_kernels, e->ev[1], e->ev[2]);
         cudaEventElapsedTime(&stats->ms_d2h, e->ev[2], e->ev[3]);
-        for (size_t i = 0; i + 1 < t_dec.size(); i += 2) { float ms = 0; cudaEventElapsedTime(&ms, t_dec[i], t_dec[i + 1]); stats->ms_decode += ms; }
+        for (size_t i = 0; i + 1 < t_dec.size(); i += 2) {
+            float ms = 0;
+            cudaEventElapsedTime(&ms, t_dec[i], t_dec[i + 1]); stats->ms_decode += ms;
+            cudaEventElapsedTime(&ms, t_dec[i], e->t_mid[i / 2]); stats->ms_entropy += ms;
+            cudaEventElapsedTime(&ms, e->t_mid[i / 2], t_dec[i + 1]); stats->ms_finish += ms;
+        }
     }
     return first_err;
 }

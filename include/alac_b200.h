@@ -71,9 +71,12 @@ typedef struct alac_b200_stats {
     uint32_t max_packet_bytes;
     uint32_t kernel_launches;     /* CUDA kernels launched by the call */
     float    ms_h2d, ms_kernels, ms_d2h;   /* CUDA-event times of the three phases */
-    float    ms_search;           /* encode: sum over launches of enc_search_kernel (the dominant kernel) */
+    float    ms_search;           /* encode: sum over launches of the search kernels (stages A+B; A+B+C when not split) */
     float    ms_assemble;         /* encode: sum over launches of enc_assemble_kernel */
-    float    ms_decode;           /* decode: dec_packet_kernel */
+    float    ms_decode;           /* decode: dec_entropy_kernel + dec_finish_kernel */
+    float    ms_final;            /* encode: sum over launches of enc_final_kernel (stage C, split form only) */
+    float    ms_entropy;          /* decode: sum over launches of dec_entropy_kernel */
+    float    ms_finish;           /* decode: sum over launches of dec_finish_kernel */
 } alac_b200_stats;
 
 /* ---- engine ------------------------------------------------------------------------------ */

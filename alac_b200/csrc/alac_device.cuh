@@ -320,7 +320,7 @@ struct BitPeek {
 constexpr uint32_t kRingSlots = 64;
 constexpr uint32_t kTopUpEvery = 8;
 #ifndef ALAC_DEC_LANES
-#define ALAC_DEC_LANES 128
+#define ALAC_DEC_LANES 32
 #endif
 constexpr uint32_t kRingStride = ALAC_DEC_LANES;     // lanes per CTA of the kernels that use BitReader
 static_assert(2 * kTopUpEvery * 66 + 4 * 32 <= kRingSlots * 32, "ring too small for the top-up cadence");

@@ -64,6 +64,8 @@ struct MixSrc {
                                   : PACKED ? (DEPTH == 16 ? 1 : DEPTH == 32 ? 2 : 3)
                                            : ((DEPTH == 16 || DEPTH == 32) ? 2 : 6);
     static constexpr int kAhead = kWords <= 2 ? 4 : 2;      // prefetch distance in samples
+    // 16-bit packed stereo: the main loop of predict_pass reads four sample-frames per 16-byte load
+    static constexpr bool kWide = STEREO && PACKED && DEPTH == 16;
     struct Raw { uint32_t w[kWords]; };
 
     const uint8_t *base;    // sample-frame 0 of the packet, first channel of the element
@@ -151,6 +153,31 @@ __device__ __forceinline__ void predict_pass(const Src &src, uint32_t num, int32
         prev = x;
     }
     if (num <= TAPS + 1) return;
+    if constexpr (Src::kWide) {
+        // head: single frames up to the next 16-byte boundary of the PCM
+        uint32_t j = TAPS + 1;
+        const uint32_t a0 = (uint32_t)(reinterpret_cast<uintptr_t>(src.base) >> 2);
+        for (; j < num && ((a0 + j) & 3u); j++) sink(j, predict_enc_step<TAPS, WRAP>(src.get(j), hist, a, chanshift));
+        // blocks of four frames, loads two blocks (eight samples) ahead of the arithmetic; unrolling by four also
+        // lets the history shift become register renaming
+        const uint32_t nblk = (num - j) >> 2;
+        if (nblk) {
+            const uint4 *p = reinterpret_cast<const uint4 *>(src.base + (size_t)j * 4u);
+            uint4 cur = __ldg(p), nxt = __ldg(p + min(1u, nblk - 1u));
+            for (uint32_t b = 0; b < nblk; b++, j += 4) {
+                const uint4 far = __ldg(p + min(b + 2u, nblk - 1u));
+                typename Src::Raw r;
+                r.w[0] = cur.x; sink(j, predict_enc_step<TAPS, WRAP>(src.mix(r), hist, a, chanshift));
+                r.w[0] = cur.y; sink(j + 1, predict_enc_step<TAPS, WRAP>(src.mix(r), hist, a, chanshift));
+                r.w[0] = cur.z; sink(j + 2, predict_enc_step<TAPS, WRAP>(src.mix(r), hist, a, chanshift));
+                r.w[0] = cur.w; sink(j + 3, predict_enc_step<TAPS, WRAP>(src.mix(r), hist, a, chanshift));
+                cur = nxt;
+                nxt = far;
+            }
+        }
+        for (; j < num; j++) sink(j, predict_enc_step<TAPS, WRAP>(src.get(j), hist, a, chanshift));
+        return;
+    }
     constexpr int D = Src::kAhead;
     const uint32_t last = num - 1;
     typename Src::Raw q[D];

@@ -20,8 +20,11 @@ res = {}
 for _ in range(3):
     e = eng.encode(pcm, cfg)
     d = eng.decode(e.cookie, e.packets, e.sizes, out=out)
-    res = {"lib": os.path.basename(os.environ.get("ALAC_B200_LIB", "default")), "search_ms": round(e.stats["ms_search"], 3),
+    res = {"lib": os.path.basename(os.environ.get("ALAC_B200_LIB", "default")), "depth": depth, "channels": ch, "sample_frames": frames,
+           "search_ms": round(e.stats["ms_search"], 3), "final_ms": round(e.stats["ms_final"], 3),
            "asm_ms": round(e.stats["ms_assemble"], 3), "enc_ms": round(e.stats["ms_kernels"], 3),
-           "dec_ms": round(d.stats["ms_decode"], 3), "dec_all_ms": round(d.stats["ms_kernels"], 3)}
+           "entropy_ms": round(d.stats["ms_entropy"], 3), "finish_ms": round(d.stats["ms_finish"], 3), "dec_all_ms": round(d.stats["ms_kernels"], 3),
+           "ratio": round(e.nbytes / pcm.numel(), 4),
+           "roundtrip_msamples_s": round(frames / ((e.stats["ms_kernels"] + d.stats["ms_kernels"]) / 1e3) / 1e6, 1)}
 assert torch.equal(d.pcm, pcm)
 print(json.dumps(res))

@@ -303,3 +303,116 @@ def test_decode_from_caf_table(engine):
     sizes = engine.ber_table_sizes(t_table, t_data.numel())
     dec = engine.decode(bytes(g["cookie"]), t_data, sizes)
     assert dec.status == 0 and np.array_equal(dec.pcm.cpu().numpy(), g["pcm"])
+
+
+# ---------------------------------------------------------------------------------------------
+# hand-crafted packets: syntax the encoder never emits but the decoder must accept
+# (codec/ALACDecoder.cu:660-694 general predictor headers, :1012-1059 FIL / DSE)
+# ---------------------------------------------------------------------------------------------
+def _craft_sce(oracle, x, chan_bits, num, den_shift, mode, pb_factor, coefs, frame=4096, partial=None):
+    """One SCE element holding x (int32, already within chan_bits): returns the element's bit list."""
+    from tests.bitpack import BitWriter
+    c = np.zeros(32, np.int16)
+    c[:num] = coefs[:num]
+    res = oracle.pc_block(x, c.copy(), num, chan_bits, den_shift)
+    if mode:
+        # the decoder undoes a first-difference pass (numactive 31) after dyn_decomp when mode != 0
+        res = oracle.pc_block(res, np.zeros(32, np.int16), 31, chan_bits, 0)
+    data, nbits, st = oracle.dyn_comp(res, chan_bits, pb=(40 * pb_factor) // 4)
+    assert st == 0
+    w = BitWriter()
+    w.put(0, 3); w.put(0, 4); w.put(0, 12)                      # ID_SCE, instance tag, unused
+    n = len(x)
+    is_partial = n != frame
+    w.put((int(is_partial) << 3) | 0, 4)                        # partial, bytesShifted = 0, escape = 0
+    if is_partial:
+        w.put(n, 32)
+    w.put(0, 8); w.put(0, 8)                                    # mixBits, mixRes
+    w.put((mode << 4) | den_shift, 8)
+    w.put((pb_factor << 5) | num, 8)
+    for k in range(num):
+        w.put(int(c[k]) & 0xffff, 16)
+    w.put_bytes(data, nbits)
+    return w.bits
+
+
+def _finish_packet(bit_list):
+    from tests.bitpack import BitWriter
+    w = BitWriter()
+    w.bits = list(bit_list)
+    w.put(7, 3)                                                 # ID_END
+    return w.to_bytes()
+
+
+@pytest.mark.parametrize("num,den_shift,mode,pb_factor", [(0, 9, 0, 4), (2, 9, 0, 4), (4, 8, 0, 4), (8, 9, 1, 4), (16, 9, 0, 4),
+                                                          (31, 9, 0, 4), (12, 6, 1, 2), (8, 9, 0, 7), (5, 10, 0, 4)])
+def test_decoder_general_predictor_headers(engine, oracle, num, den_shift, mode, pb_factor):
+    """Orders other than 4 / 8, denShift != 9, mode != 0 and pbFactor != 4: GPU == oracle decoder == source."""
+    import alac_b200
+    rng = np.random.default_rng(num * 100 + den_shift)
+    packets, sizes, want = [], [], []
+    for i in range(40):                                         # more than one warp of packets, ragged lengths
+        n = 4096 if i % 3 else int(rng.integers(40, 4096))
+        x = np.cumsum(rng.integers(-300, 301, n)).astype(np.int64)
+        x = (np.clip(x, -30000, 30000) + rng.integers(-40, 41, n)).astype(np.int32)
+        coefs = (oracle.init_coefs(32, den_shift).astype(np.int32) >> (0 if num <= 8 else 1)).astype(np.int16)
+        p = _finish_packet(_craft_sce(oracle, x, 16, num, den_shift, mode, pb_factor, coefs))
+        packets.append(p); sizes.append(len(p)); want.append(x.astype(np.int16))
+    cfg = alac_b200.EncoderConfig(channels=1, bit_depth=16)
+    cookie = alac_b200.magic_cookie(cfg)
+    blob, sz = np.concatenate(packets), np.array(sizes, np.uint32)
+    ref, st = oracle.Decoder(cookie).decode_stream(blob, sz)
+    assert not st.any()
+    assert np.array_equal(ref.view(np.int16), np.concatenate(want)), "oracle decoder disagrees with the crafted source"
+    dec = engine.decode(cookie, blob, sz)
+    assert dec.status == 0 and np.array_equal(dec.pcm, ref)
+
+
+def test_decoder_skips_fil_and_dse(engine, oracle):
+    """FIL and DSE elements in front of / between audio elements are skipped (codec/ALACDecoder.cu:1012-1059)."""
+    import alac_b200
+    from tests.bitpack import BitWriter, bits_of
+    g = np.load([p for p in _GOLDEN if "music_stereo16_k1" in p][0])
+    sizes, packets = g["sizes"], g["packets"]
+    rng = np.random.default_rng(5)
+    out_p, out_s, off = [], [], 0
+    for i, s in enumerate(sizes):
+        body = bits_of(packets[off:off + int(s)])
+        off += int(s)
+        w = BitWriter()
+        if i % 4 == 1:                                          # short FIL: count < 15
+            cnt = int(rng.integers(0, 15))
+            w.put(6, 3); w.put(cnt, 4)
+            for _ in range(cnt): w.put(int(rng.integers(0, 256)), 8)
+        elif i % 4 == 2:                                        # long FIL: count = 15 + ext - 1
+            ext = int(rng.integers(1, 40))
+            w.put(6, 3); w.put(15, 4); w.put(ext, 8)
+            for _ in range(15 + ext - 1): w.put(int(rng.integers(0, 256)), 8)
+        elif i % 4 == 3:                                        # DSE with byte alignment and a 255+ count
+            cnt = 255 + int(rng.integers(0, 30))
+            w.put(4, 3); w.put(3, 4); w.put(1, 1); w.put(255, 8); w.put(cnt - 255, 8)
+            w.align()
+            for _ in range(cnt): w.put(int(rng.integers(0, 256)), 8)
+        w.bits.extend(body)                                     # the original elements + ID_END (+ padding)
+        p = w.to_bytes()
+        out_p.append(p); out_s.append(len(p))
+    blob, sz = np.concatenate(out_p), np.array(out_s, np.uint32)
+    ref, st = oracle.Decoder(bytes(g["cookie"])).decode_stream(blob, sz)
+    assert not st.any() and np.array_equal(ref, g["pcm"])
+    dec = engine.decode(bytes(g["cookie"]), blob, sz)
+    assert dec.status == 0 and np.array_equal(dec.pcm, g["pcm"])
+
+
+def test_odd_frame_length_and_mixed_kinds_in_one_group(engine, oracle):
+    """A frame length that is not a multiple of the 32-sample tile, with escape (noise), run-heavy (silence) and
+    ordinary packets decoded side by side in the same 32-packet groups; stereo 24-bit exercises the shift region."""
+    import alac_b200
+    ch, depth, F = 2, 24, 1000
+    parts = []
+    for i in range(70):
+        kind = ["music", "noise", "silence", "music"][i % 4]
+        parts.append(synth.make(kind, F, ch, depth, seed=100 + i))
+    parts.append(synth.make("music", 333, ch, depth, seed=7))          # ragged tail frame
+    pcm = np.concatenate(parts)
+    got, _ = _check_encode(engine, oracle, pcm, ch, depth, K=1, frame_size=F)
+    _check_decode(engine, oracle, got, pcm)

@@ -51,6 +51,7 @@ struct DecChanMeta {
 };
 
 constexpr uint32_t kDecClasses = 16;
+constexpr uint32_t kRegularClasses = 4;     // classes below this are taken by dec_fused_kernel
 
 // walk element tags until the first SCE/LFE/CPE and return its sample count
 __global__ void dec_header_kernel(DecArgs A)
@@ -67,16 +68,24 @@ __global__ void dec_header_kernel(DecArgs A)
         if (!((br.pos >> 3) < size)) break;
         const uint32_t tag = br.get(3);
         if (tag == ID_SCE || tag == ID_LFE || tag == ID_CPE) {
-            br.pos += 4 + 12;
+            br.pos += 4;
+            const bool hdr_ok = br.get(12) == 0;
             const uint32_t hb = br.get(4);
             if (hb >> 3) { n = br.get(16) << 16; n |= br.get(16); }
-            if (!(hb & 1u)) {
-                // predictor orders of the first element: class = 3 * order(U) + order(V), order in {4, 8, other}
-                br.pos += 16 + 8;
-                const uint32_t nu = br.get(8) & 0x1fu;
-                uint32_t nv = 4;
-                if (tag == ID_CPE) { br.pos += nu * 16 + 8; nv = br.get(8) & 0x1fu; }
-                cls = 3 * (nu == 4 ? 0u : nu == 8 ? 1u : 2u) + (nv == 4 ? 0u : nv == 8 ? 1u : 2u);
+            const bool first = true;        // skipped FIL / DSE elements in front do not matter
+            if (!(hb & 1u) && ((hb >> 1) & 3u) != 3u) {
+                // predictor set-up of the first element.  Classes 0..3 are "regular" (what dec_fused_kernel takes):
+                // the element matches the channel count, mode 0, denShift 9, 4 or 8 taps -> class = 2 * [U has 8] + [V has 8].
+                // Other compressed elements: class = 4 + 3 * order(U) + order(V), order in {4, 8, other}.
+                const bool pair = (tag == ID_CPE);
+                br.pos += 16;
+                const uint32_t mu = br.get(8), nu = br.get(8) & 0x1fu;
+                uint32_t mv = (0u << 4) | kDenShift, nv = 4;
+                if (pair) { br.pos += nu * 16; mv = br.get(8); nv = br.get(8) & 0x1fu; }
+                const bool layout_ok = first && hdr_ok && (A.num_channels == (pair ? 2u : 1u)) && n <= A.frame_length;
+                const bool fast = mu == kDenShift && mv == kDenShift && (nu == 4 || nu == 8) && (nv == 4 || nv == 8);
+                if (layout_ok && fast) cls = 2 * (nu == 8 ? 1u : 0u) + (nv == 8 ? 1u : 0u);
+                else cls = kRegularClasses + 3 * (nu == 4 ? 0u : nu == 8 ? 1u : 2u) + (nv == 4 ? 0u : nv == 8 ? 1u : 2u);
             }
             break;
         } else if (tag == ID_DSE) {                 // codec/ALACDecoder.cu:1033-1059
@@ -160,6 +169,81 @@ __device__ __forceinline__ int32_t entropy_channel(BitReader &br, BitPeek &bp, u
     return ag.status;
 }
 
+constexpr uint32_t kTileRows = 32;
+constexpr uint32_t kTilePitch = 36;     // words per row: 32 lanes + 4 pad keeps rows 16-byte aligned and the
+                                        // transposed read of phase 3 at 4-way bank conflicts at most
+constexpr uint32_t kTileWords = kTileRows * kTilePitch;
+
+
+struct FinMeta {
+    uint64_t out_frame;
+    const uint8_t *pkt;
+    uint32_t pkt_size, n, shift_pos;
+    uint8_t kind, shift, mix_bits;
+    int8_t mix_res;
+};
+
+// 16-byte cp.async with zero-fill (src_bytes = 0 reads nothing)
+__device__ __forceinline__ void cp_async_16(uint32_t smem_dst, const void *gsrc, uint32_t src_bytes)
+{
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_dst), "l"(gsrc), "r"(src_bytes) : "memory");
+}
+
+// un-mix / merge / store one tile: lane = sample j0 + lane, loop over the group's packets (codec/ALACDecoder.cu:193-495)
+template <int DEPTH>
+__device__ __forceinline__ void flush_tile(const DecArgs &A, const FinMeta *metas, const int32_t *bu, const int32_t *bv, uint32_t j0,
+                                           uint32_t c, uint32_t lane, uint32_t pr0, uint32_t pr_step, bool out_pair32,
+                                           uint32_t zero_chans)
+{
+    constexpr uint32_t bps = DepthTraits<DEPTH>::kBytes;
+    const uint32_t stride = A.num_channels * bps;
+    const uint32_t j = j0 + lane;
+    for (uint32_t pr = pr0; pr < 32; pr += pr_step) {
+        const FinMeta &m = metas[pr];
+        if (m.kind == CH_PAIR_V || j >= m.n) continue;
+        uint8_t *out = A.pcm_out + (m.out_frame + j) * stride + (size_t)c * bps;
+        if (m.kind == CH_ZERO) {
+            for (uint32_t cc = 0; cc < zero_chans; cc++) store_sample<DEPTH>(out + cc * bps, 0);
+            continue;
+        }
+        int32_t l = bu[lane * kTilePitch + pr];
+        BitPeek bp;
+        if (m.shift) bp.start(m.pkt, m.pkt_size);
+        if (m.kind == CH_MONO) {
+            if (m.shift) l = (int32_t)(((uint32_t)l << m.shift) | bp.bits_at(m.shift_pos + j * m.shift, m.shift));   // :436-495
+            store_sample<DEPTH>(out, l);
+        } else {
+            const int32_t v = bv[lane * kTilePitch + pr];
+            int32_t r;
+            if (m.mix_res != 0) {                       // :193-223
+                l = l + v - (((int32_t)m.mix_res * v) >> m.mix_bits);
+                r = l - v;
+            } else {
+                r = v;
+            }
+            if (m.shift) {                              // :282-383
+                const uint32_t both = bp.bits_at(m.shift_pos + j * 2u * m.shift, 2u * m.shift);
+                l = (int32_t)(((uint32_t)l << m.shift) | (both >> m.shift));
+                r = (int32_t)(((uint32_t)r << m.shift) | (both & ((1u << m.shift) - 1u)));
+            }
+            if (DEPTH == 16 && out_pair32) {
+                *reinterpret_cast<uint32_t *>(out) = ((uint32_t)l & 0xffffu) | ((uint32_t)r << 16);
+            } else {
+                store_sample<DEPTH>(out, l);
+                store_sample<DEPTH>(out + bps, r);
+            }
+        }
+    }
+}
+
+// are all packets of the group regular?  (lanes past the last packet count as regular)
+__device__ __forceinline__ bool group_is_regular(const DecArgs &A, uint32_t group, uint32_t lane)
+{
+    const uint32_t slot = group * 32u + lane;
+    const uint32_t cls = slot < A.num_packets ? A.pkt_class[A.perm[A.pkt_base + slot]] : 0u;
+    return __all_sync(0xffffffffu, cls < kRegularClasses);
+}
+
 // ---- entropy kernel: one lane per packet ---------------------------------------------------------------------
 // The serial walk through the packet's bits (codec/ALACDecoder.cu:571-1002): element loop, headers, Golomb
 // streams, escape samples.  Residuals go to the channel tiles, headers to chan_hdr / chan_meta.
@@ -168,6 +252,8 @@ __global__ void __launch_bounds__(kRingStride) dec_entropy_kernel(DecArgs A)
 {
     __shared__ uint32_t s_ring[kRingSlots][kRingStride];
     const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
+    static_assert(kRingStride == 32, "one group of 32 packets per CTA");
+    if (group_is_regular(A, blockIdx.x, threadIdx.x)) return;          // dec_fused_kernel's group
     if (tid >= A.num_packets) return;
     const uint32_t pkt = A.perm[A.pkt_base + tid];
     const uint32_t nch = A.num_channels;
@@ -281,11 +367,6 @@ __global__ void __launch_bounds__(kRingStride) dec_entropy_kernel(DecArgs A)
 //      packet's 32 finished sample-frames are un-mixed, merged with their shift bytes, packed and stored as one
 //      contiguous run.
 // The class permutation makes the lanes of a warp run the same tap counts.
-constexpr uint32_t kTileRows = 32;
-constexpr uint32_t kTilePitch = 36;     // words per row: 32 lanes + 4 pad keeps rows 16-byte aligned and the
-                                        // transposed read of phase 3 at 4-way bank conflicts at most
-constexpr uint32_t kTileWords = kTileRows * kTilePitch;
-
 enum : uint32_t { PM_PASS = 0, PM_FAST4 = 1, PM_FAST8 = 2, PM_WRAP = 4 };
 struct PredState { int32_t a[8]; int32_t hist[9]; };
 
@@ -381,6 +462,7 @@ __device__ __noinline__ void unpc_general(int32_t *col, uint32_t n, DecChanHdr h
 
 // per-lane predictor set-up for one channel; returns the PM_* mode.  Channels the register paths do not cover
 // are finished right here, in place in global memory, and then pass through the tiles untouched.
+template <bool ALLOW_GENERAL = true>
 __device__ __forceinline__ uint32_t pred_setup(const DecChanHdr *hp, uint32_t n, int32_t *gcol, PredState &s)
 {
     const uint32_t num = hp->num;
@@ -401,23 +483,11 @@ __device__ __forceinline__ uint32_t pred_setup(const DecChanHdr *hp, uint32_t n,
         const bool safe = (uint32_t)amax + n <= 32767u;
         return (num == 4 ? PM_FAST4 : PM_FAST8) | (safe ? 0u : (uint32_t)PM_WRAP);
     }
-    unpc_general(gcol, n, *hp, chanshift);
-    __threadfence();        // other lanes of the warp copy these words into the tiles
+    if (ALLOW_GENERAL) {
+        unpc_general(gcol, n, *hp, chanshift);
+        __threadfence();    // other lanes of the warp copy these words into the tiles
+    }
     return PM_PASS;
-}
-
-struct FinMeta {
-    uint64_t out_frame;
-    const uint8_t *pkt;
-    uint32_t pkt_size, n, shift_pos;
-    uint8_t kind, shift, mix_bits;
-    int8_t mix_res;
-};
-
-// 16-byte cp.async with zero-fill (src_bytes = 0 reads nothing)
-__device__ __forceinline__ void cp_async_16(uint32_t smem_dst, const void *gsrc, uint32_t src_bytes)
-{
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_dst), "l"(gsrc), "r"(src_bytes) : "memory");
 }
 
 template <int DEPTH>
@@ -425,14 +495,13 @@ __global__ void __launch_bounds__(64) dec_finish_kernel(DecArgs A)
 {
     __shared__ __align__(16) int32_t s_tile[2][2][kTileWords];     // [buffer][channel c / c + 1][row * pitch + lane]
     __shared__ FinMeta s_meta[32];
-    constexpr uint32_t bps = DepthTraits<DEPTH>::kBytes;
-    const uint32_t nch = A.num_channels, F = A.frame_length;
+        const uint32_t nch = A.num_channels, F = A.frame_length;
     const uint32_t w = threadIdx.x >> 5, lane = threadIdx.x & 31u;      // warp w owns channel slot c + w
     const uint32_t group = blockIdx.x / nch, c = blockIdx.x - group * nch;
     const uint32_t slot = group * 32u + lane;
-    const uint32_t stride = nch * bps;
     // 16-bit stereo: one 32-bit store per sample-frame when the output is 4-byte aligned
     const bool out_pair32 = (nch == 2) && ((reinterpret_cast<uintptr_t>(A.pcm_out) & 3u) == 0);
+    if (group_is_regular(A, group, lane)) return;                       // dec_fused_kernel's group
 
     // ---- this lane's packet: what is channel slot c?  (both warps read the same records)
     FinMeta M;
@@ -491,47 +560,215 @@ __global__ void __launch_bounds__(64) dec_finish_kernel(DecArgs A)
         if (j0 < n_pred) unpc_rows_any(mode, st, s_tile[t & 1u][w] + lane, j0, 0, min(n_pred - j0, kTileRows), chanshift);
         __syncthreads();
         // ---- parallel phase: lane = sample; warp w takes the packets of its parity
-        const uint32_t j = j0 + lane;
-        for (uint32_t pr = w; pr < 32; pr += 2) {
-            const FinMeta &m = s_meta[pr];
-            if (m.kind == CH_PAIR_V || j >= m.n) continue;
-            uint8_t *out = A.pcm_out + (m.out_frame + j) * stride + (size_t)c * bps;
-            if (m.kind == CH_ZERO) {
-                store_sample<DEPTH>(out, 0);
-                continue;
-            }
-            int32_t l = bu[lane * kTilePitch + pr];
-            BitPeek bp;
-            if (m.shift) bp.start(m.pkt, m.pkt_size);
-            if (m.kind == CH_MONO) {
-                if (m.shift) l = (int32_t)(((uint32_t)l << m.shift) | bp.bits_at(m.shift_pos + j * m.shift, m.shift));   // :436-495
-                store_sample<DEPTH>(out, l);
-            } else {
-                const int32_t v = bv[lane * kTilePitch + pr];
-                int32_t r;
-                if (m.mix_res != 0) {                       // :193-223
-                    l = l + v - (((int32_t)m.mix_res * v) >> m.mix_bits);
-                    r = l - v;
-                } else {
-                    r = v;
-                }
-                if (m.shift) {                              // :282-383
-                    const uint32_t both = bp.bits_at(m.shift_pos + j * 2u * m.shift, 2u * m.shift);
-                    l = (int32_t)(((uint32_t)l << m.shift) | (both >> m.shift));
-                    r = (int32_t)(((uint32_t)r << m.shift) | (both & ((1u << m.shift) - 1u)));
-                }
-                if (DEPTH == 16 && out_pair32) {
-                    *reinterpret_cast<uint32_t *>(out) = ((uint32_t)l & 0xffffu) | ((uint32_t)r << 16);
-                } else {
-                    store_sample<DEPTH>(out, l);
-                    store_sample<DEPTH>(out + bps, r);
-                }
-            }
-        }
+        flush_tile<DEPTH>(A, s_meta, bu, bv, j0, c, lane, w, 2, out_pair32, 1);
         __syncthreads();
         request(t + 2);                 // refills the buffer just drained (an empty group past the last tile)
     }
     cp_async_wait<0>();
+}
+
+// ---- fused decode kernel: regular mono / stereo packets ---------------------------------------------------------------
+// A CTA is one group of 32 packets and two warps that run concurrently:
+//   warp 0 (entropy): lane = packet.  Parses the element header, then decodes the Golomb streams of channel 0 and
+//           channel 1 tile by tile (32 samples x 32 packets) into shared memory;
+//   warp 1 (finish):  consumes each tile as it becomes ready: predictor down each lane's column (lane = packet), then,
+//           with the roles flipped (lane = sample), un-mix / shift-merge / pack / store as in dec_finish_kernel.
+// The two serial chains of a packet (entropy coder and predictor) thus overlap instead of adding up, and the residuals
+// never leave the SM.  Only the finished U samples of a stereo pair make one trip through the channel scratch, because
+// the whole U stream precedes the V stream in the packet.  Hand-off uses two residual buffers and four named barriers
+// (FULL / EMPTY per buffer, 64 participants each: 32 arrive, 32 wait).
+// "Regular" (classes 0..3 of dec_header_kernel) means: exactly one element that matches the channel count, compressed,
+// predictor mode 0, denShift 9, 4 or 8 taps.  Every lane of the entropy warp then executes the same tile loop, which the
+// barrier protocol needs; groups holding any other packet are left to dec_entropy_kernel + dec_finish_kernel.
+enum : uint32_t { BAR_FULL0 = 1, BAR_EMPTY0 = 3 };      // + buffer index
+
+// Barrier numbers are immediates (a register operand makes ptxas reserve all 16 barriers for the CTA, which caps
+// the SM at 4 resident CTAs); `second` selects buffer 1.
+template <uint32_t ID> __device__ __forceinline__ void bar_sync64() { asm volatile("bar.sync %0, 64;" ::"n"(ID) : "memory"); }
+template <uint32_t ID> __device__ __forceinline__ void bar_arrive64() { asm volatile("bar.arrive %0, 64;" ::"n"(ID) : "memory"); }
+template <uint32_t ID0> __device__ __forceinline__ void named_sync(bool second)
+{
+    if (second) bar_sync64<ID0 + 1>(); else bar_sync64<ID0>();
+}
+template <uint32_t ID0> __device__ __forceinline__ void named_arrive(bool second)
+{
+    __threadfence_block();      // what this warp wrote to the buffer is visible to the warp that waits
+    if (second) bar_arrive64<ID0 + 1>(); else bar_arrive64<ID0>();
+}
+
+template <int DEPTH>
+__global__ void __launch_bounds__(64) dec_fused_kernel(DecArgs A)
+{
+    __shared__ uint32_t s_ring[kRingSlots][32];
+    __shared__ __align__(16) int32_t s_res[2][kTileWords];      // residual tiles: entropy warp -> finish warp
+    __shared__ __align__(16) int32_t s_xu[kTileWords];          // finished U tile, back from the scratch (stereo, V phase)
+    __shared__ FinMeta s_meta[32];
+    __shared__ uint32_t s_nmax;
+
+    const uint32_t w = threadIdx.x >> 5, lane = threadIdx.x & 31u;
+    const uint32_t group = blockIdx.x;
+    if (!group_is_regular(A, group, lane)) return;              // both warps agree
+    const uint32_t nch = A.num_channels, F = A.frame_length;    // 1 or 2 here
+    const uint32_t slot = group * 32u + lane;
+    const bool valid = slot < A.num_packets;
+    const uint32_t pkt = valid ? A.perm[A.pkt_base + slot] : 0u;
+    int32_t *gtile_u = A.chan_scratch + ((size_t)(group * nch) * F) * 32u;
+    const bool out_pair32 = (nch == 2) && ((reinterpret_cast<uintptr_t>(A.pcm_out) & 3u) == 0);
+
+    if (w == 0) {
+        // ================= entropy warp =================
+        const uint32_t size = valid ? A.pkt_size[pkt] : 0u;
+        const uint32_t cap_bits = size * 8u;
+        const uint32_t slot_samples = valid ? A.pkt_samples[pkt] : 0u;
+        const uint8_t *packet = A.packets + (valid ? A.pkt_off[pkt] : 0u);
+        int32_t status = 0;
+        uint32_t n = 0;
+        ChanHeader hu, hv;
+        hu.pb_factor = hv.pb_factor = 4;
+        uint32_t chan_bits = DEPTH;
+        FinMeta M;
+        M.kind = valid ? (uint8_t)CH_ZERO : (uint8_t)CH_PAIR_V; M.n = slot_samples; M.out_frame = valid ? A.out_frame[pkt] : 0u;
+        M.pkt = packet; M.pkt_size = size; M.shift_pos = 0; M.shift = 0; M.mix_bits = 0; M.mix_res = 0;
+        BitPeek bp;
+        bp.start(packet, size);
+        if (valid) {
+            // the same walk as dec_entropy_kernel up to the first audio element (codec/ALACDecoder.cu:571-694)
+            for (int guard = 0; guard < 64 && status == 0; guard++) {
+                if (!((bp.pos >> 3) < size)) { status = -50; break; }
+                const uint32_t tag = bp.get(3);
+                if (tag == ID_SCE || tag == ID_LFE || tag == ID_CPE) {
+                    const bool pair = (tag == ID_CPE);
+                    bp.pos += 4;
+                    if (bp.get(12) != 0) { status = -50; break; }
+                    const uint32_t hb = bp.get(4);
+                    const uint32_t bytes_shifted = (hb >> 1) & 3u;
+                    n = F;
+                    if (hb >> 3) { n = bp.get(16) << 16; n |= bp.get(16); }
+                    if (bytes_shifted == 3 || (hb & 1u) || n > slot_samples || pair != (nch == 2)) { status = -50; break; }   // excluded by the class
+                    chan_bits = DEPTH - bytes_shifted * 8 + (pair ? 1u : 0u);
+                    M.mix_bits = (uint8_t)bp.get(8);
+                    M.mix_res = (int8_t)bp.get(8);
+                    read_chan_header(bp, hu);
+                    if (pair) read_chan_header(bp, hv);
+                    if (bytes_shifted) {
+                        M.shift = (uint8_t)(bytes_shifted * 8);
+                        M.shift_pos = bp.pos;
+                        bp.pos += M.shift * (pair ? 2u : 1u) * n;
+                    }
+                    M.kind = pair ? CH_PAIR_U : CH_MONO;
+                    M.n = n;
+                    break;
+                } else if (tag == ID_DSE) {
+                    bp.pos += 4;
+                    const uint32_t align = bp.get(1);
+                    uint32_t count = bp.get(8);
+                    if (count == 255) count += bp.get(8);
+                    if (align && (bp.pos & 7u)) bp.pos += 8u - (bp.pos & 7u);
+                    bp.pos += count * 8;
+                    if ((bp.pos >> 3) > size) status = -50;
+                } else if (tag == ID_FIL) {
+                    int32_t count = (int32_t)bp.get(4);
+                    if (count == 15) count += (int32_t)bp.get(8) - 1;
+                    bp.pos += (uint32_t)count * 8;
+                    if ((bp.pos >> 3) > size) status = -50;
+                } else {
+                    status = -50;
+                }
+            }
+            if (status) { n = 0; M.kind = CH_ZERO; M.n = slot_samples; }      // zero-filled like any failed packet
+            else {
+                DecChanHdr *hdrs = A.chan_hdr + (size_t)pkt * nch;
+                store_chan_hdr(&hdrs[0], hu, chan_bits);
+                if (nch == 2) store_chan_hdr(&hdrs[1], hv, chan_bits);
+            }
+        }
+        s_meta[lane] = M;
+        const uint32_t n_max = __reduce_max_sync(0xffffffffu, valid ? M.n : 0u);     // failed packets are zero-filled to their slot size
+        if (lane == 0) s_nmax = n_max;
+        __threadfence_block();
+        __syncthreads();                                        // (1) headers and metas are out
+        const uint32_t tiles = (n_max + kTileRows - 1) / kTileRows;
+        BitReader br;
+        br.start(packet, size, &s_ring[0][lane]);
+        br.seek(bp.pos);
+        for (uint32_t c = 0; c < nch; c++) {
+            AgDec ag;
+            ag.start(br, n, A.mb, (A.pb * (c ? hv.pb_factor : hu.pb_factor)) / 4, A.kb, chan_bits);     // codec/ALACDecoder.cu:682
+            for (uint32_t t = 0; t < tiles; t++) {
+                const uint32_t b = t & 1u;
+                __syncwarp();
+                named_sync<BAR_EMPTY0>(b != 0);
+                int32_t *col = s_res[b] + lane;
+                const uint32_t j0 = t * kTileRows;
+#pragma unroll 1
+                for (uint32_t r = 0; r < kTileRows; r++) {
+                    if (j0 + r < n) col[r * kTilePitch] = ag.next(br, cap_bits);
+                    if ((r & (kTopUpEvery - 1u)) == kTopUpEvery - 1u) br.top_up();
+                }
+                __syncwarp();
+                named_arrive<BAR_FULL0>(b != 0);
+            }
+            // dyn_decomp's exit check "cur <= end" (codec/ag_dec.c:359)
+            if (!ag.status && (br.pos >> 3) > (cap_bits >> 3)) ag.status = -50;
+            if (n && !status) status = ag.status;
+            __syncthreads();                                    // (2) the finish warp is done with this channel's tiles
+        }
+        cp_async_wait<0>();
+        if (valid) A.pkt_status[pkt] = status;
+        return;
+    }
+
+    // ================= finish warp =================
+    __syncthreads();                                            // (1)
+    const uint32_t n_max = s_nmax;
+    const uint32_t tiles = (n_max + kTileRows - 1) / kTileRows;
+    const FinMeta M = s_meta[lane];
+    const bool mine = (M.kind == CH_MONO || M.kind == CH_PAIR_U);
+    const uint32_t n_pred = mine ? M.n : 0u;
+    for (uint32_t c = 0; c < nch; c++) {
+        PredState st;
+        uint32_t mode = PM_PASS, chanshift = 0;
+        if (mine) {
+            const DecChanHdr *hp = A.chan_hdr + (size_t)pkt * nch + c;
+            chanshift = 32u - hp->chan_bits;
+            mode = pred_setup<false>(hp, M.n, nullptr, st);     // regular: a register path, never the general one
+        }
+        const bool last_chan = (c + 1 == nch);
+        for (uint32_t b = 0; b < min(tiles, 2u); b++) named_arrive<BAR_EMPTY0>(b != 0);   // both buffers start empty
+        for (uint32_t t = 0; t < tiles; t++) {
+            const uint32_t b = t & 1u;
+            const uint32_t j0 = t * kTileRows;
+            if (nch == 2 && last_chan) {
+                // the finished U tile comes back from the scratch while this warp waits for the V residuals
+#pragma unroll
+                for (uint32_t i = 0; i < 8; i++) {
+                    const uint32_t ch = i * 32u + lane, row = ch >> 3, part = ch & 7u;
+                    const bool in = j0 + row < F;
+                    cp_async_16((uint32_t)__cvta_generic_to_shared(s_xu + row * kTilePitch + part * 4u),
+                                gtile_u + (size_t)(in ? j0 + row : 0u) * 32u + part * 4u, in ? 16u : 0u);
+                }
+                cp_async_commit();
+            }
+            __syncwarp();
+            named_sync<BAR_FULL0>(b != 0);
+            int32_t *buf = s_res[b];
+            if (j0 < n_pred) unpc_rows_any(mode, st, buf + lane, j0, 0, min(n_pred - j0, kTileRows), chanshift);
+            if (!last_chan) {
+                // U of a pair: park the finished column in the scratch (one 128-byte row per store)
+                int32_t *g = gtile_u + (size_t)j0 * 32u + lane;
+                for (uint32_t r = 0; r < kTileRows && j0 + r < F; r++) g[(size_t)r * 32u] = buf[r * kTilePitch + lane];
+            } else {
+                cp_async_wait<0>();
+                __syncwarp();
+                flush_tile<DEPTH>(A, s_meta, nch == 2 ? s_xu : buf, buf, j0, 0, lane, 0, 1, out_pair32, nch);
+                __syncwarp();
+            }
+            __syncwarp();
+            if (t + 2 < tiles) named_arrive<BAR_EMPTY0>(b != 0);
+        }
+        __threadfence_block();
+        __syncthreads();                                        // (2)
+    }
 }
 
 // ---- CAF packet table on the device -------------------------------------------------------

@@ -61,6 +61,7 @@ struct alac_b200_engine {
     // decode
     DevBuf d_packets, d_sizes, d_pkt_off, d_pkt_samples, d_out_frame, d_status, d_pcm, d_class, d_rank, d_perm, d_chan, d_meta, d_hdr, jobs, job_counts;
     uint32_t launches = 0;
+    bool decode_configured = false;
     // per-kernel timers: (start, stop) event pairs, grown on demand, reused across calls
     std::vector<cudaEvent_t> timers;
     size_t timers_used = 0;
@@ -704,6 +705,23 @@ extern "C" int32_t alac_b200_encode(alac_b200_engine *e, const alac_b200_enc_con
 // ------------------------------------------------------------------------------------------------
 // decode
 // ------------------------------------------------------------------------------------------------
+// The decode kernels keep their tiles / rings in static shared memory and want 8-9 CTAs per SM resident (one
+// wave for the 1-hour workload).  With the default carve-out the driver leaves most of the 228 KB to L1 and only
+// about half of those CTAs fit, so ask for the maximum shared-memory carve-out once per device.
+template <class K> static void prefer_max_shared(K kernel)
+{
+    cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+}
+static void configure_decode_kernels()
+{
+    prefer_max_shared(dec_fused_kernel<16>); prefer_max_shared(dec_fused_kernel<20>);
+    prefer_max_shared(dec_fused_kernel<24>); prefer_max_shared(dec_fused_kernel<32>);
+    prefer_max_shared(dec_finish_kernel<16>); prefer_max_shared(dec_finish_kernel<20>);
+    prefer_max_shared(dec_finish_kernel<24>); prefer_max_shared(dec_finish_kernel<32>);
+    prefer_max_shared(dec_entropy_kernel<16>); prefer_max_shared(dec_entropy_kernel<20>);
+    prefer_max_shared(dec_entropy_kernel<24>); prefer_max_shared(dec_entropy_kernel<32>);
+}
+
 extern "C" int32_t alac_b200_decode(alac_b200_engine *e, const void *cookie, uint32_t cookie_size, const void *packets,
                                     const uint32_t *packet_sizes, uint64_t num_packets, int32_t in_mem, void *pcm_out,
                                     uint64_t pcm_cap, uint32_t *packet_samples, int32_t *packet_status, int32_t out_mem,
@@ -722,6 +740,7 @@ extern "C" int32_t alac_b200_decode(alac_b200_engine *e, const void *cookie, uin
     if ((!packets || !packet_sizes || !pcm_out) && num_packets) return ALAC_B200_PARAM_ERROR;
     if (num_packets == 0) return ALAC_B200_OK;
     CU_CHECK(e, cudaSetDevice(e->device));
+    if (!e->decode_configured) { configure_decode_kernels(); e->decode_configured = true; }
     e->launches = 0;
     e->timers_used = 0;
     e->t_mid.clear();
@@ -853,7 +872,21 @@ extern "C" int32_t alac_b200_decode(alac_b200_engine *e, const void *cookie, uin
         }
         t_dec.push_back(e->timer());
         const uint32_t lgrid = (c.cnt + kRingStride - 1) / kRingStride;
-        const uint32_t fgrid = ((c.cnt + 31) / 32) * nch;
+        const uint32_t groups_c = (c.cnt + 31) / 32;
+        const uint32_t fgrid = groups_c * nch;
+        // regular mono / stereo groups: entropy and finish warps side by side in one kernel
+        if (nch <= 2) {
+            switch (depth) {
+            case 16: dec_fused_kernel<16><<<groups_c, 64, 0, cs>>>(A); break;
+            case 20: dec_fused_kernel<20><<<groups_c, 64, 0, cs>>>(A); break;
+            case 24: dec_fused_kernel<24><<<groups_c, 64, 0, cs>>>(A); break;
+            default: dec_fused_kernel<32><<<groups_c, 64, 0, cs>>>(A); break;
+            }
+            e->launches += 1;
+        }
+        e->t_mid.push_back(e->timer());
+        // everything else (multichannel, escapes, other predictor set-ups): the two general kernels; groups the
+        // fused kernel took return at once
         switch (depth) {
         case 16: dec_entropy_kernel<16><<<lgrid, kRingStride, 0, cs>>>(A); break;
         case 20: dec_entropy_kernel<20><<<lgrid, kRingStride, 0, cs>>>(A); break;
@@ -916,8 +949,9 @@ extern "C" int32_t alac_b200_decode(alac_b200_engine *e, const void *cookie, uin
         for (size_t i = 0; i + 1 < t_dec.size(); i += 2) {
             float ms = 0;
             cudaEventElapsedTime(&ms, t_dec[i], t_dec[i + 1]); stats->ms_decode += ms;
-            cudaEventElapsedTime(&ms, t_dec[i], e->t_mid[i / 2]); stats->ms_entropy += ms;
-            cudaEventElapsedTime(&ms, e->t_mid[i / 2], t_dec[i + 1]); stats->ms_finish += ms;
+            cudaEventElapsedTime(&ms, t_dec[i], e->t_mid[i]); stats->ms_fused += ms;
+            cudaEventElapsedTime(&ms, e->t_mid[i], e->t_mid[i + 1]); stats->ms_entropy += ms;
+            cudaEventElapsedTime(&ms, e->t_mid[i + 1], t_dec[i + 1]); stats->ms_finish += ms;
         }
     }
     return first_err;

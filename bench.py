@@ -246,7 +246,7 @@ def run_cuda(args):
     barrier()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     launches = 0
-    ms_search = ms_final = ms_asm = ms_dec = ms_ent = ms_fin = ms_enc_k = ms_dec_k = 0.0
+    ms_search = ms_final = ms_asm = ms_dec = ms_ent = ms_fin = ms_fus = ms_enc_k = ms_dec_k = 0.0
     ev0.record()
     for _ in range(args.steps):
         e_, d_ = step_device()
@@ -257,6 +257,7 @@ def run_cuda(args):
         ms_dec += d_.stats["ms_decode"]
         ms_ent += d_.stats["ms_entropy"]
         ms_fin += d_.stats["ms_finish"]
+        ms_fus += d_.stats["ms_fused"]
         ms_enc_k += e_.stats["ms_kernels"]
         ms_dec_k += d_.stats["ms_kernels"]
     ev1.record()
@@ -327,13 +328,14 @@ def run_cuda(args):
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
     peak_kind = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6.65 TB/s"
     # per-kernel CUDA-event times (recorded by the engine on the launching stream), ms per step
-    kernels = {"enc_search_split": ms_search / args.steps, "enc_final": ms_final / args.steps, "enc_assemble": ms_asm / args.steps,
+    kernels = {"enc_search_split": ms_search / args.steps, "enc_final": ms_final / args.steps, "enc_assemble": ms_asm / args.steps, "dec_fused": ms_fus / args.steps,
                "dec_entropy": ms_ent / args.steps, "dec_finish": ms_fin / args.steps}
     # algorithmic bytes per launch: what the kernel must read and write once
     pcm_bytes, chan_bytes = pcm_d.numel(), 4 * CHANNELS * frames_total
     alg = {"enc_search_split": pcm_bytes // 8 * 5 + pcm_bytes // 8,     # stage A reads n/8 five times, stage B re-reads n/8 (cache hits: counted once each)
            "enc_final": pcm_bytes + payload,                            # PCM once, Golomb streams once
            "enc_assemble": 2 * payload,
+           "dec_fused": payload + chan_bytes + pcm_bytes,               # packets once, the U channel once out and back, PCM once
            "dec_entropy": payload + chan_bytes,                          # packets once, one int32 residual per channel-sample
            "dec_finish": chan_bytes + pcm_bytes}
     dominant = max(kernels, key=kernels.get)

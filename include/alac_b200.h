@@ -73,10 +73,11 @@ typedef struct alac_b200_stats {
     float    ms_h2d, ms_kernels, ms_d2h;   /* CUDA-event times of the three phases */
     float    ms_search;           /* encode: sum over launches of the search kernels (stages A+B; A+B+C when not split) */
     float    ms_assemble;         /* encode: sum over launches of enc_assemble_kernel */
-    float    ms_decode;           /* decode: dec_entropy_kernel + dec_finish_kernel */
+    float    ms_decode;           /* decode: dec_fused_kernel + dec_entropy_kernel + dec_finish_kernel */
     float    ms_final;            /* encode: sum over launches of enc_final_kernel (stage C, split form only) */
-    float    ms_entropy;          /* decode: sum over launches of dec_entropy_kernel */
-    float    ms_finish;           /* decode: sum over launches of dec_finish_kernel */
+    float    ms_entropy;          /* decode: sum over launches of dec_entropy_kernel (groups the fused kernel does not take) */
+    float    ms_finish;           /* decode: sum over launches of dec_finish_kernel (same) */
+    float    ms_fused;            /* decode: sum over launches of dec_fused_kernel (regular mono / stereo groups) */
 } alac_b200_stats;
 
 /* ---- engine ------------------------------------------------------------------------------ */

@@ -160,11 +160,10 @@ __device__ __forceinline__ int32_t entropy_channel(BitReader &br, BitPeek &bp, u
     AgDec ag;
     ag.start(br, n, A.mb, (A.pb * h.pb_factor) / 4, A.kb, chan_bits);       // codec/ALACDecoder.cu:682
     for (uint32_t j = 0; j < n; j++) {
-        dst[(size_t)j * 32u] = ag.next(br, cap_bits);
+        dst[(size_t)j * 32u] = ag.at(br, j);
         if ((j & (kTopUpEvery - 1u)) == kTopUpEvery - 1u) br.top_up();
     }
-    // dyn_decomp's exit check "cur <= end" (codec/ag_dec.c:359)
-    if (!ag.status && (br.pos >> 3) > (cap_bits >> 3)) ag.status = -50;
+    ag.finish(br, cap_bits);
     bp.pos = br.pos;
     return ag.status;
 }
@@ -175,13 +174,16 @@ constexpr uint32_t kTilePitch = 36;     // words per row: 32 lanes + 4 pad keeps
 constexpr uint32_t kTileWords = kTileRows * kTilePitch;
 
 
-struct FinMeta {
-    uint64_t out_frame;
-    const uint8_t *pkt;
-    uint32_t pkt_size, n, shift_pos;
+// what the parallel phase needs to know about one packet; the first 16 bytes are all the common case reads
+struct __align__(16) FinMeta {
+    uint8_t *out0;          // where sample-frame 0 of this packet's channel slot goes
+    uint32_t n;
     uint8_t kind, shift, mix_bits;
     int8_t mix_res;
+    const uint8_t *pkt;     // for the shift region
+    uint32_t pkt_size, shift_pos;
 };
+static_assert(sizeof(FinMeta) == 32, "FinMeta is read as two 16-byte halves");
 
 // 16-byte cp.async with zero-fill (src_bytes = 0 reads nothing)
 __device__ __forceinline__ void cp_async_16(uint32_t smem_dst, const void *gsrc, uint32_t src_bytes)
@@ -192,39 +194,41 @@ __device__ __forceinline__ void cp_async_16(uint32_t smem_dst, const void *gsrc,
 // un-mix / merge / store one tile: lane = sample j0 + lane, loop over the group's packets (codec/ALACDecoder.cu:193-495)
 template <int DEPTH>
 __device__ __forceinline__ void flush_tile(const DecArgs &A, const FinMeta *metas, const int32_t *bu, const int32_t *bv, uint32_t j0,
-                                           uint32_t c, uint32_t lane, uint32_t pr0, uint32_t pr_step, bool out_pair32,
-                                           uint32_t zero_chans)
+                                           uint32_t lane, uint32_t pr0, uint32_t pr_step, bool out_pair32, uint32_t zero_chans)
 {
     constexpr uint32_t bps = DepthTraits<DEPTH>::kBytes;
     const uint32_t stride = A.num_channels * bps;
     const uint32_t j = j0 + lane;
     for (uint32_t pr = pr0; pr < 32; pr += pr_step) {
-        const FinMeta &m = metas[pr];
-        if (m.kind == CH_PAIR_V || j >= m.n) continue;
-        uint8_t *out = A.pcm_out + (m.out_frame + j) * stride + (size_t)c * bps;
-        if (m.kind == CH_ZERO) {
+        const uint4 q = *reinterpret_cast<const uint4 *>(&metas[pr]);          // out0, n, {kind, shift, mix_bits, mix_res}
+        const uint32_t n = q.z, kind = q.w & 0xffu, shift = (q.w >> 8) & 0xffu, mix_bits = (q.w >> 16) & 0xffu;
+        const int32_t mix_res = (int32_t)q.w >> 24;
+        if (kind == CH_PAIR_V || j >= n) continue;
+        uint8_t *out = reinterpret_cast<uint8_t *>(((uint64_t)q.y << 32) | q.x) + (size_t)j * stride;
+        if (kind == CH_ZERO) {
             for (uint32_t cc = 0; cc < zero_chans; cc++) store_sample<DEPTH>(out + cc * bps, 0);
             continue;
         }
         int32_t l = bu[lane * kTilePitch + pr];
         BitPeek bp;
-        if (m.shift) bp.start(m.pkt, m.pkt_size);
-        if (m.kind == CH_MONO) {
-            if (m.shift) l = (int32_t)(((uint32_t)l << m.shift) | bp.bits_at(m.shift_pos + j * m.shift, m.shift));   // :436-495
+        uint32_t shift_pos = 0;
+        if (shift) { const FinMeta &m = metas[pr]; bp.start(m.pkt, m.pkt_size); shift_pos = m.shift_pos; }
+        if (kind == CH_MONO) {
+            if (shift) l = (int32_t)(((uint32_t)l << shift) | bp.bits_at(shift_pos + j * shift, shift));       // :436-495
             store_sample<DEPTH>(out, l);
         } else {
             const int32_t v = bv[lane * kTilePitch + pr];
             int32_t r;
-            if (m.mix_res != 0) {                       // :193-223
-                l = l + v - (((int32_t)m.mix_res * v) >> m.mix_bits);
+            if (mix_res != 0) {                         // :193-223
+                l = l + v - ((mix_res * v) >> mix_bits);
                 r = l - v;
             } else {
                 r = v;
             }
-            if (m.shift) {                              // :282-383
-                const uint32_t both = bp.bits_at(m.shift_pos + j * 2u * m.shift, 2u * m.shift);
-                l = (int32_t)(((uint32_t)l << m.shift) | (both >> m.shift));
-                r = (int32_t)(((uint32_t)r << m.shift) | (both & ((1u << m.shift) - 1u)));
+            if (shift) {                                // :282-383
+                const uint32_t both = bp.bits_at(shift_pos + j * 2u * shift, 2u * shift);
+                l = (int32_t)(((uint32_t)l << shift) | (both >> shift));
+                r = (int32_t)(((uint32_t)r << shift) | (both & ((1u << shift) - 1u)));
             }
             if (DEPTH == 16 && out_pair32) {
                 *reinterpret_cast<uint32_t *>(out) = ((uint32_t)l & 0xffffu) | ((uint32_t)r << 16);
@@ -504,14 +508,15 @@ __global__ void __launch_bounds__(64) dec_finish_kernel(DecArgs A)
     if (group_is_regular(A, group, lane)) return;                       // dec_fused_kernel's group
 
     // ---- this lane's packet: what is channel slot c?  (both warps read the same records)
+    constexpr uint32_t bps = DepthTraits<DEPTH>::kBytes;
     FinMeta M;
-    M.kind = CH_PAIR_V; M.n = 0; M.out_frame = 0; M.pkt = nullptr; M.pkt_size = 0; M.shift_pos = 0; M.shift = 0; M.mix_bits = 0; M.mix_res = 0;
+    M.kind = CH_PAIR_V; M.n = 0; M.out0 = nullptr; M.pkt = nullptr; M.pkt_size = 0; M.shift_pos = 0; M.shift = 0; M.mix_bits = 0; M.mix_res = 0;
     uint32_t pkt = 0;
     if (slot < A.num_packets) {
         pkt = A.perm[A.pkt_base + slot];
         const DecChanMeta m = A.chan_meta[(size_t)pkt * nch + c];
         M.kind = m.kind; M.n = m.n; M.shift_pos = m.shift_pos; M.shift = m.shift; M.mix_bits = m.mix_bits; M.mix_res = m.mix_res;
-        M.out_frame = A.out_frame[pkt];
+        M.out0 = A.pcm_out + A.out_frame[pkt] * (nch * bps) + (size_t)c * bps;
         M.pkt = A.packets + A.pkt_off[pkt];
         M.pkt_size = A.pkt_size[pkt];
     }
@@ -560,7 +565,7 @@ __global__ void __launch_bounds__(64) dec_finish_kernel(DecArgs A)
         if (j0 < n_pred) unpc_rows_any(mode, st, s_tile[t & 1u][w] + lane, j0, 0, min(n_pred - j0, kTileRows), chanshift);
         __syncthreads();
         // ---- parallel phase: lane = sample; warp w takes the packets of its parity
-        flush_tile<DEPTH>(A, s_meta, bu, bv, j0, c, lane, w, 2, out_pair32, 1);
+        flush_tile<DEPTH>(A, s_meta, bu, bv, j0, lane, w, 2, out_pair32, 1);
         __syncthreads();
         request(t + 2);                 // refills the buffer just drained (an empty group past the last tile)
     }
@@ -627,7 +632,8 @@ __global__ void __launch_bounds__(64) dec_fused_kernel(DecArgs A)
         hu.pb_factor = hv.pb_factor = 4;
         uint32_t chan_bits = DEPTH;
         FinMeta M;
-        M.kind = valid ? (uint8_t)CH_ZERO : (uint8_t)CH_PAIR_V; M.n = slot_samples; M.out_frame = valid ? A.out_frame[pkt] : 0u;
+        M.kind = valid ? (uint8_t)CH_ZERO : (uint8_t)CH_PAIR_V; M.n = slot_samples;
+        M.out0 = A.pcm_out + (valid ? A.out_frame[pkt] : 0u) * (nch * DepthTraits<DEPTH>::kBytes);
         M.pkt = packet; M.pkt_size = size; M.shift_pos = 0; M.shift = 0; M.mix_bits = 0; M.mix_res = 0;
         BitPeek bp;
         bp.start(packet, size);
@@ -701,15 +707,15 @@ __global__ void __launch_bounds__(64) dec_fused_kernel(DecArgs A)
                 int32_t *col = s_res[b] + lane;
                 const uint32_t j0 = t * kTileRows;
 #pragma unroll 1
-                for (uint32_t r = 0; r < kTileRows; r++) {
-                    if (j0 + r < n) col[r * kTilePitch] = ag.next(br, cap_bits);
-                    if ((r & (kTopUpEvery - 1u)) == kTopUpEvery - 1u) br.top_up();
+                for (uint32_t r0 = 0; r0 < kTileRows; r0 += kTopUpEvery) {
+#pragma unroll
+                    for (uint32_t i = 0; i < kTopUpEvery; i++) col[(r0 + i) * kTilePitch] = ag.at(br, j0 + r0 + i);
+                    br.top_up();
                 }
                 __syncwarp();
                 named_arrive<BAR_FULL0>(b != 0);
             }
-            // dyn_decomp's exit check "cur <= end" (codec/ag_dec.c:359)
-            if (!ag.status && (br.pos >> 3) > (cap_bits >> 3)) ag.status = -50;
+            ag.finish(br, cap_bits);
             if (n && !status) status = ag.status;
             __syncthreads();                                    // (2) the finish warp is done with this channel's tiles
         }
@@ -760,7 +766,7 @@ __global__ void __launch_bounds__(64) dec_fused_kernel(DecArgs A)
             } else {
                 cp_async_wait<0>();
                 __syncwarp();
-                flush_tile<DEPTH>(A, s_meta, nch == 2 ? s_xu : buf, buf, j0, 0, lane, 0, 1, out_pair32, nch);
+                flush_tile<DEPTH>(A, s_meta, nch == 2 ? s_xu : buf, buf, j0, lane, 0, 1, out_pair32, nch);
                 __syncwarp();
             }
             __syncwarp();

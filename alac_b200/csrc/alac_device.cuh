@@ -448,24 +448,26 @@ struct BitReader {
 // (codec/ag_dec.c:220-270 dyn_get_32bit, prefix < 9) is straight-line code; the escape code and the zero-run
 // code (codec/ag_dec.c:171-217 dyn_get) are the only branches.
 struct AgDec {
-    uint32_t mb, zmode, pending_zeros, c, count;
+    uint32_t mb, zmode, count;
+    uint32_t next_real;     // index of the next sample that has a code of its own (samples before it are a zero run)
     uint32_t pb, kb, wb, max_size;
     uint32_t start_rel;     // first bit's byte-floor, for the reference's "bitPos < maxPos" test
+    uint32_t last_start;    // bit position at which the latest code started
     int32_t status;
     __device__ __forceinline__ void start(const BitReader &br, uint32_t n, uint32_t mb0, uint32_t pb_, uint32_t kb_, uint32_t max_size_)
     {
-        mb = mb0; zmode = 0; pending_zeros = 0; c = 0; count = n;
+        mb = mb0; zmode = 0; next_real = 0; count = n;
         pb = pb_; kb = kb_; wb = (1u << kb_) - 1u; max_size = min(max_size_, 32u);
         start_rel = br.pos & ~7u;
+        last_start = start_rel;
         status = 0;
     }
-    // cap_bits = packet bytes * 8
-    __device__ __forceinline__ int32_t next(BitReader &br, uint32_t cap_bits)
+    // residual of sample j; call with j = 0, 1, 2, ... (every lane of a warp at the same j: zero runs are
+    // waited out, not skipped, so the ring top-up cadence stays warp-uniform).  j >= count yields 0.
+    __device__ __forceinline__ int32_t at(BitReader &br, uint32_t j)
     {
-        if (pending_zeros) { pending_zeros--; c++; return 0; }
-        // ag_dec.c:302 "bitPos < maxPos".  An error latches; decoding goes on over zero-filled words (a failed
-        // packet's samples are unspecified) so the hot loop carries no early-out.
-        if (!((br.pos - start_rel) < cap_bits)) status = -50;
+        if ((j - next_real) >= (count - next_real)) return 0;       // inside a zero run, or past the end
+        last_start = br.pos;
         const uint32_t k = min(bfind_u32((mb >> kQbShift) + 3u), kb);
         const uint32_t m = (1u << k) - 1u;
         const uint32_t window = br.peek32();
@@ -485,13 +487,12 @@ struct AgDec {
         }
         br.refill();
         const uint32_t nd = n + zmode;
-        const int32_t mult = (-(int32_t)(nd & 1u)) | 1;
-        const int32_t del = (int32_t)(((nd + 1u) >> 1) * (uint32_t)mult);              // ag_dec.c:313-319
-        c++;
+        const int32_t del = (int32_t)(nd >> 1) ^ -(int32_t)(nd & 1u);                    // ag_dec.c:313-319 (zig-zag)
+        next_real = j + 1u;
         mb = pb * nd + mb - ((pb * mb) >> kQbShift);
         if (n > kMeanClamp) mb = kMeanClamp;
         zmode = 0;
-        if (((mb << 2) < kQb) && (c < count)) {                                          // ag_dec.c:334
+        if (((mb << 2) < kQb) && (j + 1u < count)) {                                     // ag_dec.c:334
             zmode = 1;
             const uint32_t kz = (uint32_t)__clz((int)mb) - 24u + ((mb + 16u) >> 6);
             const uint32_t mz = ((1u << kz) - 1u) & wb;
@@ -509,12 +510,22 @@ struct AgDec {
                 br.consume(nb);
             }
             br.refill();
-            if (!(c + run <= count)) { status = -50; }                                   // ag_dec.c:341
-            else pending_zeros = run;
+            if (!(j + 1u + run <= count)) { status = -50; }                              // ag_dec.c:341
+            else next_real = j + 1u + run;
             if (run >= 65535u) zmode = 0;
             mb = 0;
         }
         return del;
+    }
+    // ag_dec.c:302 "bitPos < maxPos" is tested before every code; positions only grow, so testing the start of the
+    // LAST code is the same test.  (Decoding runs on over zero-filled words after the end of a packet: a failed
+    // packet's samples are unspecified and the hot loop carries no early-out.)  Then dyn_decomp's exit check
+    // "cur <= end" (ag_dec.c:359).  cap_bits = packet bytes * 8.
+    __device__ __forceinline__ int32_t finish(const BitReader &br, uint32_t cap_bits)
+    {
+        if (count && !((last_start - start_rel) < cap_bits)) status = -50;
+        if (!status && (br.pos >> 3) > (cap_bits >> 3)) status = -50;
+        return status;
     }
 };
 

@@ -676,7 +676,8 @@ __global__ void enc_size_kernel(ElemRec *recs, EncLayout lay, uint32_t depth, co
 }
 
 // ---- exclusive scan (single block, sequential tiles) -------------------------------------------------------
-// offsets[i] = sum_{j<i} sizes[j]; offsets[n] = total.  One 1024-thread block walks the array in tiles.
+// offsets[i] = sum_{j<i} sizes[j]; offsets[n] = total.  One 1024-thread block walks the array in tiles of 4096
+// (four consecutive elements per thread).
 __global__ void __launch_bounds__(1024) scan_u32_to_u64_kernel(const uint32_t *in, uint64_t *out, uint64_t n, uint32_t *max_out, int chain_base,
                                                                uint64_t *host_total = nullptr)
 {
@@ -688,11 +689,13 @@ __global__ void __launch_bounds__(1024) scan_u32_to_u64_kernel(const uint32_t *i
     if (threadIdx.x == 0) carry_s = chain_base ? out[0] : 0;
     __syncthreads();
     uint32_t my_max = 0;
-    for (uint64_t tile = 0; tile < n; tile += 1024) {
-        const uint64_t i = tile + threadIdx.x;
-        const uint32_t v = i < n ? in[i] : 0u;
-        my_max = max(my_max, v);
-        uint64_t x = v;
+    for (uint64_t tile = 0; tile < n; tile += 4096) {
+        const uint64_t i0 = tile + 4ull * threadIdx.x;
+        uint32_t v[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) { v[k] = i0 + k < n ? in[i0 + k] : 0u; my_max = max(my_max, v[k]); }
+        uint64_t x = (uint64_t)v[0] + v[1] + v[2] + v[3];
+        const uint64_t mine = x;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
             const uint64_t y = __shfl_up_sync(0xffffffffu, x, d);
@@ -712,7 +715,12 @@ __global__ void __launch_bounds__(1024) scan_u32_to_u64_kernel(const uint32_t *i
         __syncthreads();
         const uint64_t carry = carry_s;
         const uint64_t incl = x + (wid ? warp_sums[wid - 1] : 0) + carry;
-        if (i < n) out[i] = incl - v;
+        uint64_t run = incl - mine;         // exclusive prefix of this thread's first element
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            if (i0 + k < n) out[i0 + k] = run;
+            run += v[k];
+        }
         __syncthreads();
         if (threadIdx.x == 1023) carry_s = incl;
         __syncthreads();

@@ -62,6 +62,12 @@ struct alac_b200_engine {
     DevBuf d_packets, d_sizes, d_pkt_off, d_pkt_samples, d_out_frame, d_status, d_pcm, d_class, d_rank, d_perm, d_chan, d_meta, d_hdr, jobs, job_counts;
     uint32_t launches = 0;
     bool decode_configured = false;
+    // encode geometry tables of the previous call (see alac_b200_encode)
+    std::vector<uint64_t> h_pkt_frame;
+    std::vector<uint32_t> h_pkt_samples, h_seg_first, h_seg_count, h_seg_stream;
+    std::vector<alac_b200_stream> tab_streams;
+    uint32_t tab_F = 0, tab_K = 0;
+    bool tables_valid = false;
     // per-kernel timers: (start, stop) event pairs, grown on demand, reused across calls
     std::vector<cudaEvent_t> timers;
     size_t timers_used = 0;
@@ -274,7 +280,9 @@ const char *alac_b200_last_error(const alac_b200_engine *e) { return e ? e->err.
 int32_t alac_b200_engine_set_stream(alac_b200_engine *e, void *cuda_stream)
 {
     if (!e) return ALAC_B200_PARAM_ERROR;
-    e->stream = cuda_stream ? reinterpret_cast<cudaStream_t>(cuda_stream) : e->own_stream;
+    const cudaStream_t ns = cuda_stream ? reinterpret_cast<cudaStream_t>(cuda_stream) : e->own_stream;
+    if (ns != e->stream) e->tables_valid = false;      // cached tables were uploaded in the old stream's order
+    e->stream = ns;
     return ALAC_B200_OK;
 }
 
@@ -432,31 +440,43 @@ extern "C" int32_t alac_b200_encode(alac_b200_engine *e, const alac_b200_enc_con
     const uint32_t F = cfg->frame_size, K = cfg->frames_per_segment;
     const uint64_t bpf = (uint64_t)bytes_per_sample(cfg->bit_depth) * cfg->channels;
 
-    // ---- packet / segment tables (host) ----
-    std::vector<uint64_t> h_pkt_frame;
-    std::vector<uint32_t> h_pkt_samples, h_seg_first, h_seg_count, h_seg_stream;
-    for (uint64_t s = 0; s < n_streams; s++) {
-        const alac_b200_stream &st = streams[s];
-        if (st.first_sample_frame + st.num_sample_frames > num_sample_frames) return ALAC_B200_PARAM_ERROR;
-        const uint64_t packets = (st.num_sample_frames + F - 1) / F;
-        if (h_pkt_frame.size() + packets > 0x3fffffffull) return ALAC_B200_PARAM_ERROR;
-        const uint32_t first_pkt = (uint32_t)h_pkt_frame.size();
-        for (uint64_t p = 0; p < packets; p++) {
-            h_pkt_frame.push_back(st.first_sample_frame + p * F);
-            h_pkt_samples.push_back((uint32_t)std::min<uint64_t>(F, st.num_sample_frames - p * F));
+    // ---- packet / segment tables (host).  They depend only on the stream list, the frame size and K, so a call
+    //      with the same geometry as the previous one (the usual batch loop) reuses them, on the host and on the device ----
+    std::vector<uint64_t> &h_pkt_frame = e->h_pkt_frame;
+    std::vector<uint32_t> &h_pkt_samples = e->h_pkt_samples, &h_seg_first = e->h_seg_first, &h_seg_count = e->h_seg_count,
+                          &h_seg_stream = e->h_seg_stream;
+    const bool same_tables = e->tables_valid && e->tab_F == F && e->tab_K == K && e->tab_streams.size() == n_streams &&
+                             memcmp(e->tab_streams.data(), streams, n_streams * sizeof(alac_b200_stream)) == 0;
+    if (!same_tables) {
+        e->tables_valid = false;
+        h_pkt_frame.clear(); h_pkt_samples.clear(); h_seg_first.clear(); h_seg_count.clear(); h_seg_stream.clear();
+        for (uint64_t s = 0; s < n_streams; s++) {
+            const alac_b200_stream &st = streams[s];
+            const uint64_t packets = (st.num_sample_frames + F - 1) / F;
+            if (h_pkt_frame.size() + packets > 0x3fffffffull) return ALAC_B200_PARAM_ERROR;
+            const uint32_t first_pkt = (uint32_t)h_pkt_frame.size();
+            for (uint64_t p = 0; p < packets; p++) {
+                h_pkt_frame.push_back(st.first_sample_frame + p * F);
+                h_pkt_samples.push_back((uint32_t)std::min<uint64_t>(F, st.num_sample_frames - p * F));
+            }
+            const uint64_t per_seg = K ? K : std::max<uint64_t>(packets, 1);
+            const size_t seg0 = h_seg_first.size();
+            for (uint64_t p = 0; p < packets; p += per_seg) {
+                h_seg_first.push_back(first_pkt + (uint32_t)p);
+                h_seg_count.push_back((uint32_t)std::min<uint64_t>(per_seg, packets - p));
+                h_seg_stream.push_back((uint32_t)s);
+            }
+            if (h_seg_first.size() > seg0) {
+                h_seg_stream[seg0] |= 0x80000000u;
+                h_seg_stream.back() |= 0x40000000u;
+            }
         }
-        const uint64_t per_seg = K ? K : std::max<uint64_t>(packets, 1);
-        const size_t seg0 = h_seg_first.size();
-        for (uint64_t p = 0; p < packets; p += per_seg) {
-            h_seg_first.push_back(first_pkt + (uint32_t)p);
-            h_seg_count.push_back((uint32_t)std::min<uint64_t>(per_seg, packets - p));
-            h_seg_stream.push_back((uint32_t)s);
-        }
-        if (h_seg_first.size() > seg0) {
-            h_seg_stream[seg0] |= 0x80000000u;
-            h_seg_stream.back() |= 0x40000000u;
-        }
+        e->tab_streams.assign(streams, streams + n_streams);
+        e->tab_F = F;
+        e->tab_K = K;
     }
+    for (uint64_t s = 0; s < n_streams; s++)
+        if (streams[s].first_sample_frame + streams[s].num_sample_frames > num_sample_frames) return ALAC_B200_PARAM_ERROR;
     const uint32_t P = (uint32_t)h_pkt_frame.size(), S = (uint32_t)h_seg_first.size();
     if (P > sizes_cap) return ALAC_B200_PARAM_ERROR;
     if (packets_cap < alac_b200_encode_bound(cfg, num_sample_frames, n_streams)) return ALAC_B200_PARAM_ERROR;
@@ -540,11 +560,14 @@ extern "C" int32_t alac_b200_encode(alac_b200_engine *e, const alac_b200_enc_con
     cudaStream_t st = e->stream;
     CU_CHECK(e, cudaEventRecord(e->ev[0], st));
     // small tables first: they share the H2D copy engine with the PCM chunks and must not queue behind them
-    CU_CHECK(e, cudaMemcpyAsync(e->pkt_frame.p, h_pkt_frame.data(), (size_t)P * 8, cudaMemcpyHostToDevice, st));
-    CU_CHECK(e, cudaMemcpyAsync(e->pkt_samples.p, h_pkt_samples.data(), (size_t)P * 4, cudaMemcpyHostToDevice, st));
-    CU_CHECK(e, cudaMemcpyAsync(e->seg_first.p, h_seg_first.data(), (size_t)S * 4, cudaMemcpyHostToDevice, st));
-    CU_CHECK(e, cudaMemcpyAsync(e->seg_count.p, h_seg_count.data(), (size_t)S * 4, cudaMemcpyHostToDevice, st));
-    CU_CHECK(e, cudaMemcpyAsync(e->seg_stream.p, h_seg_stream.data(), (size_t)S * 4, cudaMemcpyHostToDevice, st));
+    if (!same_tables) {
+        CU_CHECK(e, cudaMemcpyAsync(e->pkt_frame.p, h_pkt_frame.data(), (size_t)P * 8, cudaMemcpyHostToDevice, st));
+        CU_CHECK(e, cudaMemcpyAsync(e->pkt_samples.p, h_pkt_samples.data(), (size_t)P * 4, cudaMemcpyHostToDevice, st));
+        CU_CHECK(e, cudaMemcpyAsync(e->seg_first.p, h_seg_first.data(), (size_t)S * 4, cudaMemcpyHostToDevice, st));
+        CU_CHECK(e, cudaMemcpyAsync(e->seg_count.p, h_seg_count.data(), (size_t)S * 4, cudaMemcpyHostToDevice, st));
+        CU_CHECK(e, cudaMemcpyAsync(e->seg_stream.p, h_seg_stream.data(), (size_t)S * 4, cudaMemcpyHostToDevice, st));
+        e->tables_valid = true;     // (a failed call below leaves them valid: they only describe the geometry)
+    }
     int16_t *d_state = nullptr;
     if (coef_state) {
         CU_CHECK(e, e->state.reserve((size_t)n_streams * ALAC_B200_STATE_INT16S * 2));

@@ -706,9 +706,10 @@ __global__ void __launch_bounds__(64) dec_fused_kernel(DecArgs A)
                 named_sync<BAR_EMPTY0>(b != 0);
                 int32_t *col = s_res[b] + lane;
                 const uint32_t j0 = t * kTileRows;
+                // (not unrolled further: at() is long and the kernel is sensitive to instruction-cache misses)
 #pragma unroll 1
                 for (uint32_t r0 = 0; r0 < kTileRows; r0 += kTopUpEvery) {
-#pragma unroll
+#pragma unroll 1
                     for (uint32_t i = 0; i < kTopUpEvery; i++) col[(r0 + i) * kTilePitch] = ag.at(br, j0 + r0 + i);
                     br.top_up();
                 }

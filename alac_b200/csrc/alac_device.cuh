@@ -35,6 +35,13 @@ __device__ __forceinline__ int32_t sext_bits(int32_t v, uint32_t chanshift)
 __device__ __forceinline__ int32_t sext16(int32_t v) { return (int32_t)(int16_t)v; }
 __device__ __forceinline__ int32_t sign3(int32_t v) { return min(max(v, -1), 1); }
 __device__ __forceinline__ uint32_t bswap32(uint32_t v) { return __byte_perm(v, 0, 0x0123); }
+__device__ __forceinline__ uint32_t bfind_u32(uint32_t v)     // index of the highest set bit = 31 - clz(v), v != 0
+{
+    uint32_t r;
+    asm("bfind.u32 %0, %1;" : "=r"(r) : "r"(v));
+    return r;
+}
+
 
 // ---- PCM sample access (packed little-endian) ------------------------------------------------
 // full-width, right-aligned, sign-extended sample; codec/matrix_enc.cu:72-99,120-159,186-282,330-391
@@ -194,13 +201,13 @@ __constant__ uint32_t c_div_magic[16] = {
     16843010u, 8405025u, 4198405u, 2098178u, 1048833u, 524353u, 262161u, 131077u
 };
 
-// codec/ag_enc.c:115-148 dyn_code for a zero-run length
-template <bool EMIT, class Sink>
-__device__ __forceinline__ void ag_flush_run(AgEnc &s, Sink &sink, uint32_t zmode_after)
+// codec/ag_enc.c:115-148 dyn_code for a zero-run length: (length, code word) from the running mean and the run.
+// Out of line on purpose: runs are rare, the routine holds an integer division, and ag_put is inlined into every
+// unrolled predictor loop -- keeping this body out of those loops keeps them inside the instruction cache.
+__device__ __forceinline__ uint2 ag_run_code_inline(uint32_t mb, uint32_t n)
 {
-    const uint32_t k = (uint32_t)__clz((int)s.mb) - 24u + ((s.mb + 16u) >> 6);   // ag_enc.c:352
+    const uint32_t k = (uint32_t)__clz((int)mb) - 24u + ((mb + 16u) >> 6);   // ag_enc.c:352
     const uint32_t mz = ((1u << k) - 1u) & ((1u << kKb0) - 1u);
-    const uint32_t n = s.nz;
     const uint32_t div = n / mz;
     uint32_t len, value;
     if (div < kMaxPrefix) {
@@ -213,8 +220,18 @@ __device__ __forceinline__ void ag_flush_run(AgEnc &s, Sink &sink, uint32_t zmod
         len = kMaxPrefix + kRunRawBits;
         value = (((1u << kMaxPrefix) - 1u) << kRunRawBits) + n;
     }
-    s.bits += len;
-    if (EMIT) sink.put(value, len);
+    return make_uint2(len, value);
+}
+
+__device__ __noinline__ uint2 ag_run_code(uint32_t mb, uint32_t n) { return ag_run_code_inline(mb, n); }
+
+template <bool EMIT, class Sink>
+__device__ __forceinline__ void ag_flush_run(AgEnc &s, Sink &sink, uint32_t zmode_after)
+{
+    // the emitting loops (one per kernel) keep it inline; the many costing loops of the search kernel call it
+    const uint2 code = EMIT ? ag_run_code_inline(s.mb, s.nz) : ag_run_code(s.mb, s.nz);
+    s.bits += code.x;
+    if (EMIT) sink.put(code.y, code.x);
     s.mb = 0;
     s.zmode = zmode_after;
     s.in_run = 0;
@@ -236,8 +253,7 @@ __device__ __forceinline__ void ag_put(AgEnc &s, int32_t del, uint32_t bit_size,
         ag_flush_run<EMIT>(s, sink, 1u);
     }
     const uint32_t mb = s.mb;
-    uint32_t k = 31u - (uint32_t)__clz((int)((mb >> kQbShift) + 3u));
-    k = min(k, kKb0);
+    const uint32_t k = min(bfind_u32((mb >> kQbShift) + 3u), kKb0);
     const uint32_t m = (1u << k) - 1u;
     const uint32_t n = (uint32_t)((del << 1) ^ (del >> 31)) - s.zmode;           // ag_enc.c:287
 
@@ -343,12 +359,6 @@ __device__ __forceinline__ void lds_u32_if(uint32_t &v, uint32_t smem_addr, bool
 {
     asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %2, 0;\n\t@q ld.shared.u32 %0, [%1];\n\t}"
                  : "+r"(v) : "r"(smem_addr), "r"((uint32_t)take) : "memory");
-}
-__device__ __forceinline__ uint32_t bfind_u32(uint32_t v)     // index of the highest set bit = 31 - clz(v), v != 0
-{
-    uint32_t r;
-    asm("bfind.u32 %0, %1;" : "=r"(r) : "r"(v));
-    return r;
 }
 
 struct BitReader {

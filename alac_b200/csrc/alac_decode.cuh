@@ -68,6 +68,7 @@ __global__ void dec_header_kernel(DecArgs A)
         if (!((br.pos >> 3) < size)) break;
         const uint32_t tag = br.get(3);
         if (tag == ID_SCE || tag == ID_LFE || tag == ID_CPE) {
+            if (tag == ID_CPE && A.num_channels < 2) break;    // a pair that does not fit ends the packet unread (:759-760)
             br.pos += 4;
             const bool hdr_ok = br.get(12) == 0;
             const uint32_t hb = br.get(4);
@@ -220,7 +221,7 @@ __device__ __forceinline__ void flush_tile(const DecArgs &A, const FinMeta *meta
             const int32_t v = bv[lane * kTilePitch + pr];
             int32_t r;
             if (mix_res != 0) {                         // :193-223
-                l = l + v - ((mix_res * v) >> mix_bits);
+                l = l + v - ((mix_res * v) >> (mix_bits & 31u));    // an out-of-range mixBits shifts like the reference's int32 shift on x86
                 r = l - v;
             } else {
                 r = v;

@@ -292,6 +292,7 @@ struct BitPeek {
     const uint32_t *base;   // 4-byte aligned address at or before the packet
     uint32_t bias;          // bit offset of the packet's first bit inside base[0]
     uint32_t last_word;     // index of the last word holding packet bytes
+    uint32_t tail_mask;     // the packet's bits inside that word (MSB-first view)
     uint32_t pos;
     bool valid;
     __device__ __forceinline__ void start(const uint8_t *packet, uint32_t nbytes)
@@ -301,9 +302,17 @@ struct BitPeek {
         bias = (uint32_t)(addr & 3u) * 8u;
         valid = nbytes != 0;
         last_word = valid ? (bias + nbytes * 8u - 1u) >> 5 : 0u;
+        const uint32_t tail_bits = valid ? ((bias + nbytes * 8u - 1u) & 31u) + 1u : 32u;     // valid bits of the last word, from its MSB
+        tail_mask = tail_bits == 32u ? 0xffffffffu : ~(0xffffffffu >> tail_bits);
         pos = 0;
     }
-    __device__ __forceinline__ uint32_t word(uint32_t i) const { return (valid && i <= last_word) ? bswap32(__ldg(base + i)) : 0u; }
+    // bytes past the packet's last byte read as zero, also inside its last word
+    __device__ __forceinline__ uint32_t word(uint32_t i) const
+    {
+        if (!(valid && i <= last_word)) return 0u;
+        const uint32_t w = bswap32(__ldg(base + i));
+        return i == last_word ? (w & tail_mask) : w;
+    }
     __device__ __forceinline__ uint32_t peek32_at(uint32_t p) const
     {
         const uint32_t abs_bit = bias + p;
@@ -365,6 +374,7 @@ struct BitReader {
     const uint32_t *base;   // 4-byte aligned address at or before the packet
     uint32_t bias;          // bit offset of the packet's first bit inside base[0]
     int32_t last_word;      // index of the last word holding packet bytes; -1 for an empty packet
+    uint32_t tail_bytes;    // packet bytes inside that word
     uint32_t ring;          // shared-memory address of this lane's ring column
     uint32_t rd;            // index of the word held in nxt (the next one to enter the window)
     uint32_t wr;            // next word index to request
@@ -379,7 +389,8 @@ struct BitReader {
     __device__ __forceinline__ void issue(uint32_t i)
     {
         const bool in = (int32_t)i <= last_word;
-        cp_async_word(slot_addr(i), base + (in ? i : 0u), in ? 4u : 0u);
+        // the last word is copied only up to the packet's last byte: the copy zero-fills the rest
+        cp_async_word(slot_addr(i), base + (in ? i : 0u), in ? ((int32_t)i == last_word ? tail_bytes : 4u) : 0u);
     }
     // request everything up to kRingSlots words past the read position (slots of words < rd are free)
     __device__ __forceinline__ uint32_t request_ahead()
@@ -447,6 +458,7 @@ struct BitReader {
         base = reinterpret_cast<const uint32_t *>(addr & ~(uintptr_t)3);
         bias = (uint32_t)(addr & 3u) * 8u;
         last_word = nbytes ? (int32_t)((bias + nbytes * 8u - 1u) >> 5) : -1;
+        tail_bytes = (((bias >> 3) + nbytes - 1u) & 3u) + 1u;
         if (!nbytes) base = ring_column;        // never dereferenced (every request has size 0), but keep it sane
         ring = (uint32_t)__cvta_generic_to_shared(ring_column);
         pos = 0;

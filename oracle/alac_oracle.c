@@ -961,7 +961,7 @@ struct orc_decoder {
     int32_t *mix_u, *mix_v, *pred;
     uint16_t *shift_buf;
     uint8_t *padded;
-    uint32_t padded_cap;
+    size_t padded_cap, padded_dirty;
 };
 
 static inline uint32_t get_be32(const uint8_t *p) { return ((uint32_t)p[0] << 24) | ((uint32_t)p[1] << 16) | ((uint32_t)p[2] << 8) | p[3]; }
@@ -1090,15 +1090,23 @@ int32_t orc_decode_packet(orc_decoder *d, const uint8_t *packet, uint32_t packet
 
     if (nch == 0) return ORC_PARAM_ERROR;
     if (!(depth == 16 || depth == 20 || depth == 24 || depth == 32)) return ORC_PARAM_ERROR;
-    /* padded private copy so 32/64-bit peeks never leave the allocation */
-    if (d->padded_cap < packet_bytes + 16) {
-        free(d->padded);
-        d->padded_cap = packet_bytes + 4096;
-        d->padded = (uint8_t *)malloc(d->padded_cap);
-        if (!d->padded) { d->padded_cap = 0; return ORC_MEM_ERROR; }
+    /* Private copy in which every byte past the packet reads as zero -- the defined behaviour of this oracle (and of
+       the CUDA bit readers) where the reference reads on into whatever follows its input buffer: escape samples and
+       header fields of a truncated packet.  The tail is sized for the longest over-read (a whole raw frame); only the
+       bytes an earlier, longer packet left behind need clearing. */
+    {
+        const size_t need = (size_t)packet_bytes + (size_t)d->cfg.frame_length * nch * 4u + 64u;
+        if (d->padded_cap < need) {
+            free(d->padded);
+            d->padded_cap = need + 4096;
+            d->padded = (uint8_t *)calloc(d->padded_cap, 1);
+            if (!d->padded) { d->padded_cap = 0; return ORC_MEM_ERROR; }
+            d->padded_dirty = 0;
+        }
+        memcpy(d->padded, packet, packet_bytes);
+        if (d->padded_dirty > packet_bytes) memset(d->padded + packet_bytes, 0, d->padded_dirty - packet_bytes);
+        d->padded_dirty = packet_bytes;
     }
-    memcpy(d->padded, packet, packet_bytes);
-    memset(d->padded + packet_bytes, 0, 16);
     orc_bits_init(&b, d->padded, packet_bytes);
     *out_num_samples = n;
 

@@ -416,3 +416,57 @@ def test_odd_frame_length_and_mixed_kinds_in_one_group(engine, oracle):
     pcm = np.concatenate(parts)
     got, _ = _check_encode(engine, oracle, pcm, ch, depth, K=1, frame_size=F)
     _check_decode(engine, oracle, got, pcm)
+
+
+@pytest.mark.parametrize("seed", [11, 12, 13, 14, 15, 16])
+def test_decode_fuzzed_packets_do_not_hang_or_leak(engine, oracle, seed):
+    """Bit-flipped, truncated, header-damaged and random packets next to good ones: the call returns, the GPU and the
+    oracle decoder agree on which packets are accepted (status 0 / kALAC_ParamErr), and every accepted packet decodes to
+    the same samples.  Bytes past the end of a short packet read as zero on both sides."""
+    import alac_b200
+    rng = np.random.default_rng(seed)
+    for ch, depth, golden in [(2, 16, "music_stereo16_k1"), (2, 24, "music_stereo24_k0"), (1, 20, "music_mono20_k2"),
+                              (2, 32, "music_stereo32_k1"), (2, 16, "silence_stereo16_runs"), (2, 16, "noise_stereo16_escape")]:
+        g = np.load([p for p in _GOLDEN if golden in p][0])
+        sizes = g["sizes"].astype(np.int64)
+        offs = np.concatenate([[0], np.cumsum(sizes)])
+        good = [g["packets"][offs[i]:offs[i + 1]].copy() for i in range(len(sizes))]
+        pk, is_good = [], []
+        for rep in range(20):
+            for i, p in enumerate(good):
+                mode = int(rng.integers(0, 6))
+                q = p.copy()
+                if mode == 1:                                   # a few bit flips anywhere
+                    for _ in range(int(rng.integers(1, 6))):
+                        q[int(rng.integers(0, len(q)))] ^= 1 << int(rng.integers(0, 8))
+                elif mode == 2:                                 # truncation
+                    q = q[: int(rng.integers(1, len(q)))]
+                elif mode == 3:                                 # header byte damage
+                    q[int(rng.integers(0, min(8, len(q))))] = int(rng.integers(0, 256))
+                elif mode == 4:                                 # noise
+                    q = rng.integers(0, 256, int(rng.integers(1, 600)), dtype=np.uint8).astype(np.uint8)
+                pk.append(q)
+                is_good.append(mode in (0, 5))
+        blob, sz = np.concatenate(pk), np.array([len(q) for q in pk], np.uint32)
+        cookie = bytes(g["cookie"])
+        dec = engine.decode(cookie, blob, sz, raise_on_error=False)
+        ref = oracle.Decoder(cookie)
+        F = 4096
+        bpf = ch * (2 if depth == 16 else 4 if depth == 32 else 3)
+        pos = 0
+        st = np.asarray(dec.packet_status)
+        ns = np.asarray(dec.packet_samples)
+        checked = 0
+        for i, q in enumerate(pk):
+            n = int(ns[i])
+            # (bytes past the end of a short packet read as zero in the oracle and in the CUDA bit readers alike)
+            want, rst = ref.decode_stream(q, np.array([len(q)], np.uint32))
+            if is_good[i]:
+                assert st[i] == 0 and rst[0] == 0
+            assert (st[i] == 0) == (rst[0] == 0), f"packet {i}: GPU status {st[i]}, oracle status {rst[0]}"
+            if rst[0] == 0 and st[i] == 0:
+                got = dec.pcm[pos * bpf:(pos + n) * bpf]
+                assert len(want) == len(got) and np.array_equal(got, want), f"packet {i} differs"
+                checked += 1
+            pos += n
+        assert checked >= sum(is_good)

@@ -2,8 +2,11 @@
 
 Encode shards by whole segments of frames_per_segment packets (DESIGN.md D1), decode by packets;
 both are byte-identical to the unsharded result by construction.  The only cross-rank step is
-putting the per-rank packet blocks back in order: every rank contributes (sizes, bytes) and the
-gather concatenates them in rank order -- a size all-gather plus a padded byte all-gather.
+putting the per-rank packet blocks back in order, and only when one consumer wants one buffer:
+  concat_packets_to(dst, ...)  the packet-offset scan over the ranks' byte totals plus one point-to-point copy
+                               per rank straight into its slice of the destination buffer (NCCL send/recv =
+                               NVLink P2P copies on a B200 box); no collective on the data path;
+  gather_packets(...)          every rank gets everything (a size all-gather plus a padded byte all-gather).
 Works with any torch.distributed backend (NCCL on GPUs, gloo in the CPU tests).
 """
 from __future__ import annotations
@@ -66,4 +69,49 @@ def gather_packets(packets, sizes, group=None):
     dist.all_gather(all_c, pc, group=group)
     out_p = torch.cat([b[:n] for b, n in zip(all_b, nbytes)])
     out_s = torch.cat([c[:n] for c, n in zip(all_c, ncount)])
+    return out_p, out_s
+
+
+def concat_packets_to(dst: int, packets, sizes, group=None):
+    """Rank-ordered concatenation of every rank's packet block on rank `dst`, with point-to-point copies only.
+
+    Every rank calls this with its packet bytes (uint8 tensor) and sizes (int32 tensor).  Rank `dst` learns the
+    other ranks' totals (two int64 each), runs the exclusive scan that places each block, and receives each
+    block directly into its slice of the output -- under NCCL these are peer-to-peer copies over NVLink, one per
+    rank, with no staging and no padding.  Returns (packets, sizes) on `dst`, None elsewhere."""
+    import torch
+    import torch.distributed as dist
+
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    dev = packets.device
+    sizes = sizes.to(torch.int32)
+    meta = torch.tensor([packets.numel(), sizes.numel()], dtype=torch.int64, device=dev)
+    if rank != dst:
+        dist.send(meta, dst, group=group)
+        if packets.numel():
+            dist.send(packets.contiguous(), dst, group=group)
+        if sizes.numel():
+            dist.send(sizes.contiguous(), dst, group=group)
+        return None
+    metas = []
+    for r in range(world):
+        m = meta.clone()
+        if r != dst:
+            dist.recv(m, r, group=group)
+        metas.append((int(m[0]), int(m[1])))
+    # exclusive scan of the byte / packet totals = where each rank's block starts
+    out_p = torch.empty(sum(m[0] for m in metas), dtype=torch.uint8, device=dev)
+    out_s = torch.empty(sum(m[1] for m in metas), dtype=torch.int32, device=dev)
+    ob = oc = 0
+    for r, (nb, nc) in enumerate(metas):
+        if r == dst:
+            out_p[ob:ob + nb] = packets
+            out_s[oc:oc + nc] = sizes
+        else:
+            if nb:
+                dist.recv(out_p[ob:ob + nb], r, group=group)
+            if nc:
+                dist.recv(out_s[oc:oc + nc], r, group=group)
+        ob += nb
+        oc += nc
     return out_p, out_s

@@ -37,21 +37,27 @@ def _worker(rank, world, port, pcm, ch, depth, K, q):
     a, n = shard.plan_frame_shards(pcm.nbytes // bpf, 4096, world, K)[rank]
     es = O.Encoder(ch, depth).encode_stream(pcm[a * bpf:(a + n) * bpf], K)
     pk, sz = shard.gather_packets(torch.from_numpy(es.packets), torch.from_numpy(es.sizes.astype(np.int32)))
+    # the point-to-point form: only the destination rank (the last one here) receives, block by block
+    res = shard.concat_packets_to(world - 1, torch.from_numpy(es.packets), torch.from_numpy(es.sizes.astype(np.int32)))
+    assert (res is not None) == (rank == world - 1)
+    if res is not None:
+        assert torch.equal(res[0], pk) and torch.equal(res[1], sz)
     if rank == 0:
         q.put((pk.numpy(), sz.numpy()))
     dist.barrier()
     dist.destroy_process_group()
 
 
+@pytest.mark.parametrize("world", [2, 3])
 @pytest.mark.parametrize("K", [1, 3])
-def test_sharded_encode_is_byte_identical(oracle, K):
+def test_sharded_encode_is_byte_identical(oracle, K, world):
     ch, depth = 2, 16
     pcm = synth.make("music", 4096 * 7 + 321, ch, depth, seed=5)
     whole = oracle.Encoder(ch, depth).encode_stream(pcm, K)
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    port = 29500 + (os.getpid() % 2000) + K
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, pcm, ch, depth, K, q)) for r in range(2)]
+    port = 29500 + (os.getpid() % 2000) + K + 10 * world
+    procs = [ctx.Process(target=_worker, args=(r, world, port, pcm, ch, depth, K, q)) for r in range(world)]
     for p in procs:
         p.start()
     pk, sz = q.get(timeout=120)

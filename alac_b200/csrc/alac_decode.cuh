@@ -814,4 +814,27 @@ __global__ void ber_count_kernel(const uint32_t *sizes, const uint64_t *offsets,
     if (sizes[k] == 0 || offsets[k] + sizes[k] > data_bytes) atomicMin(first_bad, (unsigned long long)k);
 }
 
+// the other direction: packet sizes -> BER bytes (convert-utility/CAFFileALAC.cpp:189-222 WriteBERInteger).
+// ber_len_kernel gives each entry's byte count (1..5), an exclusive scan places it, ber_emit_kernel writes it.
+__global__ void ber_len_kernel(const uint32_t *sizes, uint64_t n, uint32_t *lens)
+{
+    const uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    const uint32_t v = sizes[k];
+    lens[k] = v < (1u << 7) ? 1u : v < (1u << 14) ? 2u : v < (1u << 21) ? 3u : v < (1u << 28) ? 4u : 5u;
+}
+
+__global__ void ber_emit_kernel(const uint32_t *sizes, const uint64_t *offsets, uint64_t n, uint8_t *table)
+{
+    const uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    const uint32_t v = sizes[k];
+    const uint32_t len = (uint32_t)(offsets[k + 1] - offsets[k]);
+    uint8_t *p = table + offsets[k];
+    for (uint32_t i = 0; i < len; i++) {
+        const uint32_t sh = 7u * (len - 1u - i);
+        p[i] = (uint8_t)(((v >> sh) & 0x7fu) | (i + 1u < len ? 0x80u : 0u));
+    }
+}
+
 }  // namespace alacb

@@ -1039,3 +1039,45 @@ extern "C" int32_t alac_b200_ber_table_sizes(alac_b200_engine *e, const void *ta
     *out_num_packets = n;
     return ALAC_B200_OK;
 }
+
+// packet sizes -> BER table (the 'pakt' payload after its 24-byte header), on the device
+extern "C" int32_t alac_b200_ber_table_build(alac_b200_engine *e, const uint32_t *sizes, uint64_t num_packets, int32_t sizes_mem,
+                                             void *table_out, uint64_t table_cap, int32_t out_mem, uint64_t *out_table_bytes)
+{
+    if (!e || !out_table_bytes || (!sizes && num_packets) || (!table_out && num_packets)) return ALAC_B200_PARAM_ERROR;
+    e->err.clear();
+    *out_table_bytes = 0;
+    if (num_packets == 0) return ALAC_B200_OK;
+    if (num_packets > 0x3fffffffull) return ALAC_B200_PARAM_ERROR;
+    CU_CHECK(e, cudaSetDevice(e->device));
+    cudaStream_t st = e->stream;
+    const uint32_t *d_sizes;
+    if (sizes_mem == ALAC_B200_MEM_DEVICE) {
+        d_sizes = sizes;
+    } else {
+        CU_CHECK(e, e->d_sizes.reserve((size_t)num_packets * 4));
+        CU_CHECK(e, cudaMemcpyAsync(e->d_sizes.p, sizes, (size_t)num_packets * 4, cudaMemcpyHostToDevice, st));
+        d_sizes = e->d_sizes.as<uint32_t>();
+    }
+    CU_CHECK(e, e->d_class.reserve((size_t)num_packets * 4));                 // entry lengths
+    CU_CHECK(e, e->d_pkt_off.reserve(((size_t)num_packets + 1) * 8));         // entry offsets
+    const uint32_t blocks = (uint32_t)((num_packets + 255) / 256);
+    ber_len_kernel<<<blocks, 256, 0, st>>>(d_sizes, num_packets, e->d_class.as<uint32_t>());
+    scan_u32_to_u64_kernel<<<1, 1024, 0, st>>>(e->d_class.as<uint32_t>(), e->d_pkt_off.as<uint64_t>(), num_packets, nullptr, 0, &e->h_totals[0]);
+    CU_CHECK(e, cudaStreamSynchronize(st));
+    const uint64_t total = e->h_totals[0];
+    if (total > table_cap) { e->err = "table capacity exceeded"; return ALAC_B200_PARAM_ERROR; }
+    uint8_t *d_table;
+    if (out_mem == ALAC_B200_MEM_DEVICE) {
+        d_table = static_cast<uint8_t *>(table_out);
+    } else {
+        CU_CHECK(e, e->d_packets.reserve((size_t)total + 64));
+        d_table = e->d_packets.as<uint8_t>();
+    }
+    ber_emit_kernel<<<blocks, 256, 0, st>>>(d_sizes, e->d_pkt_off.as<uint64_t>(), num_packets, d_table);
+    CU_CHECK(e, cudaGetLastError());
+    if (out_mem != ALAC_B200_MEM_DEVICE) CU_CHECK(e, cudaMemcpyAsync(table_out, d_table, (size_t)total, cudaMemcpyDeviceToHost, st));
+    CU_CHECK(e, cudaStreamSynchronize(st));
+    *out_table_bytes = total;
+    return ALAC_B200_OK;
+}

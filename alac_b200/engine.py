@@ -94,6 +94,8 @@ def load_library():
     lib.alac_b200_decode.restype = i32
     lib.alac_b200_ber_table_sizes.argtypes = [vp, vp, u64, i32, u64, vp, u64, i32, C.POINTER(u64)]
     lib.alac_b200_ber_table_sizes.restype = i32
+    lib.alac_b200_ber_table_build.argtypes = [vp, vp, u64, i32, vp, u64, i32, C.POINTER(u64)]
+    lib.alac_b200_ber_table_build.restype = i32
     _lib = lib
     return lib
 
@@ -286,6 +288,23 @@ class Engine:
         if st:
             raise AlacError(st, self._err())
         return out[:n.value]
+
+    def ber_table_build(self, sizes):
+        """Packet sizes (uint32 numpy array or int32/uint32 torch CUDA tensor) -> BER bytes of a CAF 'pakt' chunk, built on
+        the GPU.  Output lives where the sizes live."""
+        sptr, sbytes, mem = _buf(sizes)
+        self._follow_torch_stream(sizes)
+        n = sbytes // 4
+        if mem == MEM_DEVICE:
+            import torch
+            out = torch.empty(max(5 * n, 1), dtype=torch.uint8, device=sizes.device)
+        else:
+            out = np.empty(max(5 * n, 1), np.uint8)
+        nb = C.c_uint64(0)
+        st = self.lib.alac_b200_ber_table_build(self.h, C.c_void_p(sptr), n, mem, C.c_void_p(_buf(out)[0]), max(5 * n, 1), mem, C.byref(nb))
+        if st:
+            raise AlacError(st, self._err())
+        return out[:nb.value]
 
     # ------------------------------------------------------------------ decode
     def decode(self, cookie: bytes, packets, sizes, out=None, raise_on_error: bool = True) -> DecodeResult:

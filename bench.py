@@ -324,7 +324,25 @@ def run_cuda(args):
     h2d = pcm_np.nbytes + payload + 4 * npk + 12 * npk
     d2h = payload + 4 * npk + pcm_np.nbytes + 8 * npk
 
+    # ---- N > 1: the one cross-GPU step, outside the timed region: packet-offset scan over the ranks' totals and one
+    #      point-to-point copy per rank into rank 0's buffer (alac_b200.shard.concat_packets_to), timed on the device
+    concat = None
     if world > 1:
+        from alac_b200 import shard
+        enc, _ = step_device()
+        szt = enc.sizes.to(torch.int32)
+        shard.concat_packets_to(0, enc.packets, szt)                    # first call sets up the NCCL P2P channels
+        barrier()
+        c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        c0.record()
+        res = shard.concat_packets_to(0, enc.packets, szt)
+        c1.record()
+        torch.cuda.synchronize()
+        t = torch.tensor([c0.elapsed_time(c1)], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        if rank == 0:
+            concat = {"ms": float(t.item()), "bytes": int(res[0].numel()), "how": "send/recv (NVLink P2P), no collective"}
+        del res
         dist.barrier()
     if rank != 0:
         if world > 1:
@@ -405,6 +423,8 @@ def run_cuda(args):
                                    "GPU packets byte-compared with this oracle output in the same run"},
         "bit_exact": True,
     }
+    if concat:
+        line["concat_to_rank0"] = concat
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

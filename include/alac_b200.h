@@ -149,6 +149,12 @@ int32_t alac_b200_ber_table_sizes(alac_b200_engine *engine, const void *table, u
                                   uint64_t data_bytes, uint32_t *sizes_out, uint64_t sizes_cap, int32_t out_mem,
                                   uint64_t *out_num_packets);
 
+/* The other direction (convert-utility/CAFFileALAC.cpp:189-222): packet_sizes[] -> the BER bytes of a 'pakt' chunk
+ * (without its 24-byte header), built on the device (entry lengths, scan, emit).  With device buffers the table of a
+ * rank's packet block can be sent to its place in the file image with the block itself. */
+int32_t alac_b200_ber_table_build(alac_b200_engine *engine, const uint32_t *packet_sizes, uint64_t num_packets, int32_t sizes_mem,
+                                  void *table_out, uint64_t table_cap, int32_t out_mem, uint64_t *out_table_bytes);
+
 /* parse a cookie on the host (no GPU work): fills the 11 ALACSpecificConfig fields in order
    frameLength, compatibleVersion, bitDepth, pb, mb, kb, numChannels, maxRun, maxFrameBytes,
    avgBitRate, sampleRate (codec/ALACAudioTypes.h:162-176) */

@@ -293,6 +293,23 @@ def test_ber_table_on_device(engine):
     assert np.array_equal(engine.ber_table_sizes(table, cut), sizes[:1000])
 
 
+def test_ber_table_build_on_device(engine):
+    """sizes -> BER bytes on the device == the container writer's bytes; and back again."""
+    import torch
+    from tests import caf_ref
+    rng = np.random.default_rng(2)
+    sizes = np.concatenate([rng.integers(1, 128, 300), rng.integers(128, 16384, 3000), rng.integers(16384, 3000000, 500),
+                            [1, 127, 128, 16383, 16384, 2097151, 2097152, 268435455, 268435456, 4294967295]]).astype(np.uint32)
+    rng.shuffle(sizes)
+    want = np.frombuffer(b"".join(caf_ref.ber(int(s)) for s in sizes), np.uint8)
+    assert np.array_equal(engine.ber_table_build(sizes), want)
+    got_d = engine.ber_table_build(torch.from_numpy(sizes.view(np.int32)).cuda())
+    assert np.array_equal(got_d.cpu().numpy(), want)
+    small = sizes[sizes < 200000]
+    back = engine.ber_table_sizes(engine.ber_table_build(small), int(small.astype(np.int64).sum()))
+    assert np.array_equal(back, small)
+
+
 def test_decode_from_caf_table(engine):
     """Config-5 path: packets addressed through the BER table of a CAF file, all on the device."""
     import torch

@@ -487,3 +487,34 @@ def test_decode_fuzzed_packets_do_not_hang_or_leak(engine, oracle, seed):
                 checked += 1
             pos += n
         assert checked >= sum(is_good)
+
+
+@pytest.mark.parametrize("ch,depth", [(2, 16), (1, 16), (2, 24), (2, 32), (1, 20)])
+def test_encode_pathological_pcm(engine, oracle, ch, depth):
+    """PCM built to stress the integer corner cases: full-scale alternation (coefficient wrap, escape post-check),
+    impulses in silence (zero runs of every length, run overflow past 65535 does not occur in a 4096 frame but
+    long runs do), ramps and DC at the rails, random bytes; one signal per frame so that all of them share warps."""
+    from tests.synth import pack
+    rng = np.random.default_rng(depth * 10 + ch)
+    F, hi, lo = 4096, (1 << (depth - 1)) - 1, -(1 << (depth - 1))
+    t = np.arange(F)
+    frames = [
+        np.where(t % 2 == 0, hi, lo),                               # Nyquist at full scale
+        np.where((t // 3) % 2 == 0, hi, lo),
+        np.full(F, hi), np.full(F, lo), np.zeros(F, np.int64),
+        np.where(t % 997 == 0, hi, 0),                              # sparse impulses
+        np.where(t % 64 == 0, 1, 0), np.where(t % 5 == 0, -1, 0),
+        np.clip((t - 2048) * (hi // 2048), lo, hi),                 # ramp rail to rail
+        (t * 37) % 3 - 1,                                           # tiny dither around zero
+        rng.integers(lo, hi + 1, F),                                # white noise
+        np.cumsum(rng.integers(-3, 4, F)),                          # slow random walk
+        np.where(t < 2048, 0, rng.integers(lo, hi + 1, F)),         # silence then noise
+        np.where(t < 100, rng.integers(lo, hi + 1, F), 0),          # noise then silence
+    ]
+    sig = np.stack([np.concatenate(frames)] * ch, axis=1).astype(np.int64)
+    if ch == 2:
+        sig[:, 1] = np.roll(sig[:, 1], 7) // 2                      # a different but related second channel
+    pcm = pack(sig, depth)
+    for K in (1, 0):
+        got, _ = _check_encode(engine, oracle, pcm, ch, depth, K=K)
+        _check_decode(engine, oracle, got, pcm)

@@ -58,6 +58,27 @@ struct EncArgs {
 // while it works on sample j: fetch() only loads (no arithmetic on the result), mix() unpacks.
 // PACKED: a pure stereo stream (L, R adjacent, nothing in between) at natural alignment, so one
 // sample-frame is a single 32/64-bit load (16/32-bit) or three 16-bit loads (20/24-bit).
+// PCM ring of the wide path: per lane kPcmSlots slots of 16 bytes (four 16-bit stereo sample-frames), slot s of lane l
+// at [s][l], so a warp's 128-bit accesses are conflict-free.  cp.async fills it kPcmSlots - 1 blocks ahead of the
+// arithmetic; unlike a register queue (whose rotating moves wait for the newest load once per block) nothing waits
+// on a load before its data is due.
+constexpr uint32_t kPcmSlots = 4;
+template <uint32_t THREADS> struct PcmRing { uint4 slot[kPcmSlots][THREADS]; };
+template <uint32_t THREADS> __device__ __forceinline__ uint32_t pcm_ring_addr(PcmRing<THREADS> &r)
+{
+    return (uint32_t)__cvta_generic_to_shared(&r.slot[0][threadIdx.x]);
+}
+__device__ __forceinline__ uint4 lds_u128(uint32_t smem_addr)
+{
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(smem_addr) : "memory");
+    return v;
+}
+__device__ __forceinline__ void cp_async_u128(uint32_t smem_dst, const void *gsrc, uint32_t src_bytes)
+{
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_dst), "l"(gsrc), "r"(src_bytes) : "memory");
+}
+
 template <int DEPTH, bool STEREO, bool PACKED>
 struct MixSrc {
     static constexpr int kWords = !STEREO ? ((DEPTH == 16 || DEPTH == 32) ? 1 : 3)
@@ -70,6 +91,8 @@ struct MixSrc {
 
     const uint8_t *base;    // sample-frame 0 of the packet, first channel of the element
     uint32_t stride;        // bytes per sample-frame
+    uint32_t ring;          // kWide: shared-memory address of this lane's slot 0 of the PCM ring
+    uint32_t ring_stride;   // kWide: bytes from one slot to the next (16 x threads of the CTA)
     uint32_t valid;
     int32_t mix_res;
     bool is_v;
@@ -162,18 +185,28 @@ __device__ __forceinline__ void predict_pass(const Src &src, uint32_t num, int32
         // lets the history shift become register renaming
         const uint32_t nblk = (num - j) >> 2;
         if (nblk) {
+            // blocks of four frames stream through the lane's shared-memory ring, kPcmSlots - 1 blocks ahead;
+            // unrolling by four also lets the history shift become register renaming
             const uint4 *p = reinterpret_cast<const uint4 *>(src.base + (size_t)j * 4u);
-            uint4 cur = __ldg(p), nxt = __ldg(p + min(1u, nblk - 1u));
+            const uint32_t slot_bytes = src.ring_stride;
+#pragma unroll
+            for (uint32_t d = 0; d + 1 < kPcmSlots; d++) {
+                cp_async_u128(src.ring + d * slot_bytes, p + min(d, nblk - 1u), d < nblk ? 16u : 0u);
+                cp_async_commit();
+            }
             for (uint32_t b = 0; b < nblk; b++, j += 4) {
-                const uint4 far = __ldg(p + min(b + 2u, nblk - 1u));
+                const uint32_t ahead = b + kPcmSlots - 1u;
+                cp_async_u128(src.ring + (ahead & (kPcmSlots - 1u)) * slot_bytes, p + min(ahead, nblk - 1u), ahead < nblk ? 16u : 0u);
+                cp_async_commit();
+                cp_async_wait<kPcmSlots - 1>();         // block b is in
+                const uint4 cur = lds_u128(src.ring + (b & (kPcmSlots - 1u)) * slot_bytes);
                 typename Src::Raw r;
                 r.w[0] = cur.x; sink(j, predict_enc_step<TAPS, WRAP>(src.mix(r), hist, a, chanshift));
                 r.w[0] = cur.y; sink(j + 1, predict_enc_step<TAPS, WRAP>(src.mix(r), hist, a, chanshift));
                 r.w[0] = cur.z; sink(j + 2, predict_enc_step<TAPS, WRAP>(src.mix(r), hist, a, chanshift));
                 r.w[0] = cur.w; sink(j + 3, predict_enc_step<TAPS, WRAP>(src.mix(r), hist, a, chanshift));
-                cur = nxt;
-                nxt = far;
             }
+            cp_async_wait<0>();
         }
         for (; j < num; j++) sink(j, predict_enc_step<TAPS, WRAP>(src.get(j), hist, a, chanshift));
         return;
@@ -345,6 +378,7 @@ enc_search_kernel(EncArgs A, uint32_t elems_of_kind, uint32_t kind_elem0 /* bitm
     // the 4-tap pass, lanes [n4, n4 + n8) the 8-tap pass, and each warp stays uniform.
     __shared__ FinalJob s_job[kSearchThreads];
     __shared__ uint32_t s_cnt[kSearchThreads / 32][2];
+    __shared__ PcmRing<kSearchThreads> s_pcm;
     __shared__ uint32_t s_pn_max;
 
     constexpr uint32_t kLanesPerJob = STEREO ? 2 : 1;
@@ -405,6 +439,7 @@ enc_search_kernel(EncArgs A, uint32_t elems_of_kind, uint32_t kind_elem0 /* bitm
 
         MixSrc<DEPTH, STEREO, PACKED> src;
         src.base = base; src.stride = stride; src.valid = n;
+        src.ring = pcm_ring_addr(s_pcm); src.ring_stride = (uint32_t)sizeof(uint4) * kSearchThreads;
         src.set_mix(0, is_v);
 
         const SearchOut so = search_stages<DEPTH, STEREO, PACKED, WRAP>(src, A, valid, is_v, n, partial, pair_mask, chan_bits, chanshift, slab, c4, c8);
@@ -463,6 +498,7 @@ enc_search_kernel(EncArgs A, uint32_t elems_of_kind, uint32_t kind_elem0 /* bitm
             FinalJob &J = s_job[threadIdx.x];
             MixSrc<DEPTH, STEREO, PACKED> fs;
             fs.base = J.base; fs.stride = stride;
+            fs.ring = pcm_ring_addr(s_pcm); fs.ring_stride = (uint32_t)sizeof(uint4) * kSearchThreads;
             fs.set_mix((int32_t)(J.flags >> 1), (J.flags & 1u) != 0);
             fs.valid = J.n;
             EmitSink es;
@@ -552,8 +588,10 @@ enc_search_split_kernel(EncArgs A, uint32_t elems_of_kind, uint32_t kind_elem0, 
     uint32_t *slab = A.scratch + ((size_t)(pkt - A.pkt_base) * A.lay.chains_per_packet + chain) * A.cap_words;
     const uint32_t partial = (n != A.lay.frame_size);
 
+    __shared__ PcmRing<32> s_pcm;
     MixSrc<DEPTH, STEREO, PACKED> src;
     src.base = base; src.stride = stride; src.valid = n;
+    src.ring = pcm_ring_addr(s_pcm); src.ring_stride = (uint32_t)sizeof(uint4) * 32u;
     src.set_mix(0, is_v);
     const SearchOut so = search_stages<DEPTH, STEREO, PACKED, WRAP>(src, A, valid, is_v, n, partial, pair_mask, chan_bits, chanshift, slab, c4, c8);
     const uint32_t best_res = so.best_res, num_mine = so.num_mine;
@@ -616,8 +654,10 @@ enc_final_kernel(EncArgs A, JobLists Q, uint32_t ctas_per_list)
     constexpr uint32_t shift = DepthTraits<DEPTH>::kShift;
     const uint32_t chan_bits = DEPTH - shift + (STEREO ? 1u : 0u);
     const uint32_t chanshift = 32u - chan_bits;
+    __shared__ PcmRing<32> s_pcm;
     MixSrc<DEPTH, STEREO, PACKED> fs;
     fs.base = J.base; fs.stride = A.lay.channels * bps;
+    fs.ring = pcm_ring_addr(s_pcm); fs.ring_stride = (uint32_t)sizeof(uint4) * 32u;
     fs.set_mix((int32_t)(J.flags >> 1), (J.flags & 1u) != 0);
     fs.valid = J.n;
     EmitSink es;

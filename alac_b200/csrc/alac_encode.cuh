@@ -177,38 +177,44 @@ __device__ __forceinline__ void predict_pass(const Src &src, uint32_t num, int32
     }
     if (num <= TAPS + 1) return;
     if constexpr (Src::kWide) {
-        // head: single frames up to the next 16-byte boundary of the PCM
+        // single frames up to the next 16-byte boundary of the PCM, then blocks of four, then the remaining frames.
+        // Head and tail share ONE copy of the scalar loop (two trips of the phase loop): the body -- predictor step
+        // plus Golomb step -- is long, and these kernels are sensitive to instruction-cache pressure.
         uint32_t j = TAPS + 1;
         const uint32_t a0 = (uint32_t)(reinterpret_cast<uintptr_t>(src.base) >> 2);
-        for (; j < num && ((a0 + j) & 3u); j++) sink(j, predict_enc_step<TAPS, WRAP>(src.get(j), hist, a, chanshift));
-        // blocks of four frames, loads two blocks (eight samples) ahead of the arithmetic; unrolling by four also
-        // lets the history shift become register renaming
-        const uint32_t nblk = (num - j) >> 2;
-        if (nblk) {
-            // blocks of four frames stream through the lane's shared-memory ring, kPcmSlots - 1 blocks ahead;
-            // unrolling by four also lets the history shift become register renaming
-            const uint4 *p = reinterpret_cast<const uint4 *>(src.base + (size_t)j * 4u);
-            const uint32_t slot_bytes = src.ring_stride;
+        uint32_t stop = min(num, j + ((0u - (a0 + j)) & 3u));
+#pragma unroll 1
+        for (int phase = 0; phase < 2; phase++) {
+#pragma unroll 1
+            for (; j < stop; j++) sink(j, predict_enc_step<TAPS, WRAP>(src.get(j), hist, a, chanshift));
+            stop = num;
+            if (phase) break;
+            const uint32_t nblk = (num - j) >> 2;
+            if (nblk) {
+                // blocks of four frames stream through the lane's shared-memory ring, kPcmSlots - 1 blocks ahead;
+                // unrolling by four also lets the history shift become register renaming
+                const uint4 *p = reinterpret_cast<const uint4 *>(src.base + (size_t)j * 4u);
+                const uint32_t slot_bytes = src.ring_stride;
 #pragma unroll
-            for (uint32_t d = 0; d + 1 < kPcmSlots; d++) {
-                cp_async_u128(src.ring + d * slot_bytes, p + min(d, nblk - 1u), d < nblk ? 16u : 0u);
-                cp_async_commit();
+                for (uint32_t d = 0; d + 1 < kPcmSlots; d++) {
+                    cp_async_u128(src.ring + d * slot_bytes, p + min(d, nblk - 1u), d < nblk ? 16u : 0u);
+                    cp_async_commit();
+                }
+                for (uint32_t b = 0; b < nblk; b++, j += 4) {
+                    const uint32_t ahead = b + kPcmSlots - 1u;
+                    cp_async_u128(src.ring + (ahead & (kPcmSlots - 1u)) * slot_bytes, p + min(ahead, nblk - 1u), ahead < nblk ? 16u : 0u);
+                    cp_async_commit();
+                    cp_async_wait<kPcmSlots - 1>();         // block b is in
+                    const uint4 cur = lds_u128(src.ring + (b & (kPcmSlots - 1u)) * slot_bytes);
+                    typename Src::Raw r;
+                    r.w[0] = cur.x; sink(j, predict_enc_step<TAPS, WRAP>(src.mix(r), hist, a, chanshift));
+                    r.w[0] = cur.y; sink(j + 1, predict_enc_step<TAPS, WRAP>(src.mix(r), hist, a, chanshift));
+                    r.w[0] = cur.z; sink(j + 2, predict_enc_step<TAPS, WRAP>(src.mix(r), hist, a, chanshift));
+                    r.w[0] = cur.w; sink(j + 3, predict_enc_step<TAPS, WRAP>(src.mix(r), hist, a, chanshift));
+                }
+                cp_async_wait<0>();
             }
-            for (uint32_t b = 0; b < nblk; b++, j += 4) {
-                const uint32_t ahead = b + kPcmSlots - 1u;
-                cp_async_u128(src.ring + (ahead & (kPcmSlots - 1u)) * slot_bytes, p + min(ahead, nblk - 1u), ahead < nblk ? 16u : 0u);
-                cp_async_commit();
-                cp_async_wait<kPcmSlots - 1>();         // block b is in
-                const uint4 cur = lds_u128(src.ring + (b & (kPcmSlots - 1u)) * slot_bytes);
-                typename Src::Raw r;
-                r.w[0] = cur.x; sink(j, predict_enc_step<TAPS, WRAP>(src.mix(r), hist, a, chanshift));
-                r.w[0] = cur.y; sink(j + 1, predict_enc_step<TAPS, WRAP>(src.mix(r), hist, a, chanshift));
-                r.w[0] = cur.z; sink(j + 2, predict_enc_step<TAPS, WRAP>(src.mix(r), hist, a, chanshift));
-                r.w[0] = cur.w; sink(j + 3, predict_enc_step<TAPS, WRAP>(src.mix(r), hist, a, chanshift));
-            }
-            cp_async_wait<0>();
         }
-        for (; j < num; j++) sink(j, predict_enc_step<TAPS, WRAP>(src.get(j), hist, a, chanshift));
         return;
     }
     constexpr int D = Src::kAhead;

@@ -958,6 +958,19 @@ extern "C" int32_t alac_b200_decode(alac_b200_engine *e, const void *cookie, uin
     CU_CHECK(e, cudaStreamSynchronize(st));
     if (overflow) { e->err = "pcm capacity exceeded"; return ALAC_B200_PARAM_ERROR; }
 
+    if (getenv("ALAC_B200_TRACE")) {        // developer aid: per-chunk timeline in ms since the call started
+        for (size_t ci = 0; ci < chunks.size(); ci++) {
+            float a = 0, b = 0, c = 0, d = 0;
+            if (in_host) cudaEventElapsedTime(&a, e->ev[0], h2d_done[ci]);
+            cudaEventElapsedTime(&b, e->ev[0], t_dec[2 * ci]);
+            cudaEventElapsedTime(&c, e->ev[0], t_dec[2 * ci + 1]);
+            cudaEventElapsedTime(&d, e->ev[0], comp_done[ci]);
+            fprintf(stderr, "[alac_b200] dec chunk %zu: %u packets, h2d done %.2f, kernels %.2f..%.2f, done %.2f\n", ci, chunks[ci].cnt, a, b, c, d);
+        }
+        float z = 0;
+        cudaEventElapsedTime(&z, e->ev[0], e->ev[3]);
+        fprintf(stderr, "[alac_b200] dec last byte on the host at %.2f\n", z);
+    }
     if (out_sample_frames) *out_sample_frames = total_frames;
     int32_t first_err = 0;
     for (uint32_t i = 0; i < P && !first_err; i++) first_err = h_status[i];

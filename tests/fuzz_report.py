@@ -1,12 +1,12 @@
 """Developer aid: decode fuzzed packets on the GPU and with the oracle, report every packet both accept but decode differently."""
 import glob, os, sys
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))   # repo root
 import numpy as np
 import alac_b200
 from oracle import oracle as O
 O.build()
 eng = alac_b200.Engine(0)
-GOLD = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "..", "tests", "golden", "*.npz")))
+GOLD = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.npz")))
 nbad = 0
 nstat = 0
 for seed in range(11, 17):

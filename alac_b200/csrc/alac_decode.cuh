@@ -2,20 +2,26 @@
 //
 //   dec_header_kernel   one lane per packet: reads the first audio element's header to learn the
 //                       packet's sample count (partial-frame field), so output offsets can be scanned.
-//                       Also classifies the packet by predictor orders; dec_perm_kernel turns the
-//                       classes into a lane -> packet permutation so warps run uniform tap counts.
-//   dec_entropy_kernel  one lane per packet: the serial walk through the packet's bits
-//                       (codec/ALACDecoder.cu:571-1002): element loop, header parse, dyn_decomp, escape
-//                       samples.  Each channel's residuals go to a scratch laid out
+//                       Also classifies the packet (classes 0..3 = "regular": one compressed element matching the
+//                       channel count, mode 0, denShift 9, 4 or 8 taps); dec_perm_kernel turns the classes into a
+//                       lane -> packet permutation so warps run uniform tap counts and regular packets fill groups.
+//   dec_fused_kernel    groups of 32 regular mono / stereo packets: an entropy warp (lane = packet: dyn_decomp of
+//                       both channels into shared-memory tiles) and a finish warp (unpc_block down each lane's
+//                       column, then un-mix / pack / store with lane = sample) run side by side, handing tiles
+//                       over through named barriers.  The residuals never leave the SM.
+//   dec_entropy_kernel  every other group, one lane per packet: the general element loop
+//                       (codec/ALACDecoder.cu:571-1002): header parse, dyn_decomp, escape samples, FIL / DSE.
+//                       Each channel's residuals go to a scratch laid out
 //                       [group of 32 packets][channel][sample][lane], so every store of a warp is one
-//                       128-byte line; a DecChanMeta / DecChanHdr per channel says how to finish it.  The
-//                       bitstream arrives through a cp.async shared-memory ring read by a branch-free window.
-//   dec_finish_kernel   one lane per (packet, element): unpc_block, then the data-parallel tail
+//                       128-byte line; a DecChanMeta / DecChanHdr per channel says how to finish it.
+//   dec_finish_kernel   the same groups, one lane per (packet, element): unpc_block, then the data-parallel tail
 //                       (codec/ALACDecoder.cu:193-495 unmixNN / copyPredictorToNN).  Residual tiles of 32 samples x
 //                       32 packets stream through shared memory (cp.async, one tile ahead); the predictor runs down
 //                       each lane's column in place, then the warp flips roles (lane = sample) to un-mix, merge
 //                       the shift bytes read straight from the packet, pack and store each packet's 32
 //                       sample-frames as one contiguous run.
+//   ber_*_kernel        CAF 'pakt' table <-> packet sizes on the device.
+// The Golomb streams are read through BitReader (alac_device.cuh): a branch-free 64-bit window over a cp.async ring.
 #pragma once
 #include "alac_device.cuh"
 

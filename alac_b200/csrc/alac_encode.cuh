@@ -1,11 +1,16 @@
 // alac_encode.cuh -- encode kernels.
 //
-//   enc_search_kernel   one lane per (segment, channel): the whole serial chain of
-//                       EncodeStereo / EncodeMono (codec/ALACEncoder.cu:290-558, :812-963) --
-//                       mixRes search, numU/numV search, escape estimate, final predictor +
-//                       Golomb pass -- fused sample by sample; U and V of a pair sit on adjacent
-//                       lanes and exchange bit counts by shuffle.  Emits each channel's Golomb
-//                       stream into a private scratch slab and one ElemRec per element.
+//   enc_search_split_kernel + enc_final_kernel   (frames_per_segment = 1: every frame is its own chain)
+//                       one lane per (frame, channel), one-warp CTAs.  The search kernel runs stages A and B of
+//                       EncodeStereo / EncodeMono (codec/ALACEncoder.cu:290-558, :812-963) -- mixRes search,
+//                       numU/numV search, escape estimate; U and V of a pair sit on adjacent lanes and exchange
+//                       bit counts by shuffle -- and files each channel's final-pass job under its tap count; the
+//                       final kernel runs stage C (final predictor + Golomb emission) with full, uniform warps.
+//   enc_search_kernel   chained frames (frames_per_segment != 1 or a coefficient-state hand-off): one lane per
+//                       (segment, channel) walks the frames of its segment; stages A, B, C in one kernel, the
+//                       final-pass jobs regrouped by tap count inside the CTA.
+//                       Both forms emit each channel's Golomb stream into a private scratch slab and one
+//                       ElemRec per element.
 //   enc_size_kernel     packet byte sizes from the element records.
 //   enc_assemble_kernel one warp per packet: gathers header / shift bytes / Golomb streams /
 //                       escape samples into the packet at its scanned offset (32-bit stores).

@@ -43,6 +43,7 @@ struct DecArgs {
     int32_t *chan_scratch;        // [group][channel][frame_length][32]
     struct DecChanMeta *chan_meta; // [packet][channel]
     struct DecChanHdr *chan_hdr;   // [packet][channel]
+    uint32_t fused;                // dec_fused_kernel takes the regular groups of this call
 };
 
 // how dec_finish_kernel finishes one channel of one packet
@@ -198,16 +199,40 @@ __device__ __forceinline__ void cp_async_16(uint32_t smem_dst, const void *gsrc,
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_dst), "l"(gsrc), "r"(src_bytes) : "memory");
 }
 
-// un-mix / merge / store one tile: lane = sample j0 + lane, loop over the group's packets (codec/ALACDecoder.cu:193-495)
+__device__ __forceinline__ uint4 lds_meta(uint32_t smem_addr)
+{
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(smem_addr) : "memory");
+    return v;
+}
+
+// un-mix / merge / store one tile: lane = sample j0 + lane, loop over the group's packets (codec/ALACDecoder.cu:193-495).
+// `metas` is the shared-memory ADDRESS of the FinMeta array (taken once by the caller: inside the loop the compiler
+// re-derived it from the generic pointer with an S2R at every trip).  `simple16` (warp-uniform) = 16-bit output, every
+// packet of the group a stereo pair without shift bytes and the output 4-byte aligned: a short branch-free body.
 template <int DEPTH>
-__device__ __forceinline__ void flush_tile(const DecArgs &A, const FinMeta *metas, const int32_t *bu, const int32_t *bv, uint32_t j0,
-                                           uint32_t lane, uint32_t pr0, uint32_t pr_step, bool out_pair32, uint32_t zero_chans)
+__device__ __forceinline__ void flush_tile(const DecArgs &A, uint32_t metas, const int32_t *bu, const int32_t *bv, uint32_t j0,
+                                           uint32_t lane, uint32_t pr0, uint32_t pr_step, bool out_pair32, uint32_t zero_chans,
+                                           bool simple16)
 {
     constexpr uint32_t bps = DepthTraits<DEPTH>::kBytes;
     const uint32_t stride = A.num_channels * bps;
     const uint32_t j = j0 + lane;
+    if (DEPTH == 16 && simple16) {
+        for (uint32_t pr = pr0; pr < 32; pr += pr_step) {
+            const uint4 q = lds_meta(metas + pr * (uint32_t)sizeof(FinMeta));   // out0, n, {kind, shift, mix_bits, mix_res}
+            if (j >= q.z) continue;                                             // (slots past the last packet have n = 0)
+            const int32_t l = bu[lane * kTilePitch + pr], v = bv[lane * kTilePitch + pr];
+            const int32_t mix_res = (int32_t)q.w >> 24;
+            const int32_t lm = l + v - ((mix_res * v) >> ((q.w >> 16) & 31u));  // :193-223
+            const int32_t lo = mix_res ? lm : l, ro = mix_res ? lm - v : v;
+            uint8_t *out = reinterpret_cast<uint8_t *>(((uint64_t)q.y << 32) | q.x) + (size_t)j * 4u;
+            *reinterpret_cast<uint32_t *>(out) = ((uint32_t)lo & 0xffffu) | ((uint32_t)ro << 16);
+        }
+        return;
+    }
     for (uint32_t pr = pr0; pr < 32; pr += pr_step) {
-        const uint4 q = *reinterpret_cast<const uint4 *>(&metas[pr]);          // out0, n, {kind, shift, mix_bits, mix_res}
+        const uint4 q = lds_meta(metas + pr * (uint32_t)sizeof(FinMeta));       // out0, n, {kind, shift, mix_bits, mix_res}
         const uint32_t n = q.z, kind = q.w & 0xffu, shift = (q.w >> 8) & 0xffu, mix_bits = (q.w >> 16) & 0xffu;
         const int32_t mix_res = (int32_t)q.w >> 24;
         if (kind == CH_PAIR_V || j >= n) continue;
@@ -219,7 +244,11 @@ __device__ __forceinline__ void flush_tile(const DecArgs &A, const FinMeta *meta
         int32_t l = bu[lane * kTilePitch + pr];
         BitPeek bp;
         uint32_t shift_pos = 0;
-        if (shift) { const FinMeta &m = metas[pr]; bp.start(m.pkt, m.pkt_size); shift_pos = m.shift_pos; }
+        if (shift) {
+            const uint4 q2 = lds_meta(metas + pr * (uint32_t)sizeof(FinMeta) + 16u);    // pkt, pkt_size, shift_pos
+            bp.start(reinterpret_cast<const uint8_t *>(((uint64_t)q2.y << 32) | q2.x), q2.z);
+            shift_pos = q2.w;
+        }
         if (kind == CH_MONO) {
             if (shift) l = (int32_t)(((uint32_t)l << shift) | bp.bits_at(shift_pos + j * shift, shift));       // :436-495
             store_sample<DEPTH>(out, l);
@@ -250,6 +279,7 @@ __device__ __forceinline__ void flush_tile(const DecArgs &A, const FinMeta *meta
 // are all packets of the group regular?  (lanes past the last packet count as regular)
 __device__ __forceinline__ bool group_is_regular(const DecArgs &A, uint32_t group, uint32_t lane)
 {
+    if (!A.fused) return false;
     const uint32_t slot = group * 32u + lane;
     const uint32_t cls = slot < A.num_packets ? A.pkt_class[A.perm[A.pkt_base + slot]] : 0u;
     return __all_sync(0xffffffffu, cls < kRegularClasses);
@@ -540,6 +570,7 @@ __global__ void __launch_bounds__(64) dec_finish_kernel(DecArgs A)
         chanshift = 32u - hp->chan_bits;
         mode = pred_setup(hp, M.n, gtile + lane, st);
     }
+    const uint32_t metas_saddr = (uint32_t)__cvta_generic_to_shared(s_meta);
     const bool warp_has_tiles = __any_sync(0xffffffffu, mine || (w == 0 && M.kind != CH_PAIR_V));
     const uint32_t n_pred = mine ? M.n : 0u;
     const uint32_t n_max = __reduce_max_sync(0xffffffffu, (M.kind == CH_PAIR_V) ? 0u : M.n);      // same in both warps
@@ -572,7 +603,7 @@ __global__ void __launch_bounds__(64) dec_finish_kernel(DecArgs A)
         if (j0 < n_pred) unpc_rows_any(mode, st, s_tile[t & 1u][w] + lane, j0, 0, min(n_pred - j0, kTileRows), chanshift);
         __syncthreads();
         // ---- parallel phase: lane = sample; warp w takes the packets of its parity
-        flush_tile<DEPTH>(A, s_meta, bu, bv, j0, lane, w, 2, out_pair32, 1);
+        flush_tile<DEPTH>(A, metas_saddr, bu, bv, j0, lane, w, 2, out_pair32, 1, false);
         __syncthreads();
         request(t + 2);                 // refills the buffer just drained (an empty group past the last tile)
     }
@@ -737,6 +768,10 @@ __global__ void __launch_bounds__(64) dec_fused_kernel(DecArgs A)
     const uint32_t n_max = s_nmax;
     const uint32_t tiles = (n_max + kTileRows - 1) / kTileRows;
     const FinMeta M = s_meta[lane];
+    const uint32_t metas_saddr = (uint32_t)__cvta_generic_to_shared(s_meta);
+    // every packet of the group a stereo pair without shift bytes (slots past the last packet: n = 0), aligned 16-bit output
+    const bool simple16 = DEPTH == 16 && out_pair32 &&
+                          __all_sync(0xffffffffu, (M.kind == CH_PAIR_U && M.shift == 0) || (M.kind == CH_PAIR_V && M.n == 0));
     const bool mine = (M.kind == CH_MONO || M.kind == CH_PAIR_U);
     const uint32_t n_pred = mine ? M.n : 0u;
     for (uint32_t c = 0; c < nch; c++) {
@@ -770,11 +805,16 @@ __global__ void __launch_bounds__(64) dec_fused_kernel(DecArgs A)
             if (!last_chan) {
                 // U of a pair: park the finished column in the scratch (one 128-byte row per store)
                 int32_t *g = gtile_u + (size_t)j0 * 32u + lane;
-                for (uint32_t r = 0; r < kTileRows && j0 + r < F; r++) g[(size_t)r * 32u] = buf[r * kTilePitch + lane];
+                if (j0 + kTileRows <= F) {
+#pragma unroll
+                    for (uint32_t r = 0; r < kTileRows; r++) g[r * 32u] = buf[r * kTilePitch + lane];
+                } else {
+                    for (uint32_t r = 0; r < kTileRows && j0 + r < F; r++) g[(size_t)r * 32u] = buf[r * kTilePitch + lane];
+                }
             } else {
                 cp_async_wait<0>();
                 __syncwarp();
-                flush_tile<DEPTH>(A, s_meta, nch == 2 ? s_xu : buf, buf, j0, lane, 0, 1, out_pair32, nch);
+                flush_tile<DEPTH>(A, metas_saddr, nch == 2 ? s_xu : buf, buf, j0, lane, 0, 1, out_pair32, nch, simple16);
                 __syncwarp();
             }
             __syncwarp();

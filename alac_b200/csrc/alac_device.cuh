@@ -336,10 +336,11 @@ struct BitPeek {
 //     LDS, no branch -- so hi always holds 32 valid bits;
 //   * the packet's words stream through a private shared-memory ring (slot s of this lane is
 //     ring[s * kRingStride], bank == lane) filled by cp.async (LDGSTS).  The ring is topped up at a WARP-UNIFORM
-//     cadence (every kTopUpEvery symbols, top_up()); what one top-up requests is only assumed to have landed after
-//     the NEXT top-up (wait_group 1), so the global-load latency never sits on the decode's dependency chain.
-//     One symbol step consumes at most 9 + 32 bits plus a 25-bit run code = 66 bits, so two periods consume at most
-//     2 * kTopUpEvery * 66 bits = 33 words, well inside the kRingSlots = 64 words requested ahead.
+//     cadence (every kTopUpEvery symbols, top_up()); what one top-up requests is only assumed to have landed TWO
+//     top-ups later (wait_group 2), so the global-load latency never sits on the decode's dependency chain (with
+//     wait_group 1 the entropy warp still spent a fifth of its time waiting there).
+//     One symbol step consumes at most 9 + 32 bits plus a 25-bit run code = 66 bits, so three periods consume at most
+//     3 * kTopUpEvery * 66 bits = 50 words, inside the kRingSlots = 64 words requested ahead.
 //   * headers and escape samples are sparse reads and go through BitPeek instead; seek() (synchronous) positions
 //     this reader at the first bit of a Golomb stream.
 constexpr uint32_t kRingSlots = 64;
@@ -348,7 +349,7 @@ constexpr uint32_t kTopUpEvery = 8;
 #define ALAC_DEC_LANES 32
 #endif
 constexpr uint32_t kRingStride = ALAC_DEC_LANES;     // lanes per CTA of the kernels that use BitReader
-static_assert(2 * kTopUpEvery * 66 + 4 * 32 <= kRingSlots * 32, "ring too small for the top-up cadence");
+static_assert(3 * kTopUpEvery * 66 + 4 * 32 <= kRingSlots * 32, "ring too small for the top-up cadence");
 
 // 4-byte cp.async with a source size: src_bytes = 0 reads nothing and zero-fills the destination
 __device__ __forceinline__ void cp_async_word(uint32_t smem_dst, const uint32_t *gsrc, uint32_t src_bytes)
@@ -378,7 +379,6 @@ struct BitReader {
     uint32_t ring;          // shared-memory address of this lane's ring column
     uint32_t rd;            // index of the word held in nxt (the next one to enter the window)
     uint32_t wr;            // next word index to request
-    uint32_t landed;        // words below this index are known to be in the ring
     uint32_t hi, lo;        // window: the next unread bit is the MSB of hi
     uint32_t navail;        // valid bits in hi:lo (>= 32 after refill())
     uint32_t nxt;           // word rd, byte-swapped
@@ -393,26 +393,23 @@ struct BitReader {
         cp_async_word(slot_addr(i), base + (in ? i : 0u), in ? ((int32_t)i == last_word ? tail_bytes : 4u) : 0u);
     }
     // request everything up to kRingSlots words past the read position (slots of words < rd are free)
-    __device__ __forceinline__ uint32_t request_ahead()
+    __device__ __forceinline__ void request_ahead()
     {
-        const uint32_t old = wr, limit = rd + kRingSlots;
+        const uint32_t limit = rd + kRingSlots;
         while ((int32_t)(limit - wr) > 0) issue(wr++);
         cp_async_commit();
-        return old;
     }
-    // asynchronous top-up: what THIS call requests is only usable after the next one
+    // asynchronous top-up: what THIS call requests is only usable after the next two
     __device__ __forceinline__ void top_up()
     {
-        const uint32_t old = request_ahead();
-        cp_async_wait<1>();
-        landed = old;
+        request_ahead();
+        cp_async_wait<2>();
     }
     // synchronous top-up: everything requested so far is in
     __device__ __forceinline__ void prime()
     {
         request_ahead();
         cp_async_wait<0>();
-        landed = wr;
     }
     __device__ __forceinline__ void consume(uint32_t nbits)     // 0..32 (<= navail)
     {

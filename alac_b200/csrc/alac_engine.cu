@@ -897,8 +897,11 @@ extern "C" int32_t alac_b200_decode(alac_b200_engine *e, const void *cookie, uin
         const uint32_t lgrid = (c.cnt + kRingStride - 1) / kRingStride;
         const uint32_t groups_c = (c.cnt + 31) / 32;
         const uint32_t fgrid = groups_c * nch;
-        // regular mono / stereo groups: entropy and finish warps side by side in one kernel
-        if (nch <= 2) {
+        // regular mono / stereo groups: entropy and finish warps side by side in one kernel.  Not for the depths with
+        // shift bytes (24 / 32 bit): there the parallel phase re-reads the packet for every sample, which the single
+        // finish warp of the fused kernel cannot hide (measured 4.6 ms fused against 4.3 ms with the two general kernels)
+        A.fused = (nch <= 2 && (depth == 16 || depth == 20)) ? 1u : 0u;
+        if (A.fused) {
             switch (depth) {
             case 16: dec_fused_kernel<16><<<groups_c, 64, 0, cs>>>(A); break;
             case 20: dec_fused_kernel<20><<<groups_c, 64, 0, cs>>>(A); break;

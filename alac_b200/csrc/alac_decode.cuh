@@ -242,15 +242,26 @@ __device__ __forceinline__ void flush_tile(const DecArgs &A, uint32_t metas, con
             continue;
         }
         int32_t l = bu[lane * kTilePitch + pr];
-        BitPeek bp;
-        uint32_t shift_pos = 0;
+        // this sample's shifted-off low bits (mono: `shift` bits, pair: L then R, 2 * shift bits) straight from the packet
+        uint32_t low = 0;
         if (shift) {
             const uint4 q2 = lds_meta(metas + pr * (uint32_t)sizeof(FinMeta) + 16u);    // pkt, pkt_size, shift_pos
-            bp.start(reinterpret_cast<const uint8_t *>(((uint64_t)q2.y << 32) | q2.x), q2.z);
-            shift_pos = q2.w;
+            const uint64_t addr = ((uint64_t)q2.y << 32) | q2.x;
+            const uint32_t W = (kind == CH_MONO) ? shift : 2u * shift;                  // <= 32
+            const uint32_t bias = (uint32_t)(addr & 3u) * 8u;
+            const uint32_t abs_bit = bias + q2.w + j * W, i = abs_bit >> 5;
+            if ((i + 2u) * 32u <= bias + q2.z * 8u) {
+                // both words lie inside the packet: two aligned loads and a funnel shift
+                const uint32_t *base = reinterpret_cast<const uint32_t *>(addr & ~(uint64_t)3);
+                low = __funnelshift_l(bswap32(__ldg(base + i + 1)), bswap32(__ldg(base + i)), abs_bit & 31u) >> (32u - W);
+            } else {
+                BitPeek bp;                                                             // near the end: the bounds-checked reader
+                bp.start(reinterpret_cast<const uint8_t *>(addr), q2.z);
+                low = bp.bits_at(q2.w + j * W, W);
+            }
         }
         if (kind == CH_MONO) {
-            if (shift) l = (int32_t)(((uint32_t)l << shift) | bp.bits_at(shift_pos + j * shift, shift));       // :436-495
+            if (shift) l = (int32_t)(((uint32_t)l << shift) | low);                     // :436-495
             store_sample<DEPTH>(out, l);
         } else {
             const int32_t v = bv[lane * kTilePitch + pr];
@@ -262,9 +273,8 @@ __device__ __forceinline__ void flush_tile(const DecArgs &A, uint32_t metas, con
                 r = v;
             }
             if (shift) {                                // :282-383
-                const uint32_t both = bp.bits_at(shift_pos + j * 2u * shift, 2u * shift);
-                l = (int32_t)(((uint32_t)l << shift) | (both >> shift));
-                r = (int32_t)(((uint32_t)r << shift) | (both & ((1u << shift) - 1u)));
+                l = (int32_t)(((uint32_t)l << shift) | (low >> shift));
+                r = (int32_t)(((uint32_t)r << shift) | (low & ((1u << shift) - 1u)));
             }
             if (DEPTH == 16 && out_pair32) {
                 *reinterpret_cast<uint32_t *>(out) = ((uint32_t)l & 0xffffu) | ((uint32_t)r << 16);

@@ -899,8 +899,9 @@ extern "C" int32_t alac_b200_decode(alac_b200_engine *e, const void *cookie, uin
         const uint32_t fgrid = groups_c * nch;
         // regular mono / stereo groups: entropy and finish warps side by side in one kernel.  Not for the depths with
         // shift bytes (24 / 32 bit): there the parallel phase re-reads the packet for every sample, which the single
-        // finish warp of the fused kernel cannot hide (measured 4.6 ms fused against 4.3 ms with the two general kernels)
-        A.fused = (nch <= 2 && (depth == 16 || depth == 20)) ? 1u : 0u;
+        // finish warp of the fused kernel cannot hide (24-bit: 4.2 ms either way; 32-bit: 5.3 ms fused against 4.8 ms)
+        static const int fused_mode = [] { const char *v = getenv("ALAC_B200_FUSED"); return v ? atoi(v) : -1; }();   // developer override: 0 never, 1 always
+        A.fused = (nch <= 2 && (fused_mode < 0 ? (depth == 16 || depth == 20) : fused_mode != 0)) ? 1u : 0u;
         if (A.fused) {
             switch (depth) {
             case 16: dec_fused_kernel<16><<<groups_c, 64, 0, cs>>>(A); break;

@@ -18,9 +18,12 @@ from .engine import (  # noqa: F401
     magic_cookie,
     parse_cookie,
     encode_bound,
+    Placement,
+    DevicePtr,
+    EXCHANGE_BYTES,
 )
 
 __all__ = [
     "AlacError", "EncodeResult", "DecodeResult", "Engine", "EncoderConfig",
-    "library_path", "load_library", "magic_cookie", "parse_cookie", "encode_bound",
+    "library_path", "load_library", "magic_cookie", "parse_cookie", "encode_bound", "Placement", "DevicePtr", "EXCHANGE_BYTES",
 ]

@@ -726,60 +726,85 @@ __global__ void enc_size_kernel(ElemRec *recs, EncLayout lay, uint32_t depth, co
     if (esc) atomicAdd(escapes, (unsigned long long)esc);
 }
 
-// ---- exclusive scan (single block, sequential tiles) -------------------------------------------------------
-// offsets[i] = sum_{j<i} sizes[j]; offsets[n] = total.  One 1024-thread block walks the array in tiles of 4096
-// (four consecutive elements per thread).
-__global__ void __launch_bounds__(1024) scan_u32_to_u64_kernel(const uint32_t *in, uint64_t *out, uint64_t n, uint32_t *max_out, int chain_base,
-                                                               uint64_t *host_total = nullptr)
+// ---- exclusive scan (two launches, any length) ----------------------------------------------------------------
+// offsets[i] = sum_{j<i} sizes[j]; offsets[n] = total.  Tiles of 4096 elements (four consecutive elements per thread of a
+// 1024-thread block): scan_tile_sums_kernel reduces every tile, scan_u32_to_u64_kernel sums the tile totals in front
+// of its tile (a few hundred values even for the 843,750 packets of a 10-hour stream), scans its own tile and writes it.
+constexpr uint32_t kScanTile = 4096;
+__device__ __forceinline__ uint64_t block_sum_u64(uint64_t x, uint64_t *warp_sums)
+{
+    const uint32_t lane = threadIdx.x & 31u, wid = threadIdx.x >> 5;
+#pragma unroll
+    for (int d = 16; d; d >>= 1) x += __shfl_xor_sync(0xffffffffu, x, d);
+    __syncthreads();                // warp_sums may still be read from a previous use
+    if (lane == 0) warp_sums[wid] = x;
+    __syncthreads();
+    uint64_t s = warp_sums[lane];   // 32 warps
+#pragma unroll
+    for (int d = 16; d; d >>= 1) s += __shfl_xor_sync(0xffffffffu, s, d);
+    return s;                       // every thread holds the block total
+}
+
+__global__ void __launch_bounds__(1024) scan_tile_sums_kernel(const uint32_t *in, uint64_t n, uint64_t *tile_sums)
 {
     __shared__ uint64_t warp_sums[32];
-    __shared__ uint64_t carry_s;
+    const uint64_t i0 = (uint64_t)blockIdx.x * kScanTile + 4ull * threadIdx.x;
+    uint64_t x = 0;
+#pragma unroll
+    for (int k = 0; k < 4; k++) x += i0 + k < n ? in[i0 + k] : 0u;
+    const uint64_t total = block_sum_u64(x, warp_sums);
+    if (threadIdx.x == 0) tile_sums[blockIdx.x] = total;
+}
+
+// chain_base: continue from out[0], which the previous chunk's scan left as its grand total (tile 0 rewrites out[0]
+// with that same value, so tiles reading it concurrently see one value either way).
+__global__ void __launch_bounds__(1024) scan_u32_to_u64_kernel(const uint32_t *in, uint64_t *out, uint64_t n, const uint64_t *tile_sums,
+                                                               uint32_t *max_out, int chain_base, uint64_t *host_total = nullptr)
+{
+    __shared__ uint64_t warp_sums[32];
     __shared__ uint32_t warp_max[32];
     const uint32_t lane = threadIdx.x & 31u, wid = threadIdx.x >> 5;
-    // chain_base: continue from out[0], which the previous chunk's scan left as its grand total
-    if (threadIdx.x == 0) carry_s = chain_base ? out[0] : 0;
-    __syncthreads();
+    // tile totals in front of this tile
+    uint64_t before = 0;
+    for (uint32_t t = threadIdx.x; t < blockIdx.x; t += 1024u) before += tile_sums[t];
+    uint64_t carry = block_sum_u64(before, warp_sums);
+    if (chain_base) carry += *reinterpret_cast<volatile const uint64_t *>(out);
+    const uint64_t i0 = (uint64_t)blockIdx.x * kScanTile + 4ull * threadIdx.x;
+    uint32_t v[4];
     uint32_t my_max = 0;
-    for (uint64_t tile = 0; tile < n; tile += 4096) {
-        const uint64_t i0 = tile + 4ull * threadIdx.x;
-        uint32_t v[4];
 #pragma unroll
-        for (int k = 0; k < 4; k++) { v[k] = i0 + k < n ? in[i0 + k] : 0u; my_max = max(my_max, v[k]); }
-        uint64_t x = (uint64_t)v[0] + v[1] + v[2] + v[3];
-        const uint64_t mine = x;
+    for (int k = 0; k < 4; k++) { v[k] = i0 + k < n ? in[i0 + k] : 0u; my_max = max(my_max, v[k]); }
+    uint64_t x = (uint64_t)v[0] + v[1] + v[2] + v[3];
+    const uint64_t mine = x;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint64_t y = __shfl_up_sync(0xffffffffu, x, d);
+        if (lane >= (uint32_t)d) x += y;
+    }
+    __syncthreads();
+    if (lane == 31) warp_sums[wid] = x;
+    __syncthreads();
+    if (wid == 0) {
+        uint64_t s = warp_sums[lane];
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
-            const uint64_t y = __shfl_up_sync(0xffffffffu, x, d);
-            if (lane >= (uint32_t)d) x += y;
+            const uint64_t y = __shfl_up_sync(0xffffffffu, s, d);
+            if (lane >= (uint32_t)d) s += y;
         }
-        if (lane == 31) warp_sums[wid] = x;
-        __syncthreads();
-        if (wid == 0) {
-            uint64_t s = warp_sums[lane];
-#pragma unroll
-            for (int d = 1; d < 32; d <<= 1) {
-                const uint64_t y = __shfl_up_sync(0xffffffffu, s, d);
-                if (lane >= (uint32_t)d) s += y;
-            }
-            warp_sums[lane] = s;
-        }
-        __syncthreads();
-        const uint64_t carry = carry_s;
-        const uint64_t incl = x + (wid ? warp_sums[wid - 1] : 0) + carry;
-        uint64_t run = incl - mine;         // exclusive prefix of this thread's first element
-#pragma unroll
-        for (int k = 0; k < 4; k++) {
-            if (i0 + k < n) out[i0 + k] = run;
-            run += v[k];
-        }
-        __syncthreads();
-        if (threadIdx.x == 1023) carry_s = incl;
-        __syncthreads();
+        warp_sums[lane] = s;
     }
-    if (threadIdx.x == 0) {
-        out[n] = carry_s;
+    __syncthreads();
+    const uint64_t incl = x + (wid ? warp_sums[wid - 1] : 0) + carry;
+    uint64_t run = incl - mine;         // exclusive prefix of this thread's first element
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        if (i0 + k < n) out[i0 + k] = run;
+        run += v[k];
+    }
+    if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 1023) {
+        out[n] = incl;
         // pinned host word (UVA): the host reads it after the chunk's completion event, no copy-engine op needed
-        if (host_total) { *host_total = carry_s; __threadfence_system(); }
+        if (host_total) { *host_total = incl; __threadfence_system(); }
     }
     if (max_out) {
         for (int d = 16; d; d >>= 1) my_max = max(my_max, __shfl_xor_sync(0xffffffffu, my_max, d));
@@ -790,6 +815,103 @@ __global__ void __launch_bounds__(1024) scan_u32_to_u64_kernel(const uint32_t *i
             for (int d = 16; d; d >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, d));
             if (lane == 0) atomicMax(max_out, m);
         }
+    }
+}
+
+// ---- cross-GPU packet-offset exchange -----------------------------------------------------------------
+// A 1 KB block in the destination GPU's memory.  Rank r publishes the byte total of its packet block, then waits -- on
+// the device -- for the totals of the ranks in front of it: their sum is where its block starts.  Slots are tagged with
+// the call's epoch and alternate by its parity; the home rank ends a call only when every rank has reported `done`, so no
+// rank can be more than one call ahead of another and two slots suffice.
+struct Exchange {
+    unsigned long long total[2][16];
+    uint32_t ready[2][16];
+    uint32_t done[2][16];
+};
+static_assert(sizeof(Exchange) <= 1024, "ALAC_B200_EXCHANGE_BYTES");
+constexpr unsigned long long kExchangeTimeoutNs = 20ull * 1000 * 1000 * 1000;
+
+__device__ __forceinline__ uint32_t ld_acquire_sys_u32(const uint32_t *p)
+{
+    uint32_t v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_sys_u32(uint32_t *p, uint32_t v)
+{
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_relaxed_sys_u64(const unsigned long long *p)
+{
+    unsigned long long v;
+    asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ unsigned long long global_timer_ns()
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+// spin until *flag == epoch; false on timeout
+__device__ __forceinline__ bool spin_until(const uint32_t *flag, uint32_t epoch)
+{
+    const unsigned long long t0 = global_timer_ns();
+    while (ld_acquire_sys_u32(flag) != epoch) {
+        if (global_timer_ns() - t0 > kExchangeTimeoutNs) return false;
+        __nanosleep(200);
+    }
+    return true;
+}
+
+// one warp: publish this rank's total (*total_word = offsets[P] of the rank's scan), then sum the totals in front
+__global__ void xchg_publish_resolve_kernel(Exchange *x, uint32_t rank, uint32_t epoch, const uint64_t *total_word, uint64_t *base_out,
+                                            uint32_t *err)
+{
+    const uint32_t slot = epoch & 1u, lane = threadIdx.x;
+    if (lane == 0) {
+        *reinterpret_cast<volatile unsigned long long *>(&x->total[slot][rank]) = *total_word;
+        __threadfence_system();
+        st_release_sys_u32(&x->ready[slot][rank], epoch);
+    }
+    unsigned long long mine = 0;
+    bool ok = true;
+    if (lane < rank) {
+        ok = spin_until(&x->ready[slot][lane], epoch);
+        if (ok) mine = ld_relaxed_sys_u64(&x->total[slot][lane]);
+    }
+#pragma unroll
+    for (int d = 16; d; d >>= 1) mine += __shfl_xor_sync(0xffffffffu, mine, d);
+    const bool all_ok = __all_sync(0xffffffffu, ok);
+    if (lane == 0) {
+        *base_out = all_ok ? mine : 0ull;
+        if (!all_ok) *err = 1u;
+    }
+}
+
+// after the rank's last assemble launch: its block (and sizes) are in place
+__global__ void xchg_done_kernel(Exchange *x, uint32_t rank, uint32_t epoch)
+{
+    __threadfence_system();
+    st_release_sys_u32(&x->done[epoch & 1u][rank], epoch);
+}
+
+// home rank: every rank's block is in place; also totals the job (sum of all ranks' bytes)
+__global__ void xchg_wait_all_kernel(Exchange *x, uint32_t n_ranks, uint32_t epoch, uint64_t *job_total, uint32_t *err)
+{
+    const uint32_t slot = epoch & 1u, lane = threadIdx.x;
+    bool ok = true;
+    unsigned long long mine = 0;
+    if (lane < n_ranks) {
+        ok = spin_until(&x->done[slot][lane], epoch);
+        if (ok) mine = ld_relaxed_sys_u64(&x->total[slot][lane]);
+    }
+#pragma unroll
+    for (int d = 16; d; d >>= 1) mine += __shfl_xor_sync(0xffffffffu, mine, d);
+    const bool all_ok = __all_sync(0xffffffffu, ok);
+    if (lane == 0) {
+        if (job_total) *job_total = mine;
+        if (!all_ok) *err = 2u;
     }
 }
 
@@ -838,7 +960,8 @@ struct AsmArgs {
     uint32_t cap_words;
     const uint32_t *sizes;
     const uint64_t *offsets;
-    uint8_t *out;
+    uint8_t *out;                 // local memory, or another GPU's (peer stores over NVLink)
+    const uint64_t *base;         // optional device word: byte offset of this launch's block inside `out`
     uint32_t pkt_base;            // chunk: first packet; recs / scratch are chunk-relative
     uint32_t num_packets;         // chunk: packets handled by this launch
     EncLayout lay;
@@ -931,7 +1054,7 @@ __global__ void __launch_bounds__(kAsmWarps * 32) enc_assemble_kernel(AsmArgs A)
     const uint32_t nreg = s_nreg[wid];
     const Region *R = s_reg[wid];
     const uint32_t size = A.sizes[pkt];
-    uint8_t *dst = A.out + A.offsets[pkt];
+    uint8_t *dst = A.out + (A.base ? *A.base : 0ull) + A.offsets[pkt];
     // output is written as 4-byte words aligned in the OUTPUT buffer; a = bytes before the first aligned word
     const uint32_t mis = (uint32_t)(reinterpret_cast<uintptr_t>(dst) & 3u);
     const uint32_t lead_bytes = mis ? (4u - mis) : 0u;     // bytes of the packet before the first aligned word

@@ -13,6 +13,7 @@
 #include <cstring>
 #include <string>
 #include <chrono>
+#include <thread>
 #include <vector>
 
 using namespace alacb;
@@ -57,16 +58,21 @@ struct alac_b200_engine {
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     std::string err;
     // encode
-    DevBuf pcm, pkt_frame, pkt_samples, seg_first, seg_count, seg_stream, recs, scratch, sizes, offsets, out, state, counters;
+    DevBuf pcm, pkt_frame, pkt_samples, seg_first, seg_count, seg_stream, recs, scratch, sizes, offsets, out, state, counters, scan_tiles;
     // decode
     DevBuf d_packets, d_sizes, d_pkt_off, d_pkt_samples, d_out_frame, d_status, d_pcm, d_class, d_rank, d_perm, d_chan, d_meta, d_hdr, jobs, job_counts;
     uint32_t launches = 0;
     bool decode_configured = false;
+    // several GPUs (alac_b200_engine_create_multi): subs[0] is this engine itself (the home device)
+    std::vector<alac_b200_engine *> subs;
+    DevBuf xchg, m_out, m_sizes, m_aux;      // home: exchange block; every sub: its block of a host-output / decode call
+    uint32_t epoch = 0;
     // encode geometry tables of the previous call (see alac_b200_encode)
     std::vector<uint64_t> h_pkt_frame;
     std::vector<uint32_t> h_pkt_samples, h_seg_first, h_seg_count, h_seg_stream;
     std::vector<alac_b200_stream> tab_streams;
     uint32_t tab_F = 0, tab_K = 0;
+    uint64_t tab_sample_sum = 0;     // sum of the streams' lengths (the exact output bound of the table)
     bool tables_valid = false;
     // per-kernel timers: (start, stop) event pairs, grown on demand, reused across calls
     std::vector<cudaEvent_t> timers;
@@ -258,10 +264,13 @@ int32_t alac_b200_engine_create(int32_t device, alac_b200_engine **out_engine)
 void alac_b200_engine_destroy(alac_b200_engine *e)
 {
     if (!e) return;
+    for (size_t i = 1; i < e->subs.size(); i++) alac_b200_engine_destroy(e->subs[i]);
+    e->subs.clear();
     cudaSetDevice(e->device);
+    e->xchg.release(); e->m_out.release(); e->m_sizes.release(); e->m_aux.release();
     cudaStreamSynchronize(e->stream);
     DevBuf *bufs[] = {&e->pcm, &e->pkt_frame, &e->pkt_samples, &e->seg_first, &e->seg_count, &e->seg_stream, &e->recs,
-                      &e->scratch, &e->sizes, &e->offsets, &e->out, &e->state, &e->counters, &e->d_packets, &e->d_sizes,
+                      &e->scratch, &e->sizes, &e->offsets, &e->out, &e->state, &e->counters, &e->scan_tiles, &e->d_packets, &e->d_sizes,
                       &e->d_pkt_off, &e->d_pkt_samples, &e->d_out_frame, &e->d_status, &e->d_pcm, &e->d_class, &e->d_rank, &e->d_perm, &e->d_chan, &e->d_meta, &e->d_hdr, &e->jobs, &e->job_counts};
     for (DevBuf *b : bufs) b->release();
     for (auto &ev : e->ev)
@@ -417,17 +426,49 @@ static void launch_assemble(alac_b200_engine *e, const AsmArgs &A)
     e->launches++;
 }
 
-extern "C" int32_t alac_b200_encode(alac_b200_engine *e, const alac_b200_enc_config *cfg, const void *pcm,
-                                    uint64_t num_sample_frames, int32_t pcm_mem, const alac_b200_stream *streams,
-                                    uint64_t n_streams, void *packets_out, uint64_t packets_cap, uint32_t *packet_sizes,
-                                    uint64_t sizes_cap, int32_t out_mem, int16_t *coef_state, uint64_t *out_num_packets,
-                                    uint64_t *out_bytes, alac_b200_stats *stats)
+// Synchronises every stream a call may have used when the call returns early (CU_CHECK, capacity errors): queued
+// kernels and copies must not outlive the call -- they use engine scratch the next call reuses and write to locals
+// (pinned counters, status vectors) that are destroyed on return.  Declare it AFTER those locals.
+struct DrainGuard {
+    alac_b200_engine *e;
+    bool armed = true;
+    explicit DrainGuard(alac_b200_engine *eng) : e(eng) {}
+    ~DrainGuard()
+    {
+        if (!armed) return;
+        cudaStreamSynchronize(e->stream);
+        cudaStreamSynchronize(e->copy_in);
+        cudaStreamSynchronize(e->copy_out);
+        for (auto &ln : e->lanes) cudaStreamSynchronize(ln);
+        e->cur = nullptr;
+    }
+};
+
+static void launch_scan(alac_b200_engine *e, cudaStream_t s, const uint32_t *in, uint64_t *out, uint64_t n, uint64_t *tiles,
+                        uint32_t *max_out, int chain_base, uint64_t *host_total)
+{
+    const uint32_t blocks = (uint32_t)std::max<uint64_t>(1, (n + kScanTile - 1) / kScanTile);
+    if (blocks > 1) scan_tile_sums_kernel<<<blocks, 1024, 0, s>>>(in, n, tiles);
+    scan_u32_to_u64_kernel<<<blocks, 1024, 0, s>>>(in, out, n, tiles, max_out, chain_base, host_total);
+    e->launches += blocks > 1 ? 2 : 1;
+}
+static size_t scan_tiles_for(uint64_t n) { return (size_t)((n + kScanTile - 1) / kScanTile + 1); }
+
+static int32_t encode_core(alac_b200_engine *e, const alac_b200_enc_config *cfg, const void *pcm,
+                           uint64_t num_sample_frames, int32_t pcm_mem, const alac_b200_stream *streams,
+                           uint64_t n_streams, void *packets_out, uint64_t packets_cap, uint32_t *packet_sizes,
+                           uint64_t sizes_cap, int32_t out_mem, int16_t *coef_state, uint64_t *out_num_packets,
+                           uint64_t *out_bytes, alac_b200_stats *stats, const alac_b200_placement *pl, uint64_t *out_base)
 {
     if (!e) return ALAC_B200_PARAM_ERROR;
     e->err.clear();
-    if (!valid_cfg(cfg) || (!pcm && num_sample_frames) || !packets_out || !packet_sizes) return ALAC_B200_PARAM_ERROR;
+    if (!valid_cfg(cfg) || (!pcm && num_sample_frames) || (!packets_out && !pl) || !packet_sizes) return ALAC_B200_PARAM_ERROR;
+    if (pl && (!pl->dst_packets || !pl->exchange || pl->n_ranks == 0 || pl->n_ranks > ALAC_B200_MAX_RANKS || pl->rank >= pl->n_ranks ||
+               pl->home_rank >= pl->n_ranks || pl->epoch == 0 || coef_state))
+        return ALAC_B200_PARAM_ERROR;
     if (out_num_packets) *out_num_packets = 0;
     if (out_bytes) *out_bytes = 0;
+    if (out_base) *out_base = 0;
     if (stats) memset(stats, 0, sizeof(*stats));
     CU_CHECK(e, cudaSetDevice(e->device));
     e->launches = 0;
@@ -439,6 +480,10 @@ extern "C" int32_t alac_b200_encode(alac_b200_engine *e, const alac_b200_enc_con
     if (!streams) { streams = &whole; n_streams = 1; }
     const uint32_t F = cfg->frame_size, K = cfg->frames_per_segment;
     const uint64_t bpf = (uint64_t)bytes_per_sample(cfg->bit_depth) * cfg->channels;
+    // every stream inside the buffer (no wrap-around of first + length)
+    for (uint64_t s = 0; s < n_streams; s++)
+        if (streams[s].first_sample_frame > num_sample_frames || streams[s].num_sample_frames > num_sample_frames - streams[s].first_sample_frame)
+            return ALAC_B200_PARAM_ERROR;
 
     // ---- packet / segment tables (host).  They depend only on the stream list, the frame size and K, so a call
     //      with the same geometry as the previous one (the usual batch loop) reuses them, on the host and on the device ----
@@ -450,6 +495,7 @@ extern "C" int32_t alac_b200_encode(alac_b200_engine *e, const alac_b200_enc_con
     if (!same_tables) {
         e->tables_valid = false;
         h_pkt_frame.clear(); h_pkt_samples.clear(); h_seg_first.clear(); h_seg_count.clear(); h_seg_stream.clear();
+        e->tab_sample_sum = 0;
         for (uint64_t s = 0; s < n_streams; s++) {
             const alac_b200_stream &st = streams[s];
             const uint64_t packets = (st.num_sample_frames + F - 1) / F;
@@ -459,6 +505,7 @@ extern "C" int32_t alac_b200_encode(alac_b200_engine *e, const alac_b200_enc_con
                 h_pkt_frame.push_back(st.first_sample_frame + p * F);
                 h_pkt_samples.push_back((uint32_t)std::min<uint64_t>(F, st.num_sample_frames - p * F));
             }
+            e->tab_sample_sum += st.num_sample_frames;
             const uint64_t per_seg = K ? K : std::max<uint64_t>(packets, 1);
             const size_t seg0 = h_seg_first.size();
             for (uint64_t p = 0; p < packets; p += per_seg) {
@@ -475,33 +522,34 @@ extern "C" int32_t alac_b200_encode(alac_b200_engine *e, const alac_b200_enc_con
         e->tab_F = F;
         e->tab_K = K;
     }
-    for (uint64_t s = 0; s < n_streams; s++)
-        if (streams[s].first_sample_frame + streams[s].num_sample_frames > num_sample_frames) return ALAC_B200_PARAM_ERROR;
     const uint32_t P = (uint32_t)h_pkt_frame.size(), S = (uint32_t)h_seg_first.size();
     if (P > sizes_cap) return ALAC_B200_PARAM_ERROR;
-    if (packets_cap < alac_b200_encode_bound(cfg, num_sample_frames, n_streams)) return ALAC_B200_PARAM_ERROR;
-    if (P == 0) return ALAC_B200_OK;
+    // the exact worst case of THIS packet table (streams may overlap or repeat: every packet is at most its escape
+    // form, raw samples + 7 bits per channel of tags + ID_END + padding), not the nominal bound of the buffer length
+    const uint64_t need_bytes = e->tab_sample_sum * bpf + (uint64_t)P * (7ull * cfg->channels + 1ull);
+    if (!pl && packets_cap < need_bytes) { e->err = "packets_out capacity below the worst case of this packet table"; return ALAC_B200_PARAM_ERROR; }
+    if (P == 0 && !pl) return ALAC_B200_OK;
 
     EncLayout L;
     uint32_t mono_mask, pair_mask;
     build_layout(cfg, L, mono_mask, pair_mask);
 
     // ---- chunks ----
-    // Work is cut into chunks of whole segments.  A chunk bounds the scratch (<= 65,536 packets), and when
-    // host memory is involved the chunks form a 3-stage pipeline: H2D of chunk c+1 (copy-in stream) overlaps
-    // the kernels of chunk c (compute stream) and the D2H of chunk c-1's packets (copy-out stream).
+    // Work is cut into chunks of whole segments.  A chunk bounds the scratch, and when host memory is involved the
+    // chunks form a 3-stage pipeline: H2D of chunk c+1 (copy-in stream) overlaps the kernels of chunk c (a compute
+    // lane) and the D2H of chunk c-1's packets (copy-out stream).
     const uint32_t cap_words = F + 8;       // >= worst-case Golomb words per channel (<= 32 bits/sample incl. run codes)
-    const bool in_host = pcm_mem != ALAC_B200_MEM_DEVICE, out_host = out_mem != ALAC_B200_MEM_DEVICE;
+    const bool in_host = pcm_mem != ALAC_B200_MEM_DEVICE, out_host = !pl && out_mem != ALAC_B200_MEM_DEVICE;
+    const bool sizes_host = out_mem != ALAC_B200_MEM_DEVICE;
     // default: as many packets as fit an 8 GB slab budget (bigger launches fill the GPU more evenly)
     uint64_t chunk_target = scratch_chunk_packets();
     if (!chunk_target) chunk_target = std::max<uint64_t>(4096, (8ull << 30) / ((uint64_t)L.chains_per_packet * cap_words * 4));
     const bool multi = in_host || out_host;             // host buffers: chunks run on several compute streams
-    const uint32_t nlanes = multi ? 8u : 1u;
-    if (multi) chunk_target /= nlanes;
+    if (multi) chunk_target /= 8;
     const bool taper = multi && P >= 4096;
     struct Chunk { uint32_t s0, s1, p0, cnt; uint64_t f_lo, f_hi; };
     std::vector<Chunk> chunks;
-    uint64_t max_chunk = 0;
+    uint64_t max_chunk = 0, span_lo = ~0ull, span_hi = 0;
     for (uint32_t s0 = 0; s0 < S;) {
         uint32_t s1 = s0;
         uint64_t cnt = 0;
@@ -516,51 +564,66 @@ extern "C" int32_t alac_b200_encode(alac_b200_engine *e, const alac_b200_enc_con
             c.f_lo = std::min(c.f_lo, h_pkt_frame[p]);
             c.f_hi = std::max(c.f_hi, h_pkt_frame[p] + h_pkt_samples[p]);
         }
+        span_lo = std::min(span_lo, c.f_lo);
+        span_hi = std::max(span_hi, c.f_hi);
         chunks.push_back(c);
         max_chunk = std::max(max_chunk, cnt);
         s0 = s1;
     }
+    if (chunks.empty()) { span_lo = span_hi = 0; }
     if (chunks.size() > kMaxChunks) { e->err = "too many chunks"; return ALAC_B200_PARAM_ERROR; }
+    // Scratch slots.  Host pipeline: one per compute lane in use (never more lanes than chunks: a frames_per_segment = 0
+    // stream is ONE chunk and must not reserve eight whole-stream slabs).  Placed output: assembly waits for the other
+    // ranks' totals, i.e. for every chunk's scan, so no slot is reused.  Otherwise chunks run back to back in one slot.
+    const uint32_t nstreams_used = multi ? (uint32_t)std::min<size_t>(8, std::max<size_t>(chunks.size(), 1)) : 1u;
+    const uint32_t nslots = pl ? (uint32_t)std::max<size_t>(chunks.size(), 1) : nstreams_used;
 
     // ---- device buffers ----
-    CU_CHECK(e, e->pkt_frame.reserve((size_t)P * 8));
-    CU_CHECK(e, e->pkt_samples.reserve((size_t)P * 4));
-    CU_CHECK(e, e->seg_first.reserve((size_t)S * 4));
-    CU_CHECK(e, e->seg_count.reserve((size_t)S * 4));
-    CU_CHECK(e, e->seg_stream.reserve((size_t)S * 4));
-    const size_t recs_per_lane = (size_t)max_chunk * L.elems_per_packet;
-    const size_t slab_words_per_lane = (size_t)max_chunk * L.chains_per_packet * cap_words;
-    CU_CHECK(e, e->recs.reserve(recs_per_lane * nlanes * sizeof(ElemRec)));
-    CU_CHECK(e, e->scratch.reserve(slab_words_per_lane * nlanes * 4));
-    CU_CHECK(e, e->sizes.reserve((size_t)P * 4));
+    CU_CHECK(e, e->pkt_frame.reserve((size_t)P * 8 + 8));
+    CU_CHECK(e, e->pkt_samples.reserve((size_t)P * 4 + 4));
+    CU_CHECK(e, e->seg_first.reserve((size_t)S * 4 + 4));
+    CU_CHECK(e, e->seg_count.reserve((size_t)S * 4 + 4));
+    CU_CHECK(e, e->seg_stream.reserve((size_t)S * 4 + 4));
+    const size_t recs_per_slot = (size_t)max_chunk * L.elems_per_packet;
+    const size_t slab_words_per_slot = (size_t)max_chunk * L.chains_per_packet * cap_words;
+    CU_CHECK(e, e->recs.reserve(recs_per_slot * nslots * sizeof(ElemRec) + 64));
+    CU_CHECK(e, e->scratch.reserve(slab_words_per_slot * nslots * 4 + 64));
+    CU_CHECK(e, e->sizes.reserve((size_t)P * 4 + 4));
     CU_CHECK(e, e->offsets.reserve(((size_t)P + 1) * 8));
-    CU_CHECK(e, e->counters.reserve(64));
+    CU_CHECK(e, e->counters.reserve(128));
+    CU_CHECK(e, e->scan_tiles.reserve((scan_tiles_for(P) + chunks.size() + 1) * 8));
     // every segment is a single frame and no state is handed over: search and final pass run as two kernels
     const bool split = K == 1 && coef_state == nullptr;
-    const size_t jobs_per_lane = (size_t)max_chunk * L.chains_per_packet;
+    const size_t jobs_per_slot = (size_t)max_chunk * L.chains_per_packet;
     if (split) {
-        CU_CHECK(e, e->jobs.reserve(2 * jobs_per_lane * nlanes * sizeof(FinalJob)));
-        CU_CHECK(e, e->job_counts.reserve(chunks.size() * 16));        // per chunk: {4-tap, 8-tap} x {pair, mono launch}
+        CU_CHECK(e, e->jobs.reserve(2 * jobs_per_slot * nslots * sizeof(FinalJob) + 64));
+        CU_CHECK(e, e->job_counts.reserve(chunks.size() * 16 + 16));        // per chunk: {4-tap, 8-tap} x {pair, mono launch}
     }
     const uint8_t *d_pcm;
     if (in_host) {
-        CU_CHECK(e, e->pcm.reserve((size_t)(num_sample_frames * bpf) + 64));
-        d_pcm = e->pcm.as<uint8_t>();
+        // only the span of sample-frames the streams touch is staged; d_pcm is biased so kernels index it like the caller's buffer
+        CU_CHECK(e, e->pcm.reserve((size_t)((span_hi - span_lo) * bpf) + 64));
+        d_pcm = e->pcm.as<uint8_t>() - span_lo * bpf;
     } else {
         d_pcm = static_cast<const uint8_t *>(pcm);
     }
     uint8_t *d_out;
-    if (out_host) {
-        CU_CHECK(e, e->out.reserve((size_t)alac_b200_encode_bound(cfg, num_sample_frames, n_streams) + 64));
+    if (pl) {
+        d_out = static_cast<uint8_t *>(pl->dst_packets);
+    } else if (out_host) {
+        CU_CHECK(e, e->out.reserve((size_t)need_bytes + 64));
         d_out = e->out.as<uint8_t>();
     } else {
         d_out = static_cast<uint8_t *>(packets_out);
     }
 
     cudaStream_t st = e->stream;
+    unsigned long long h_counters[4] = {0, 0, 0, 0};        // (locals the copy-out stream writes: declared before the guard)
+    unsigned long long h_place[2] = {0, 0};
+    DrainGuard guard(e);
     CU_CHECK(e, cudaEventRecord(e->ev[0], st));
     // small tables first: they share the H2D copy engine with the PCM chunks and must not queue behind them
-    if (!same_tables) {
+    if (!same_tables && P) {
         CU_CHECK(e, cudaMemcpyAsync(e->pkt_frame.p, h_pkt_frame.data(), (size_t)P * 8, cudaMemcpyHostToDevice, st));
         CU_CHECK(e, cudaMemcpyAsync(e->pkt_samples.p, h_pkt_samples.data(), (size_t)P * 4, cudaMemcpyHostToDevice, st));
         CU_CHECK(e, cudaMemcpyAsync(e->seg_first.p, h_seg_first.data(), (size_t)S * 4, cudaMemcpyHostToDevice, st));
@@ -574,14 +637,15 @@ extern "C" int32_t alac_b200_encode(alac_b200_engine *e, const alac_b200_enc_con
         CU_CHECK(e, cudaMemcpyAsync(e->state.p, coef_state, (size_t)n_streams * ALAC_B200_STATE_INT16S * 2, cudaMemcpyHostToDevice, st));
         d_state = e->state.as<int16_t>();
     }
-    CU_CHECK(e, cudaMemsetAsync(e->counters.p, 0, 64, st));
-    if (split) CU_CHECK(e, cudaMemsetAsync(e->job_counts.p, 0, chunks.size() * 16, st));
+    CU_CHECK(e, cudaMemsetAsync(e->counters.p, 0, 128, st));
+    if (P == 0) CU_CHECK(e, cudaMemsetAsync(e->offsets.p, 0, 8, st));       // a rank with no packets still publishes a total
+    if (split) CU_CHECK(e, cudaMemsetAsync(e->job_counts.p, 0, chunks.size() * 16 + 16, st));
     // copy-in stream: PCM chunks, each followed by an event the compute stream waits on
     std::vector<cudaEvent_t> h2d_done;
     if (in_host) {
         CU_CHECK(e, cudaStreamWaitEvent(e->copy_in, e->ev[0], 0));
         for (const Chunk &c : chunks) {
-            CU_CHECK(e, cudaMemcpyAsync(e->pcm.as<uint8_t>() + c.f_lo * bpf, static_cast<const uint8_t *>(pcm) + c.f_lo * bpf,
+            CU_CHECK(e, cudaMemcpyAsync(const_cast<uint8_t *>(d_pcm) + c.f_lo * bpf, static_cast<const uint8_t *>(pcm) + c.f_lo * bpf,
                                         (size_t)((c.f_hi - c.f_lo) * bpf), cudaMemcpyHostToDevice, e->copy_in));
             h2d_done.push_back(e->event_on(e->copy_in));
         }
@@ -589,24 +653,55 @@ extern "C" int32_t alac_b200_encode(alac_b200_engine *e, const alac_b200_enc_con
     CU_CHECK(e, cudaEventRecord(e->ev[1], st));
 
     // ---- kernels, chunk by chunk.  Device-resident calls stay on the caller's stream; with host buffers chunk c
-    //      runs on compute lane c % 4 (own scratch), so its kernels overlap its neighbours' kernels and copies ----
+    //      runs on compute lane c % lanes (own scratch), so its kernels overlap its neighbours' kernels and copies ----
     // coefficients move by at most 1 per predictor step and a frame runs < 2 * frame_size steps on a row:
     // starting from init_coefs (|a| <= 1216) the int16 range cannot be left within K frames if this holds
     const bool wrap = coef_state != nullptr || K == 0 || (uint64_t)K * 2u * F + 1216u > 32767u;
     const bool packed = cfg->channels == 2 && (reinterpret_cast<uintptr_t>(d_pcm) & 7u) == 0;
     unsigned long long *d_escapes = e->counters.as<unsigned long long>();
     uint32_t *d_max = reinterpret_cast<uint32_t *>(e->counters.as<uint8_t>() + 8);
+    uint64_t *d_base = reinterpret_cast<uint64_t *>(e->counters.as<uint8_t>() + 32);       // placed: where this rank's block starts
+    uint64_t *d_job_total = reinterpret_cast<uint64_t *>(e->counters.as<uint8_t>() + 40);  // placed, home rank: bytes of the whole job
+    uint32_t *d_xerr = reinterpret_cast<uint32_t *>(e->counters.as<uint8_t>() + 16);
     std::vector<cudaEvent_t> comp_done, scan_done;
     const bool trace = getenv("ALAC_B200_TRACE") != nullptr;
     const auto host_t0 = std::chrono::steady_clock::now();
+    size_t tile_at = 0;
+    auto assemble_chunk = [&](size_t ci, cudaStream_t cs) {
+        const Chunk &c = chunks[ci];
+        const uint32_t slot = (uint32_t)(ci % nslots);
+        AsmArgs B;
+        B.pcm = d_pcm;
+        B.pkt_frame = e->pkt_frame.as<uint64_t>();
+        B.pkt_samples = e->pkt_samples.as<uint32_t>();
+        B.recs = e->recs.as<ElemRec>() + recs_per_slot * slot;
+        B.scratch = e->scratch.as<uint32_t>() + slab_words_per_slot * slot;
+        B.cap_words = cap_words;
+        B.sizes = e->sizes.as<uint32_t>();
+        B.offsets = e->offsets.as<uint64_t>();
+        B.out = d_out;
+        B.base = pl ? d_base : nullptr;
+        B.pkt_base = c.p0;
+        B.num_packets = c.cnt;
+        B.lay = L;
+        e->cur = cs;
+        t_asm.push_back(e->timer());
+        switch (cfg->bit_depth) {
+        case 16: launch_assemble<16>(e, B); break;
+        case 20: launch_assemble<20>(e, B); break;
+        case 24: launch_assemble<24>(e, B); break;
+        default: launch_assemble<32>(e, B); break;
+        }
+        t_asm.push_back(e->timer());
+    };
     for (size_t ci = 0; ci < chunks.size(); ci++) {
         const Chunk &c = chunks[ci];
-        const uint32_t lane = (uint32_t)(ci % nlanes);
+        const uint32_t lane = (uint32_t)(ci % nstreams_used), slot = (uint32_t)(ci % nslots);
         cudaStream_t cs = multi ? e->lanes[lane] : st;
         e->cur = cs;
         if (trace) fprintf(stderr, "[alac_b200] host submits enc chunk %zu at +%.2f ms\n", ci,
                            std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - host_t0).count());
-        if (multi && ci < nlanes) CU_CHECK(e, cudaStreamWaitEvent(cs, e->ev[1], 0));       // tables are in
+        if (multi && ci < nstreams_used) CU_CHECK(e, cudaStreamWaitEvent(cs, e->ev[1], 0));       // tables are in
         if (in_host) CU_CHECK(e, cudaStreamWaitEvent(cs, h2d_done[ci], 0));
         EncArgs A;
         A.pcm = d_pcm;
@@ -619,13 +714,13 @@ extern "C" int32_t alac_b200_encode(alac_b200_engine *e, const alac_b200_enc_con
         A.num_segments = c.s1 - c.s0;
         A.pkt_base = c.p0;
         A.lay = L;
-        A.recs = e->recs.as<ElemRec>() + recs_per_lane * lane;
-        A.scratch = e->scratch.as<uint32_t>() + slab_words_per_lane * lane;
+        A.recs = e->recs.as<ElemRec>() + recs_per_slot * slot;
+        A.scratch = e->scratch.as<uint32_t>() + slab_words_per_slot * slot;
         A.cap_words = cap_words;
         A.state = d_state;
         JobLists Q;
-        Q.max_jobs = (uint32_t)jobs_per_lane;
-        Q.jobs = split ? e->jobs.as<FinalJob>() + 2 * jobs_per_lane * lane : nullptr;
+        Q.max_jobs = (uint32_t)jobs_per_slot;
+        Q.jobs = split ? e->jobs.as<FinalJob>() + 2 * jobs_per_slot * slot : nullptr;
         Q.counts = split ? e->job_counts.as<uint32_t>() + 4 * ci : nullptr;
         t_search.push_back(e->timer());
         switch (cfg->bit_depth) {
@@ -637,47 +732,47 @@ extern "C" int32_t alac_b200_encode(alac_b200_engine *e, const alac_b200_enc_con
         t_search.push_back(e->timer());
         enc_size_kernel<<<(c.cnt + 255) / 256, 256, 0, cs>>>(A.recs, L, cfg->bit_depth, A.pkt_samples + c.p0, c.cnt,
                                                             e->sizes.as<uint32_t>() + c.p0, d_escapes);
+        e->launches++;
         // the scan continues from the previous chunk's total: wait for that chunk's scan
         if (multi && ci > 0) CU_CHECK(e, cudaStreamWaitEvent(cs, scan_done[ci - 1], 0));
-        scan_u32_to_u64_kernel<<<1, 1024, 0, cs>>>(e->sizes.as<uint32_t>() + c.p0, e->offsets.as<uint64_t>() + c.p0, c.cnt, d_max,
-                                                   ci == 0 ? 0 : 1, &e->h_totals[ci]);
+        launch_scan(e, cs, e->sizes.as<uint32_t>() + c.p0, e->offsets.as<uint64_t>() + c.p0, c.cnt, e->scan_tiles.as<uint64_t>() + tile_at,
+                    d_max, ci == 0 ? 0 : 1, &e->h_totals[ci]);
+        tile_at += scan_tiles_for(c.cnt);
         if (multi) scan_done.push_back(e->event_on(cs));
-        e->launches += 2;
-
-        AsmArgs B;
-        B.pcm = d_pcm;
-        B.pkt_frame = A.pkt_frame;
-        B.pkt_samples = A.pkt_samples;
-        B.recs = A.recs;
-        B.scratch = A.scratch;
-        B.cap_words = cap_words;
-        B.sizes = e->sizes.as<uint32_t>();
-        B.offsets = e->offsets.as<uint64_t>();
-        B.out = d_out;
-        B.pkt_base = c.p0;
-        B.num_packets = c.cnt;
-        B.lay = L;
-        t_asm.push_back(e->timer());
-        switch (cfg->bit_depth) {
-        case 16: launch_assemble<16>(e, B); break;
-        case 20: launch_assemble<20>(e, B); break;
-        case 24: launch_assemble<24>(e, B); break;
-        default: launch_assemble<32>(e, B); break;
+        if (!pl) {
+            assemble_chunk(ci, cs);
+            // running byte total after this chunk -> pinned host word; the host needs it to size the chunk's D2H
+            comp_done.push_back(e->event_on(cs));
         }
-        t_asm.push_back(e->timer());
-        // running byte total after this chunk -> pinned host word; the host needs it to size the chunk's D2H
-        comp_done.push_back(e->event_on(cs));
+    }
+    if (pl) {
+        // ---- the cross-GPU step: publish this rank's byte total, wait (on the device) for the ranks in front, then
+        //      every chunk's packets go straight to their final place in the destination GPU's buffer
+        if (multi) for (cudaEvent_t ev : scan_done) CU_CHECK(e, cudaStreamWaitEvent(st, ev, 0));
+        Exchange *x = static_cast<Exchange *>(pl->exchange);
+        xchg_publish_resolve_kernel<<<1, 32, 0, st>>>(x, pl->rank, pl->epoch, e->offsets.as<uint64_t>() + P, d_base, d_xerr);
+        e->launches++;
+        for (size_t ci = 0; ci < chunks.size(); ci++) assemble_chunk(ci, st);
+        if (pl->dst_sizes && P)
+            CU_CHECK(e, cudaMemcpyAsync(pl->dst_sizes + pl->first_packet, e->sizes.p, (size_t)P * 4, cudaMemcpyDefault, st));
+        xchg_done_kernel<<<1, 1, 0, st>>>(x, pl->rank, pl->epoch);
+        e->launches++;
+        if (pl->rank == pl->home_rank) {
+            xchg_wait_all_kernel<<<1, 32, 0, st>>>(x, pl->n_ranks, pl->epoch, d_job_total, d_xerr);
+            e->launches++;
+        }
+        comp_done.push_back(e->event_on(st));
     }
     e->cur = nullptr;
     CU_CHECK(e, cudaGetLastError());
-    if (multi) for (cudaEvent_t ev : comp_done) CU_CHECK(e, cudaStreamWaitEvent(st, ev, 0));     // join the lanes
+    if (multi && !pl) for (cudaEvent_t ev : comp_done) CU_CHECK(e, cudaStreamWaitEvent(st, ev, 0));     // join the lanes
     CU_CHECK(e, cudaEventRecord(e->ev[2], st));
 
     // ---- results (copy-out stream) ----
-    unsigned long long h_counters[2] = {0, 0};
     uint64_t total = 0, copied = 0;
-    for (size_t ci = 0; ci < chunks.size(); ci++) {
+    for (size_t ci = 0; ci < comp_done.size(); ci++) {
         CU_CHECK(e, cudaEventSynchronize(comp_done[ci]));       // all later GPU work is already queued
+        if (pl) break;
         total = e->h_totals[ci];
         if (out_host && total > copied) {
             CU_CHECK(e, cudaMemcpyAsync(static_cast<uint8_t *>(packets_out) + copied, d_out + copied, (size_t)(total - copied),
@@ -685,16 +780,24 @@ extern "C" int32_t alac_b200_encode(alac_b200_engine *e, const alac_b200_enc_con
             copied = total;
         }
     }
-    CU_CHECK(e, cudaMemcpyAsync(packet_sizes, e->sizes.p, (size_t)P * 4, out_host ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice, e->copy_out));
-    CU_CHECK(e, cudaMemcpyAsync(h_counters, e->counters.p, 16, cudaMemcpyDeviceToHost, e->copy_out));
+    if (pl && !chunks.empty()) total = e->h_totals[chunks.size() - 1];
+    if (P) CU_CHECK(e, cudaMemcpyAsync(packet_sizes, e->sizes.p, (size_t)P * 4, sizes_host ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice, e->copy_out));
+    CU_CHECK(e, cudaMemcpyAsync(h_counters, e->counters.p, 32, cudaMemcpyDeviceToHost, e->copy_out));
+    if (pl) CU_CHECK(e, cudaMemcpyAsync(h_place, d_base, 16, cudaMemcpyDeviceToHost, e->copy_out));
     if (coef_state) {
         CU_CHECK(e, cudaMemcpyAsync(coef_state, e->state.p, (size_t)n_streams * ALAC_B200_STATE_INT16S * 2, cudaMemcpyDeviceToHost, e->copy_out));
     }
     CU_CHECK(e, cudaEventRecord(e->ev[3], e->copy_out));
     CU_CHECK(e, cudaStreamSynchronize(e->copy_out));
     CU_CHECK(e, cudaStreamSynchronize(st));
+    guard.armed = false;
+    if (pl) {
+        if (h_counters[2] & 0xffffffffull) { e->err = "cross-GPU exchange timed out (a rank of the job did not arrive)"; return ALAC_B200_CUDA_ERROR; }
+        if (h_place[0] + total > pl->dst_capacity) { e->err = "dst_packets capacity exceeded"; return ALAC_B200_PARAM_ERROR; }
+        if (out_base) *out_base = h_place[0];
+    }
 
-    if (getenv("ALAC_B200_TRACE")) {        // developer aid: per-chunk timeline in ms since the call started
+    if (getenv("ALAC_B200_TRACE") && !pl) {        // developer aid: per-chunk timeline in ms since the call started
         for (size_t ci = 0; ci < chunks.size(); ci++) {
             float a = 0, b = 0, c = 0, d = 0;
             if (in_host) cudaEventElapsedTime(&a, e->ev[0], h2d_done[ci]);
@@ -713,7 +816,7 @@ extern "C" int32_t alac_b200_encode(alac_b200_engine *e, const alac_b200_enc_con
         stats->kernel_launches = e->launches;
         // with host buffers the three phases overlap: h2d = start .. last PCM chunk landed, kernels = first .. last
         // kernel, d2h = last kernel .. last byte on the host
-        if (in_host) cudaEventElapsedTime(&stats->ms_h2d, e->ev[0], h2d_done.back());
+        if (in_host && !h2d_done.empty()) cudaEventElapsedTime(&stats->ms_h2d, e->ev[0], h2d_done.back());
         else cudaEventElapsedTime(&stats->ms_h2d, e->ev[0], e->ev[1]);
         cudaEventElapsedTime(&stats->ms_kernels, e->ev[1], e->ev[2]);
         cudaEventElapsedTime(&stats->ms_d2h, e->ev[2], e->ev[3]);
@@ -721,7 +824,250 @@ extern "C" int32_t alac_b200_encode(alac_b200_engine *e, const alac_b200_enc_con
         for (size_t i = 0; i + 1 < t_asm.size(); i += 2) { float ms = 0; cudaEventElapsedTime(&ms, t_asm[i], t_asm[i + 1]); stats->ms_assemble += ms; }
         for (size_t i = 0; i + 2 < e->t_mid.size(); i += 3) { float ms = 0; cudaEventElapsedTime(&ms, e->t_mid[i + 1], e->t_mid[i + 2]); stats->ms_final += ms; }
         stats->ms_search -= stats->ms_final;
+        if (pl) stats->payload_bytes = total;
     }
+    return ALAC_B200_OK;
+}
+
+// ---- several GPUs in one process -------------------------------------------------------------------------------
+struct Shard {
+    std::vector<alac_b200_stream> streams;
+    uint64_t first_packet = 0, packets = 0, first_stream = 0;
+    int32_t rc = 0;
+    uint64_t np = 0, bytes = 0, base = 0, frames = 0;
+    alac_b200_stats st;
+};
+
+// Contiguous frame ranges, cut at multiples of frames_per_segment packets (whole streams when a stream is one chain)
+static std::vector<Shard> plan_encode_shards(const alac_b200_enc_config *cfg, const alac_b200_stream *streams, uint64_t n_streams,
+                                             uint32_t n_dev, bool whole_streams)
+{
+    const uint64_t F = cfg->frame_size, K = cfg->frames_per_segment;
+    uint64_t P = 0;
+    for (uint64_t s = 0; s < n_streams; s++) P += (streams[s].num_sample_frames + F - 1) / F;
+    const uint64_t per_dev = std::max<uint64_t>(1, (P + n_dev - 1) / n_dev);
+    std::vector<Shard> sh(n_dev);
+    std::vector<bool> seen(n_dev, false);
+    uint64_t cum = 0;
+    for (uint64_t s = 0; s < n_streams; s++) {
+        const uint64_t ps = (streams[s].num_sample_frames + F - 1) / F;
+        for (uint64_t p = 0; p < ps;) {
+            const uint32_t d = (uint32_t)std::min<uint64_t>(n_dev - 1, cum / per_dev);
+            const uint64_t room = (uint64_t)(d + 1) * per_dev - cum;
+            uint64_t take = ps - p;
+            if (!whole_streams && K && d + 1 < n_dev) take = std::min<uint64_t>(take, (room + K - 1) / K * K);
+            if (!seen[d]) { seen[d] = true; sh[d].first_packet = cum; sh[d].first_stream = s; }
+            alac_b200_stream piece;
+            piece.first_sample_frame = streams[s].first_sample_frame + p * F;
+            piece.num_sample_frames = std::min<uint64_t>(take * F, streams[s].num_sample_frames - p * F);
+            sh[d].streams.push_back(piece);
+            sh[d].packets += take;
+            cum += take;
+            p += take;
+        }
+    }
+    while (!sh.empty() && sh.back().packets == 0) sh.pop_back();        // devices without work take no part
+    return sh;
+}
+
+static void merge_stats(alac_b200_stats *dst, const alac_b200_stats &s)
+{
+    dst->num_packets += s.num_packets;
+    dst->payload_bytes += s.payload_bytes;
+    dst->escape_elements += s.escape_elements;
+    dst->max_packet_bytes = std::max(dst->max_packet_bytes, s.max_packet_bytes);
+    dst->kernel_launches += s.kernel_launches;
+    float *a = &dst->ms_h2d;
+    const float *b = &s.ms_h2d;
+    for (int i = 0; i < 10; i++) a[i] = std::max(a[i], b[i]);         // the ten ms_* fields: slowest device
+}
+
+static int32_t multi_encode(alac_b200_engine *e, const alac_b200_enc_config *cfg, const void *pcm, uint64_t num_sample_frames,
+                            int32_t pcm_mem, const alac_b200_stream *streams, uint64_t n_streams, void *packets_out,
+                            uint64_t packets_cap, uint32_t *packet_sizes, uint64_t sizes_cap, int32_t out_mem, int16_t *coef_state,
+                            uint64_t *out_num_packets, uint64_t *out_bytes, alac_b200_stats *stats)
+{
+    e->err.clear();
+    if (!valid_cfg(cfg) || (!pcm && num_sample_frames) || !packets_out || !packet_sizes) return ALAC_B200_PARAM_ERROR;
+    if (out_num_packets) *out_num_packets = 0;
+    if (out_bytes) *out_bytes = 0;
+    if (stats) memset(stats, 0, sizeof(*stats));
+    alac_b200_stream whole = {0, num_sample_frames};
+    if (!streams) { streams = &whole; n_streams = 1; }
+    for (uint64_t s = 0; s < n_streams; s++)
+        if (streams[s].first_sample_frame > num_sample_frames || streams[s].num_sample_frames > num_sample_frames - streams[s].first_sample_frame)
+            return ALAC_B200_PARAM_ERROR;
+    const bool whole_streams = cfg->frames_per_segment == 0 || coef_state != nullptr;
+    std::vector<Shard> sh = plan_encode_shards(cfg, streams, n_streams, (uint32_t)e->subs.size(), whole_streams);
+    uint64_t P = 0, sample_sum = 0;
+    for (const Shard &h : sh) P += h.packets;
+    for (uint64_t s = 0; s < n_streams; s++) sample_sum += streams[s].num_sample_frames;
+    if (P > sizes_cap) return ALAC_B200_PARAM_ERROR;
+    const uint64_t bpf = (uint64_t)bytes_per_sample(cfg->bit_depth) * cfg->channels;
+    if (packets_cap < sample_sum * bpf + P * (7ull * cfg->channels + 1ull)) { e->err = "packets_out capacity below the worst case of this packet table"; return ALAC_B200_PARAM_ERROR; }
+    if (P == 0) return ALAC_B200_OK;
+    const bool out_dev = out_mem == ALAC_B200_MEM_DEVICE && coef_state == nullptr;    // (a state hand-off takes the block-copy form)
+    const uint32_t epoch = ++e->epoch;
+    const uint32_t m = (uint32_t)sh.size();
+    // device output: every GPU's assemble kernel stores straight into packets_out (home device) at its final offset;
+    // host output: every GPU keeps its block, the blocks go down over each GPU's own PCIe link once the totals are known
+    std::vector<std::thread> th;
+    for (uint32_t d = 0; d < m; d++) {
+        th.emplace_back([&, d] {
+            alac_b200_engine *se = e->subs[d];
+            Shard &h = sh[d];
+            memset(&h.st, 0, sizeof(h.st));
+            int16_t *state_d = coef_state ? coef_state + h.first_stream * ALAC_B200_STATE_INT16S : nullptr;
+            if (out_dev) {
+                alac_b200_placement pl;
+                pl.dst_packets = packets_out; pl.dst_capacity = packets_cap; pl.dst_sizes = nullptr; pl.first_packet = h.first_packet;
+                pl.exchange = e->xchg.p; pl.rank = d; pl.n_ranks = m; pl.home_rank = 0; pl.epoch = epoch;
+                h.rc = encode_core(se, cfg, pcm, num_sample_frames, pcm_mem, h.streams.data(), h.streams.size(), nullptr, 0,
+                                   packet_sizes + h.first_packet, h.packets, ALAC_B200_MEM_DEVICE, nullptr, &h.np, &h.bytes, &h.st, &pl, &h.base);
+            } else {
+                uint64_t need = 0;
+                for (const alac_b200_stream &q : h.streams) need += q.num_sample_frames;
+                need = need * bpf + h.packets * (7ull * cfg->channels + 1ull);
+                cudaSetDevice(se->device);
+                if (se->m_out.reserve((size_t)need + 64) != cudaSuccess || se->m_sizes.reserve((size_t)h.packets * 4 + 4) != cudaSuccess) { h.rc = ALAC_B200_MEM_ERROR; return; }
+                h.rc = encode_core(se, cfg, pcm, num_sample_frames, pcm_mem, h.streams.data(), h.streams.size(), se->m_out.p, need,
+                                   se->m_sizes.as<uint32_t>(), h.packets, ALAC_B200_MEM_DEVICE, state_d, &h.np, &h.bytes, &h.st, nullptr, nullptr);
+            }
+        });
+    }
+    for (auto &t : th) t.join();
+    int32_t rc = 0;
+    for (uint32_t d = 0; d < m && !rc; d++)
+        if (sh[d].rc) { rc = sh[d].rc; e->err = "device " + std::to_string(e->subs[d]->device) + ": " + e->subs[d]->err; }
+    uint64_t total = 0;
+    if (!rc && !out_dev) {
+        for (uint32_t d = 0; d < m; d++) {
+            alac_b200_engine *se = e->subs[d];
+            cudaSetDevice(se->device);
+            if (cudaMemcpyAsync(static_cast<uint8_t *>(packets_out) + total, se->m_out.p, (size_t)sh[d].bytes, cudaMemcpyDefault, se->stream) != cudaSuccess ||
+                cudaMemcpyAsync(packet_sizes + sh[d].first_packet, se->m_sizes.p, (size_t)sh[d].packets * 4, cudaMemcpyDefault, se->stream) != cudaSuccess)
+                rc = ALAC_B200_CUDA_ERROR;
+            total += sh[d].bytes;
+        }
+        for (uint32_t d = 0; d < m; d++) { cudaSetDevice(e->subs[d]->device); if (cudaStreamSynchronize(e->subs[d]->stream) != cudaSuccess) rc = ALAC_B200_CUDA_ERROR; }
+    } else {
+        for (uint32_t d = 0; d < m; d++) total += sh[d].bytes;
+    }
+    cudaSetDevice(e->device);
+    if (rc) return rc;
+    if (out_num_packets) *out_num_packets = P;
+    if (out_bytes) *out_bytes = total;
+    if (stats) for (uint32_t d = 0; d < m; d++) merge_stats(stats, sh[d].st);
+    return ALAC_B200_OK;
+}
+
+extern "C" int32_t alac_b200_encode(alac_b200_engine *e, const alac_b200_enc_config *cfg, const void *pcm,
+                                    uint64_t num_sample_frames, int32_t pcm_mem, const alac_b200_stream *streams,
+                                    uint64_t n_streams, void *packets_out, uint64_t packets_cap, uint32_t *packet_sizes,
+                                    uint64_t sizes_cap, int32_t out_mem, int16_t *coef_state, uint64_t *out_num_packets,
+                                    uint64_t *out_bytes, alac_b200_stats *stats)
+{
+    if (!e) return ALAC_B200_PARAM_ERROR;
+    if (e->subs.size() > 1)
+        return multi_encode(e, cfg, pcm, num_sample_frames, pcm_mem, streams, n_streams, packets_out, packets_cap, packet_sizes, sizes_cap,
+                            out_mem, coef_state, out_num_packets, out_bytes, stats);
+    return encode_core(e, cfg, pcm, num_sample_frames, pcm_mem, streams, n_streams, packets_out, packets_cap, packet_sizes, sizes_cap,
+                       out_mem, coef_state, out_num_packets, out_bytes, stats, nullptr, nullptr);
+}
+
+extern "C" int32_t alac_b200_encode_placed(alac_b200_engine *e, const alac_b200_enc_config *cfg, const void *pcm,
+                                           uint64_t num_sample_frames, int32_t pcm_mem, const alac_b200_stream *streams,
+                                           uint64_t n_streams, const alac_b200_placement *placement, uint32_t *packet_sizes,
+                                           uint64_t sizes_cap, int32_t out_mem, uint64_t *out_num_packets, uint64_t *out_bytes,
+                                           uint64_t *out_base, alac_b200_stats *stats)
+{
+    if (!e || !placement || e->subs.size() > 1) return ALAC_B200_PARAM_ERROR;
+    return encode_core(e, cfg, pcm, num_sample_frames, pcm_mem, streams, n_streams, nullptr, 0, packet_sizes, sizes_cap, out_mem, nullptr,
+                       out_num_packets, out_bytes, stats, placement, out_base);
+}
+
+extern "C" int32_t alac_b200_engine_create_multi(const int32_t *devices, uint32_t n_devices, alac_b200_engine **out_engine)
+{
+    if (!out_engine) return ALAC_B200_PARAM_ERROR;
+    *out_engine = nullptr;
+    if (!devices || n_devices == 0 || n_devices > ALAC_B200_MAX_RANKS) return ALAC_B200_PARAM_ERROR;
+    for (uint32_t i = 0; i < n_devices; i++)
+        for (uint32_t j = 0; j < i; j++)
+            if (devices[i] == devices[j] || devices[i] < 0) return ALAC_B200_PARAM_ERROR;
+    alac_b200_engine *home = nullptr;
+    int32_t rc = alac_b200_engine_create(devices[0], &home);
+    if (rc) return rc;
+    home->subs.push_back(home);
+    for (uint32_t i = 1; i < n_devices && !rc; i++) {
+        alac_b200_engine *se = nullptr;
+        rc = alac_b200_engine_create(devices[i], &se);
+        if (!rc) home->subs.push_back(se);
+    }
+    // peer access between every pair: kernels of any device store into the home device's buffers (and may read PCM
+    // that lives on another device)
+    for (uint32_t i = 0; i < n_devices && !rc; i++) {
+        for (uint32_t j = 0; j < n_devices && !rc; j++) {
+            if (i == j) continue;
+            int can = 0;
+            if (cudaDeviceCanAccessPeer(&can, devices[i], devices[j]) != cudaSuccess || !can) { rc = ALAC_B200_UNIMPLEMENTED; break; }
+            cudaSetDevice(devices[i]);
+            const cudaError_t pe = cudaDeviceEnablePeerAccess(devices[j], 0);
+            if (pe != cudaSuccess && pe != cudaErrorPeerAccessAlreadyEnabled) rc = ALAC_B200_CUDA_ERROR;
+            cudaGetLastError();
+        }
+    }
+    cudaSetDevice(devices[0]);
+    if (!rc && (home->xchg.reserve(ALAC_B200_EXCHANGE_BYTES) != cudaSuccess ||
+                cudaMemset(home->xchg.p, 0, ALAC_B200_EXCHANGE_BYTES) != cudaSuccess))
+        rc = ALAC_B200_CUDA_ERROR;
+    if (rc) { alac_b200_engine_destroy(home); return rc; }
+    *out_engine = home;
+    return ALAC_B200_OK;
+}
+
+extern "C" uint32_t alac_b200_engine_num_devices(const alac_b200_engine *e) { return e ? (uint32_t)std::max<size_t>(1, e->subs.size()) : 0u; }
+
+// plain cudaMalloc memory (exportable with cudaIpcGetMemHandle) and the IPC wrappers of a one-process-per-GPU launcher
+extern "C" int32_t alac_b200_device_alloc(alac_b200_engine *e, uint64_t bytes, void **out_ptr)
+{
+    if (!e || !out_ptr) return ALAC_B200_PARAM_ERROR;
+    *out_ptr = nullptr;
+    CU_CHECK(e, cudaSetDevice(e->device));
+    CU_CHECK(e, cudaMalloc(out_ptr, (size_t)std::max<uint64_t>(bytes, 1)));
+    return ALAC_B200_OK;
+}
+extern "C" int32_t alac_b200_device_free(alac_b200_engine *e, void *ptr)
+{
+    if (!e) return ALAC_B200_PARAM_ERROR;
+    CU_CHECK(e, cudaSetDevice(e->device));
+    CU_CHECK(e, cudaFree(ptr));
+    return ALAC_B200_OK;
+}
+extern "C" int32_t alac_b200_ipc_export(alac_b200_engine *e, void *ptr, void *out_handle64)
+{
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "handle size is part of the ABI");
+    if (!e || !ptr || !out_handle64) return ALAC_B200_PARAM_ERROR;
+    CU_CHECK(e, cudaSetDevice(e->device));
+    cudaIpcMemHandle_t h;
+    CU_CHECK(e, cudaIpcGetMemHandle(&h, ptr));
+    memcpy(out_handle64, &h, 64);
+    return ALAC_B200_OK;
+}
+extern "C" int32_t alac_b200_ipc_open(alac_b200_engine *e, const void *handle64, void **out_ptr)
+{
+    if (!e || !handle64 || !out_ptr) return ALAC_B200_PARAM_ERROR;
+    *out_ptr = nullptr;
+    CU_CHECK(e, cudaSetDevice(e->device));
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle64, 64);
+    CU_CHECK(e, cudaIpcOpenMemHandle(out_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    return ALAC_B200_OK;
+}
+extern "C" int32_t alac_b200_ipc_close(alac_b200_engine *e, void *ptr)
+{
+    if (!e || !ptr) return ALAC_B200_PARAM_ERROR;
+    CU_CHECK(e, cudaSetDevice(e->device));
+    CU_CHECK(e, cudaIpcCloseMemHandle(ptr));
     return ALAC_B200_OK;
 }
 
@@ -745,10 +1091,10 @@ static void configure_decode_kernels()
     prefer_max_shared(dec_entropy_kernel<24>); prefer_max_shared(dec_entropy_kernel<32>);
 }
 
-extern "C" int32_t alac_b200_decode(alac_b200_engine *e, const void *cookie, uint32_t cookie_size, const void *packets,
-                                    const uint32_t *packet_sizes, uint64_t num_packets, int32_t in_mem, void *pcm_out,
-                                    uint64_t pcm_cap, uint32_t *packet_samples, int32_t *packet_status, int32_t out_mem,
-                                    uint64_t *out_sample_frames, alac_b200_stats *stats)
+static int32_t decode_core(alac_b200_engine *e, const void *cookie, uint32_t cookie_size, const void *packets,
+                           const uint32_t *packet_sizes, uint64_t num_packets, int32_t in_mem, void *pcm_out,
+                           uint64_t pcm_cap, uint32_t *packet_samples, int32_t *packet_status, int32_t out_mem,
+                           uint64_t *out_sample_frames, alac_b200_stats *stats)
 {
     if (!e) return ALAC_B200_PARAM_ERROR;
     e->err.clear();
@@ -796,7 +1142,7 @@ extern "C" int32_t alac_b200_decode(alac_b200_engine *e, const void *cookie, uin
     for (const Chunk &c : chunks) max_cnt = std::max(max_cnt, c.cnt);
     const uint32_t groups = (max_cnt + 31) / 32;
     const bool multi = out_host;                        // chunks run on several compute streams
-    const uint32_t nlanes = multi ? 8u : 1u;
+    const uint32_t nlanes = multi ? (uint32_t)std::min<size_t>(8, chunks.size()) : 1u;     // never more scratch slots than chunks
     const size_t chan_words_per_lane = (size_t)groups * 32 * nch * frame_length;
 
     CU_CHECK(e, e->d_pkt_off.reserve(((size_t)P + 1) * 8));
@@ -810,7 +1156,10 @@ extern "C" int32_t alac_b200_decode(alac_b200_engine *e, const void *cookie, uin
     CU_CHECK(e, e->d_meta.reserve((size_t)P * nch * sizeof(DecChanMeta)));
     CU_CHECK(e, e->d_hdr.reserve((size_t)P * nch * sizeof(DecChanHdr)));
     CU_CHECK(e, e->counters.reserve(64 * chunks.size()));
+    CU_CHECK(e, e->scan_tiles.reserve((2 * scan_tiles_for(P) + chunks.size() + 2) * 8));
 
+    std::vector<int32_t> h_status(P);                   // (written by the copy-out stream: declared before the guard)
+    DrainGuard guard(e);
     CU_CHECK(e, cudaEventRecord(e->ev[0], st));
     const uint32_t *d_sizes;
     const uint8_t *d_packets;
@@ -843,8 +1192,8 @@ extern "C" int32_t alac_b200_decode(alac_b200_engine *e, const void *cookie, uin
     }
     CU_CHECK(e, cudaMemsetAsync(e->counters.p, 0, 64 * chunks.size(), st));     // class counters of every chunk
     // byte offsets of all packets at once (the sizes are all known up front)
-    scan_u32_to_u64_kernel<<<1, 1024, 0, st>>>(d_sizes, e->d_pkt_off.as<uint64_t>(), P, nullptr, 0);
-    e->launches += 1;
+    launch_scan(e, st, d_sizes, e->d_pkt_off.as<uint64_t>(), P, e->scan_tiles.as<uint64_t>(), nullptr, 0, nullptr);
+    size_t tile_at = scan_tiles_for(P);
     CU_CHECK(e, cudaEventRecord(e->ev[1], st));
 
     DecArgs A;
@@ -885,11 +1234,14 @@ extern "C" int32_t alac_b200_decode(alac_b200_engine *e, const void *cookie, uin
         dec_perm_kernel<<<(c.cnt + 127) / 128, 128, 0, cs>>>(A);
         // output positions continue from the previous chunk's total
         if (multi && ci > 0) CU_CHECK(e, cudaStreamWaitEvent(cs, scan_done[ci - 1], 0));
-        scan_u32_to_u64_kernel<<<1, 1024, 0, cs>>>(A.pkt_samples + c.p0, e->d_out_frame.as<uint64_t>() + c.p0, c.cnt, nullptr, ci == 0 ? 0 : 1, &e->h_totals[ci]);
+        launch_scan(e, cs, A.pkt_samples + c.p0, e->d_out_frame.as<uint64_t>() + c.p0, c.cnt, e->scan_tiles.as<uint64_t>() + tile_at, nullptr,
+                    ci == 0 ? 0 : 1, &e->h_totals[ci]);
+        tile_at += scan_tiles_for(c.cnt);
         if (multi) scan_done.push_back(e->event_on(cs));
-        e->launches += 3;
-        if (!out_host) {
-            // a caller-owned device buffer: its capacity must be known to hold before anything is written
+        e->launches += 2;
+        if (!out_host && (uint64_t)P * frame_length * bpf > pcm_cap) {
+            // a caller-owned device buffer that could not hold P full packets: the sample counts must be known to fit
+            // before anything is written (a buffer sized for full packets needs no check and no host round trip)
             CU_CHECK(e, cudaStreamSynchronize(cs));
             if (e->h_totals[ci] * bpf > pcm_cap) { e->err = "pcm capacity exceeded"; return ALAC_B200_PARAM_ERROR; }
         }
@@ -952,7 +1304,6 @@ extern "C" int32_t alac_b200_decode(alac_b200_engine *e, const void *cookie, uin
             }
         }
     }
-    std::vector<int32_t> h_status(P);
     CU_CHECK(e, cudaMemcpyAsync(h_status.data(), A.pkt_status, (size_t)P * 4, cudaMemcpyDeviceToHost, e->copy_out));
     const cudaMemcpyKind to_user = out_host ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice;
     if (packet_samples) CU_CHECK(e, cudaMemcpyAsync(packet_samples, A.pkt_samples, (size_t)P * 4, to_user, e->copy_out));
@@ -960,6 +1311,7 @@ extern "C" int32_t alac_b200_decode(alac_b200_engine *e, const void *cookie, uin
     CU_CHECK(e, cudaEventRecord(e->ev[3], e->copy_out));
     CU_CHECK(e, cudaStreamSynchronize(e->copy_out));
     CU_CHECK(e, cudaStreamSynchronize(st));
+    guard.armed = false;
     if (overflow) { e->err = "pcm capacity exceeded"; return ALAC_B200_PARAM_ERROR; }
 
     if (getenv("ALAC_B200_TRACE")) {        // developer aid: per-chunk timeline in ms since the call started
@@ -997,6 +1349,114 @@ extern "C" int32_t alac_b200_decode(alac_b200_engine *e, const void *cookie, uin
     return first_err;
 }
 
+// several GPUs: contiguous packet ranges; every GPU decodes its range into its own memory, then the blocks go to their
+// place in pcm_out (per-packet sample counts are data: the offsets are only known once every range is decoded)
+static int32_t multi_decode(alac_b200_engine *e, const void *cookie, uint32_t cookie_size, const void *packets,
+                            const uint32_t *packet_sizes, uint64_t num_packets, int32_t in_mem, void *pcm_out, uint64_t pcm_cap,
+                            uint32_t *packet_samples, int32_t *packet_status, int32_t out_mem, uint64_t *out_sample_frames,
+                            alac_b200_stats *stats)
+{
+    e->err.clear();
+    if (out_sample_frames) *out_sample_frames = 0;
+    if (stats) memset(stats, 0, sizeof(*stats));
+    uint32_t f[11];
+    int32_t rc = alac_b200_parse_cookie(cookie, cookie_size, f);
+    if (rc) return rc;
+    const uint32_t frame_length = f[0], depth = f[2], nch = f[6];
+    if (!valid_depth(depth) || nch == 0 || frame_length == 0 || num_packets > 0x3fffffffull) return ALAC_B200_PARAM_ERROR;
+    if ((!packets || !packet_sizes || !pcm_out) && num_packets) return ALAC_B200_PARAM_ERROR;
+    if (num_packets == 0) return ALAC_B200_OK;
+    const uint64_t bpf = (uint64_t)bytes_per_sample(depth) * nch;
+    // byte offsets of the shard boundaries need the sizes on the host
+    std::vector<uint32_t> h_sizes;
+    const uint32_t *hs = packet_sizes;
+    if (in_mem == ALAC_B200_MEM_DEVICE) {
+        h_sizes.resize((size_t)num_packets);
+        cudaSetDevice(e->device);
+        if (cudaMemcpy(h_sizes.data(), packet_sizes, (size_t)num_packets * 4, cudaMemcpyDeviceToHost) != cudaSuccess) return ALAC_B200_CUDA_ERROR;
+        hs = h_sizes.data();
+    }
+    const uint32_t n_dev = (uint32_t)e->subs.size();
+    const uint64_t per_dev = (num_packets + n_dev - 1) / n_dev;
+    std::vector<Shard> sh;
+    uint64_t at = 0, byte_at = 0;
+    std::vector<uint64_t> byte_off;
+    for (uint32_t d = 0; d < n_dev && at < num_packets; d++) {
+        Shard h;
+        h.first_packet = at;
+        h.packets = std::min<uint64_t>(per_dev, num_packets - at);
+        byte_off.push_back(byte_at);
+        for (uint64_t i = at; i < at + h.packets; i++) byte_at += hs[i];
+        at += h.packets;
+        sh.push_back(h);
+    }
+    const uint32_t m = (uint32_t)sh.size();
+    std::vector<std::thread> th;
+    for (uint32_t d = 0; d < m; d++) {
+        th.emplace_back([&, d] {
+            alac_b200_engine *se = e->subs[d];
+            Shard &h = sh[d];
+            memset(&h.st, 0, sizeof(h.st));
+            cudaSetDevice(se->device);
+            const uint64_t cap = h.packets * frame_length * bpf;
+            if (se->m_out.reserve((size_t)cap + 64) != cudaSuccess || se->m_aux.reserve((size_t)h.packets * 8 + 8) != cudaSuccess) { h.rc = ALAC_B200_MEM_ERROR; return; }
+            uint32_t *d_samples = se->m_aux.as<uint32_t>();
+            int32_t *d_status = reinterpret_cast<int32_t *>(d_samples + h.packets);
+            const uint32_t *sizes_d = packet_sizes + h.first_packet;
+            if (in_mem != ALAC_B200_MEM_DEVICE) {
+                // host input: decode_core stages packets and sizes itself
+                h.rc = decode_core(se, cookie, cookie_size, static_cast<const uint8_t *>(packets) + byte_off[d], sizes_d, h.packets, ALAC_B200_MEM_HOST,
+                                   se->m_out.p, cap, d_samples, d_status, ALAC_B200_MEM_DEVICE, &h.frames, &h.st);
+            } else {
+                h.rc = decode_core(se, cookie, cookie_size, static_cast<const uint8_t *>(packets) + byte_off[d], sizes_d, h.packets, ALAC_B200_MEM_DEVICE,
+                                   se->m_out.p, cap, d_samples, d_status, ALAC_B200_MEM_DEVICE, &h.frames, &h.st);
+            }
+        });
+    }
+    for (auto &t : th) t.join();
+    int32_t first_err = 0;
+    for (uint32_t d = 0; d < m; d++) {
+        // a packet status (kALAC_ParamError) is a result, not a failure of the call: the blocks are still delivered
+        if (sh[d].rc && sh[d].rc != ALAC_B200_PARAM_ERROR) { cudaSetDevice(e->device); e->err = "device " + std::to_string(e->subs[d]->device) + ": " + e->subs[d]->err; return sh[d].rc; }
+        if (sh[d].rc && !e->subs[d]->err.empty()) { cudaSetDevice(e->device); e->err = e->subs[d]->err; return sh[d].rc; }
+        if (sh[d].rc && !first_err) first_err = sh[d].rc;
+    }
+    uint64_t frames = 0;
+    bool overflow = false;
+    for (uint32_t d = 0; d < m; d++) {
+        alac_b200_engine *se = e->subs[d];
+        cudaSetDevice(se->device);
+        uint64_t nbytes = sh[d].frames * bpf;
+        if (frames * bpf + nbytes > pcm_cap) { overflow = true; nbytes = pcm_cap > frames * bpf ? pcm_cap - frames * bpf : 0; }
+        cudaError_t ce = cudaSuccess;
+        if (nbytes) ce = cudaMemcpyAsync(static_cast<uint8_t *>(pcm_out) + frames * bpf, se->m_out.p, (size_t)nbytes, cudaMemcpyDefault, se->stream);
+        uint32_t *d_samples = se->m_aux.as<uint32_t>();
+        if (ce == cudaSuccess && packet_samples) ce = cudaMemcpyAsync(packet_samples + sh[d].first_packet, d_samples, (size_t)sh[d].packets * 4, cudaMemcpyDefault, se->stream);
+        if (ce == cudaSuccess && packet_status) ce = cudaMemcpyAsync(packet_status + sh[d].first_packet, d_samples + sh[d].packets, (size_t)sh[d].packets * 4, cudaMemcpyDefault, se->stream);
+        if (ce != cudaSuccess) { cudaSetDevice(e->device); e->err = cudaGetErrorString(ce); return ALAC_B200_CUDA_ERROR; }
+        frames += sh[d].frames;
+    }
+    for (uint32_t d = 0; d < m; d++) { cudaSetDevice(e->subs[d]->device); cudaStreamSynchronize(e->subs[d]->stream); }
+    cudaSetDevice(e->device);
+    if (overflow) { e->err = "pcm capacity exceeded"; return ALAC_B200_PARAM_ERROR; }
+    if (out_sample_frames) *out_sample_frames = frames;
+    if (stats) { for (uint32_t d = 0; d < m; d++) merge_stats(stats, sh[d].st); stats->payload_bytes = frames * bpf; }
+    return first_err;
+}
+
+extern "C" int32_t alac_b200_decode(alac_b200_engine *e, const void *cookie, uint32_t cookie_size, const void *packets,
+                                    const uint32_t *packet_sizes, uint64_t num_packets, int32_t in_mem, void *pcm_out,
+                                    uint64_t pcm_cap, uint32_t *packet_samples, int32_t *packet_status, int32_t out_mem,
+                                    uint64_t *out_sample_frames, alac_b200_stats *stats)
+{
+    if (!e) return ALAC_B200_PARAM_ERROR;
+    if (e->subs.size() > 1)
+        return multi_decode(e, cookie, cookie_size, packets, packet_sizes, num_packets, in_mem, pcm_out, pcm_cap, packet_samples,
+                            packet_status, out_mem, out_sample_frames, stats);
+    return decode_core(e, cookie, cookie_size, packets, packet_sizes, num_packets, in_mem, pcm_out, pcm_cap, packet_samples,
+                       packet_status, out_mem, out_sample_frames, stats);
+}
+
 // ------------------------------------------------------------------------------------------------
 // CAF packet table -> packet sizes, on the device
 // ------------------------------------------------------------------------------------------------
@@ -1027,7 +1487,8 @@ extern "C" int32_t alac_b200_ber_table_sizes(alac_b200_engine *e, const void *ta
     CU_CHECK(e, e->counters.reserve(256));
     const uint32_t blocks = (uint32_t)((table_bytes + 255) / 256);
     ber_flag_kernel<<<blocks, 256, 0, st>>>(d_table, table_bytes, e->d_class.as<uint32_t>());
-    scan_u32_to_u64_kernel<<<1, 1024, 0, st>>>(e->d_class.as<uint32_t>(), e->d_pkt_off.as<uint64_t>(), table_bytes, nullptr, 0);
+    CU_CHECK(e, e->scan_tiles.reserve(2 * scan_tiles_for(table_bytes) * 8));
+    launch_scan(e, st, e->d_class.as<uint32_t>(), e->d_pkt_off.as<uint64_t>(), table_bytes, e->scan_tiles.as<uint64_t>(), nullptr, 0, nullptr);
     CU_CHECK(e, cudaMemsetAsync(e->d_sizes.p, 0, (size_t)table_bytes * 4, st));
     ber_value_kernel<<<blocks, 256, 0, st>>>(d_table, table_bytes, e->d_pkt_off.as<uint64_t>(), e->d_sizes.as<uint32_t>(), table_bytes);
     uint64_t entries = 0;
@@ -1038,7 +1499,7 @@ extern "C" int32_t alac_b200_ber_table_sizes(alac_b200_engine *e, const void *ta
         unsigned long long *d_first = e->counters.as<unsigned long long>() + 16;
         const unsigned long long init = entries;
         CU_CHECK(e, cudaMemcpyAsync(d_first, &init, 8, cudaMemcpyHostToDevice, st));
-        scan_u32_to_u64_kernel<<<1, 1024, 0, st>>>(e->d_sizes.as<uint32_t>(), e->d_out_frame.as<uint64_t>(), entries, nullptr, 0);
+        launch_scan(e, st, e->d_sizes.as<uint32_t>(), e->d_out_frame.as<uint64_t>(), entries, e->scan_tiles.as<uint64_t>() + scan_tiles_for(table_bytes), nullptr, 0, nullptr);
         ber_count_kernel<<<(uint32_t)((entries + 255) / 256), 256, 0, st>>>(e->d_sizes.as<uint32_t>(), e->d_out_frame.as<uint64_t>(), entries,
                                                                           data_bytes, d_first);
         unsigned long long first = 0;
@@ -1080,7 +1541,8 @@ extern "C" int32_t alac_b200_ber_table_build(alac_b200_engine *e, const uint32_t
     CU_CHECK(e, e->d_pkt_off.reserve(((size_t)num_packets + 1) * 8));         // entry offsets
     const uint32_t blocks = (uint32_t)((num_packets + 255) / 256);
     ber_len_kernel<<<blocks, 256, 0, st>>>(d_sizes, num_packets, e->d_class.as<uint32_t>());
-    scan_u32_to_u64_kernel<<<1, 1024, 0, st>>>(e->d_class.as<uint32_t>(), e->d_pkt_off.as<uint64_t>(), num_packets, nullptr, 0, &e->h_totals[0]);
+    CU_CHECK(e, e->scan_tiles.reserve(scan_tiles_for(num_packets) * 8));
+    launch_scan(e, st, e->d_class.as<uint32_t>(), e->d_pkt_off.as<uint64_t>(), num_packets, e->scan_tiles.as<uint64_t>(), nullptr, 0, &e->h_totals[0]);
     CU_CHECK(e, cudaStreamSynchronize(st));
     const uint64_t total = e->h_totals[0];
     if (total > table_cap) { e->err = "table capacity exceeded"; return ALAC_B200_PARAM_ERROR; }

@@ -58,6 +58,15 @@ class Stats(C.Structure):
         return {n: getattr(self, n) for n, _ in self._fields_}
 
 
+class Placement(C.Structure):
+    """alac_b200_placement (include/alac_b200.h): where one rank's packet block goes inside a job's single buffer."""
+    _fields_ = [("dst_packets", C.c_void_p), ("dst_capacity", C.c_uint64), ("dst_sizes", C.c_void_p),
+                ("first_packet", C.c_uint64), ("exchange", C.c_void_p), ("rank", C.c_uint32), ("n_ranks", C.c_uint32),
+                ("home_rank", C.c_uint32), ("epoch", C.c_uint32)]
+
+
+EXCHANGE_BYTES = 1024
+
 _lib = None
 
 
@@ -96,6 +105,23 @@ def load_library():
     lib.alac_b200_ber_table_sizes.restype = i32
     lib.alac_b200_ber_table_build.argtypes = [vp, vp, u64, i32, vp, u64, i32, C.POINTER(u64)]
     lib.alac_b200_ber_table_build.restype = i32
+    lib.alac_b200_engine_create_multi.argtypes = [C.POINTER(i32), u32, C.POINTER(vp)]
+    lib.alac_b200_engine_create_multi.restype = i32
+    lib.alac_b200_engine_num_devices.argtypes = [vp]
+    lib.alac_b200_engine_num_devices.restype = u32
+    lib.alac_b200_encode_placed.argtypes = [vp, C.POINTER(_EncConfig), vp, u64, i32, C.POINTER(_Stream), u64, C.POINTER(Placement),
+                                            vp, u64, i32, C.POINTER(u64), C.POINTER(u64), C.POINTER(u64), C.POINTER(Stats)]
+    lib.alac_b200_encode_placed.restype = i32
+    lib.alac_b200_device_alloc.argtypes = [vp, u64, C.POINTER(vp)]
+    lib.alac_b200_device_alloc.restype = i32
+    lib.alac_b200_device_free.argtypes = [vp, vp]
+    lib.alac_b200_device_free.restype = i32
+    lib.alac_b200_ipc_export.argtypes = [vp, vp, vp]
+    lib.alac_b200_ipc_export.restype = i32
+    lib.alac_b200_ipc_open.argtypes = [vp, vp, C.POINTER(vp)]
+    lib.alac_b200_ipc_open.restype = i32
+    lib.alac_b200_ipc_close.argtypes = [vp, vp]
+    lib.alac_b200_ipc_close.restype = i32
     _lib = lib
     return lib
 
@@ -150,8 +176,24 @@ def _is_torch(x) -> bool:
     return type(x).__module__.startswith("torch")
 
 
+class DevicePtr:
+    """A raw region of device memory (local, or another GPU's mapped by peer access / CUDA IPC): what a rank of a
+    multi-GPU job passes when the bytes live in the job's shared buffer.  The caller orders the work itself."""
+
+    def __init__(self, ptr: int, nbytes: int):
+        self.ptr, self.nbytes = int(ptr), int(nbytes)
+
+    def __getitem__(self, sl: slice) -> "DevicePtr":
+        a, b, step = sl.indices(self.nbytes)
+        if step != 1:
+            raise ValueError("contiguous slices only")
+        return DevicePtr(self.ptr + a, max(b - a, 0))
+
+
 def _buf(x) -> Tuple[int, int, int]:
-    """(pointer, nbytes, mem kind) of a numpy array or torch tensor."""
+    """(pointer, nbytes, mem kind) of a numpy array, torch tensor or DevicePtr."""
+    if isinstance(x, DevicePtr):
+        return x.ptr, x.nbytes, MEM_DEVICE
     if _is_torch(x):
         if not x.is_contiguous():
             raise ValueError("tensor must be contiguous")
@@ -185,13 +227,83 @@ class DecodeResult:
 class Engine:
     """One engine per GPU (owns a CUDA stream and its scratch)."""
 
-    def __init__(self, device: int = -1):
+    def __init__(self, device=-1):
+        """device: a CUDA device index (-1 = current), or a list of indices for one engine that shards every call
+        by frame range over several GPUs of this process (alac_b200_engine_create_multi; the first is the home device)."""
         self.lib = load_library()
         h = C.c_void_p()
-        st = self.lib.alac_b200_engine_create(device, C.byref(h))
+        if isinstance(device, (list, tuple)):
+            arr = (C.c_int32 * len(device))(*device)
+            st = self.lib.alac_b200_engine_create_multi(arr, len(device), C.byref(h))
+        else:
+            st = self.lib.alac_b200_engine_create(device, C.byref(h))
         if st:
             raise AlacError(st, "engine_create failed (no usable CUDA device?)")
         self.h = h
+
+    @property
+    def num_devices(self) -> int:
+        return int(self.lib.alac_b200_engine_num_devices(self.h))
+
+    # ------------------------------------------------------------------ shared device memory (one process per GPU)
+    def device_alloc(self, nbytes: int) -> int:
+        p = C.c_void_p()
+        st = self.lib.alac_b200_device_alloc(self.h, nbytes, C.byref(p))
+        if st:
+            raise AlacError(st, self._err())
+        return p.value
+
+    def device_free(self, ptr: int):
+        self.lib.alac_b200_device_free(self.h, C.c_void_p(ptr))
+
+    def ipc_export(self, ptr: int) -> bytes:
+        buf = (C.c_uint8 * 64)()
+        st = self.lib.alac_b200_ipc_export(self.h, C.c_void_p(ptr), buf)
+        if st:
+            raise AlacError(st, self._err())
+        return bytes(buf)
+
+    def ipc_open(self, handle: bytes) -> int:
+        buf = (C.c_uint8 * 64).from_buffer_copy(handle)
+        p = C.c_void_p()
+        st = self.lib.alac_b200_ipc_open(self.h, buf, C.byref(p))
+        if st:
+            raise AlacError(st, self._err())
+        return p.value
+
+    def ipc_close(self, ptr: int):
+        self.lib.alac_b200_ipc_close(self.h, C.c_void_p(ptr))
+
+    def encode_placed(self, pcm, cfg: EncoderConfig, placement: Placement, streams=None, out_sizes=None):
+        """This rank's share of a job several GPUs encode together (alac_b200_encode_placed): the packets go straight
+        to their final offset in the job's buffer (placement.dst_packets, usually another GPU's memory).  Returns
+        (sizes of this rank's packets, num_packets, bytes, byte offset of the block, stats)."""
+        ptr, nbytes, mem = _buf(pcm)
+        self._follow_torch_stream(pcm)
+        bpf = cfg.bytes_per_frame
+        nsf = nbytes // bpf
+        n_streams = len(streams) if streams is not None else 1
+        ccfg = cfg._c()
+        if streams is not None:
+            max_packets = sum((n + cfg.frame_size - 1) // cfg.frame_size for _, n in streams)
+            arr = (_Stream * n_streams)(*[_Stream(a, b) for a, b in streams])
+        else:
+            max_packets = (nsf + cfg.frame_size - 1) // cfg.frame_size
+            arr = None
+        max_packets = max(max_packets, 1)
+        if out_sizes is None:
+            if mem == MEM_DEVICE:
+                import torch
+                out_sizes = torch.empty(max_packets, dtype=torch.int32, device=pcm.device)
+            else:
+                out_sizes = np.empty(max_packets, np.uint32)
+        sptr, scap, smem = _buf(out_sizes)
+        npk, nb, base, stats = C.c_uint64(0), C.c_uint64(0), C.c_uint64(0), Stats()
+        st = self.lib.alac_b200_encode_placed(self.h, C.byref(ccfg), C.c_void_p(ptr), nsf, mem, arr, n_streams, C.byref(placement),
+                                              C.c_void_p(sptr), scap // 4, smem, C.byref(npk), C.byref(nb), C.byref(base), C.byref(stats))
+        if st:
+            raise AlacError(st, self._err())
+        return out_sizes[:npk.value], npk.value, nb.value, base.value, stats.as_dict()
 
     def close(self):
         if getattr(self, "h", None):
@@ -312,7 +424,7 @@ class Engine:
         cfgd = parse_cookie(cookie)
         bpf = {16: 2, 20: 3, 24: 3, 32: 4}[cfgd["bit_depth"]] * cfgd["num_channels"]
         pptr, pbytes, mem = _buf(packets)
-        self._follow_torch_stream(packets)
+        self._follow_torch_stream(sizes if isinstance(packets, DevicePtr) else packets)
         sptr, sbytes, smem = _buf(sizes)
         if smem != mem:
             raise ValueError("packets and sizes must live in the same memory kind")
@@ -322,10 +434,11 @@ class Engine:
         cap = n * cfgd["frame_length"] * bpf
         if mem == MEM_DEVICE:
             import torch
+            where = sizes.device if isinstance(packets, DevicePtr) else packets.device
             if out is None:
-                out = torch.empty(max(cap, 1), dtype=torch.uint8, device=packets.device)
-            psamp = torch.empty(max(n, 1), dtype=torch.int32, device=packets.device)
-            pstat = torch.empty(max(n, 1), dtype=torch.int32, device=packets.device)
+                out = torch.empty(max(cap, 1), dtype=torch.uint8, device=where)
+            psamp = torch.empty(max(n, 1), dtype=torch.int32, device=where)
+            pstat = torch.empty(max(n, 1), dtype=torch.int32, device=where)
         else:
             if out is None:
                 out = np.empty(max(cap, 1), np.uint8)

@@ -115,3 +115,77 @@ def concat_packets_to(dst: int, packets, sizes, group=None):
         ob += nb
         oc += nc
     return out_p, out_s
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# One packet buffer shared by all ranks of a job (one process per GPU): the cross-GPU step of SURVEY 8e inside the
+# encode call itself.  The home rank owns the buffer, the packet-size table and the 1 KB exchange block; the other ranks
+# map them with CUDA IPC (alac_b200_ipc_*), and every rank's enc_assemble_kernel then stores its packets at their final
+# offset there over NVLink (alac_b200_encode_placed).  torch.distributed is used once, at set-up, to hand the three IPC
+# handles round; nothing on the data path is a collective.
+# ---------------------------------------------------------------------------------------------------------------------
+class _RawDevice:
+    """A raw device pointer exposed through __cuda_array_interface__ (no ownership)."""
+
+    def __init__(self, ptr: int, count: int, typestr: str):
+        self.__cuda_array_interface__ = {"shape": (count,), "typestr": typestr, "data": (ptr, False), "version": 3}
+
+
+def tensor_from_pointer(ptr: int, count: int, device, typestr: str = "|u1"):
+    """torch view of `count` elements at device pointer `ptr` (local or peer-mapped memory)."""
+    import torch
+    return torch.as_tensor(_RawDevice(ptr, count, typestr), device=device)
+
+
+class SharedJob:
+    """The single output buffer of a multi-rank encode job.
+
+    capacity_bytes / total_packets size the packet buffer and the size table (worst case of the whole job).
+    Every rank calls `placement(first_packet)` once per encode call (it advances the epoch in lock step)."""
+
+    def __init__(self, engine, device, capacity_bytes: int, total_packets: int, home: int = 0, group=None):
+        import torch.distributed as dist
+        from .engine import EXCHANGE_BYTES
+        self.engine, self.device, self.home = engine, device, home
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        self.capacity, self.total_packets = int(capacity_bytes), int(total_packets)
+        self.epoch = 0
+        sizes_bytes = 4 * max(self.total_packets, 1)
+        if self.rank == home:
+            self._ptrs = [engine.device_alloc(self.capacity), engine.device_alloc(sizes_bytes), engine.device_alloc(EXCHANGE_BYTES)]
+            tensor_from_pointer(self._ptrs[2], EXCHANGE_BYTES, device).zero_()
+            import torch
+            torch.cuda.synchronize(device)
+            handles = [engine.ipc_export(p) for p in self._ptrs]
+        else:
+            handles = None
+        box = [handles]
+        dist.broadcast_object_list(box, src=home, group=group)
+        if self.rank != home:
+            self._ptrs = [engine.ipc_open(h) for h in box[0]]
+        self.packets_ptr, self.sizes_ptr, self.exchange_ptr = self._ptrs
+        from .engine import DevicePtr
+        # every rank may read the job's buffer (peer loads); torch views exist only where the memory is local
+        self.packets_region = DevicePtr(self.packets_ptr, self.capacity)
+        self.packets = self.sizes = None
+        if self.rank == home:
+            self.packets = tensor_from_pointer(self.packets_ptr, self.capacity, device)
+            self.sizes = tensor_from_pointer(self.sizes_ptr, max(self.total_packets, 1), device, "<i4")
+
+    def placement(self, first_packet: int):
+        from .engine import Placement
+        self.epoch += 1
+        return Placement(self.packets_ptr, self.capacity, self.sizes_ptr, int(first_packet), self.exchange_ptr,
+                         self.rank, self.world, self.home, self.epoch)
+
+    def close(self):
+        if getattr(self, "_ptrs", None) is None:
+            return
+        self.packets = self.sizes = None
+        if self.rank == self.home:
+            for p in self._ptrs:
+                self.engine.device_free(p)
+        else:
+            for p in self._ptrs:
+                self.engine.ipc_close(p)
+        self._ptrs = None

@@ -91,6 +91,17 @@ const char *alac_b200_version(void);
    producer's stream (cudaStreamLegacy for work issued on the legacy default stream). */
 int32_t     alac_b200_engine_set_stream(alac_b200_engine *engine, void *cuda_stream);
 
+/* ---- several GPUs of one box (no reference analogue: the fork is single-GPU) ---------------
+ * One engine that shards every encode / decode call by frame range over `n_devices` GPUs of this process
+ * (peer access is enabled between them; devices[0] is the "home" device).  Encode shards whole segments
+ * (frames_per_segment), decode shards packets; the result is byte-identical to a single-GPU call.
+ * With device output the buffers must live on the home device: every GPU writes its packets straight to their final
+ * offset there over NVLink (packet-offset scan + peer stores inside enc_assemble_kernel, no collective, no staging).
+ * With host buffers every GPU moves its own range over its own PCIe link.
+ * frames_per_segment = 0 cannot be split inside a stream: whole streams are dealt out instead. */
+int32_t     alac_b200_engine_create_multi(const int32_t *devices, uint32_t n_devices, alac_b200_engine **out_engine);
+uint32_t    alac_b200_engine_num_devices(const alac_b200_engine *engine);
+
 /* ---- magic cookie: ALACEncoder::GetMagicCookie, codec/ALACEncoder.cu:1109-1140 ------------- */
 /* Returns the cookie size (24, or 48 for > 2 channels) or 0 when cap is too small. */
 uint32_t    alac_b200_magic_cookie(const alac_b200_enc_config *cfg, uint32_t max_frame_bytes,
@@ -119,6 +130,43 @@ int32_t alac_b200_encode(alac_b200_engine *engine, const alac_b200_enc_config *c
                          int16_t *coef_state,
                          uint64_t *out_num_packets, uint64_t *out_bytes,
                          alac_b200_stats *stats);
+
+/* ---- encode one rank's frame range of a job that several GPUs share (one engine / process per GPU) -------------
+ * The cross-GPU step of SURVEY 8e inside the call: every rank scans its packet sizes, publishes its byte total in
+ * `exchange` (a zeroed ALAC_B200_EXCHANGE_BYTES block in the DESTINATION GPU's memory), waits on the device for the
+ * totals of the ranks in front of it, and its assemble kernel stores every packet at its final offset of
+ * `dst_packets` -- peer stores over NVLink when the destination is another GPU (a pointer obtained with
+ * cudaDeviceEnablePeerAccess in one process, or alac_b200_ipc_open across processes).  No collective, no staging copy.
+ * The rank whose `rank` is `home_rank` returns only after every rank's block is in place.
+ * All ranks pass the same `epoch`, incremented from call to call (it tags the exchange slots). */
+#define ALAC_B200_EXCHANGE_BYTES 1024
+#define ALAC_B200_MAX_RANKS      16
+typedef struct alac_b200_placement {
+    void     *dst_packets;     /* device pointer, local or peer: the job's single packet buffer */
+    uint64_t  dst_capacity;    /* bytes */
+    uint32_t *dst_sizes;       /* device pointer, local or peer: the job's packet size table; may be NULL */
+    uint64_t  first_packet;    /* index of this rank's first packet in that table */
+    void     *exchange;        /* device pointer, local or peer: ALAC_B200_EXCHANGE_BYTES, zeroed once */
+    uint32_t  rank, n_ranks, home_rank;
+    uint32_t  epoch;           /* > 0 */
+} alac_b200_placement;
+/* Same arguments as alac_b200_encode for this rank's PCM; packet_sizes[] (the rank's own entries) stays local
+   (out_mem says where); *out_base receives the byte offset of the rank's block inside dst_packets. */
+int32_t alac_b200_encode_placed(alac_b200_engine *engine, const alac_b200_enc_config *cfg,
+                                const void *pcm, uint64_t num_sample_frames, int32_t pcm_mem,
+                                const alac_b200_stream *streams, uint64_t n_streams,
+                                const alac_b200_placement *placement,
+                                uint32_t *packet_sizes, uint64_t sizes_cap, int32_t out_mem,
+                                uint64_t *out_num_packets, uint64_t *out_bytes, uint64_t *out_base,
+                                alac_b200_stats *stats);
+
+/* device memory that can be shared with other processes (plain cudaMalloc on the engine's device) and the
+   cudaIpc* wrappers a one-process-per-GPU launcher needs; handle = 64 bytes (cudaIpcMemHandle_t) */
+int32_t alac_b200_device_alloc(alac_b200_engine *engine, uint64_t bytes, void **out_ptr);
+int32_t alac_b200_device_free(alac_b200_engine *engine, void *ptr);
+int32_t alac_b200_ipc_export(alac_b200_engine *engine, void *ptr, void *out_handle64);
+int32_t alac_b200_ipc_open(alac_b200_engine *engine, const void *handle64, void **out_ptr);
+int32_t alac_b200_ipc_close(alac_b200_engine *engine, void *ptr);
 
 /* ---- batched decode: replaces the Decode() loop of convert-utility/main.cu:717-744 --------- */
 /*

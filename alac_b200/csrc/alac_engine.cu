@@ -458,14 +458,21 @@ static int32_t encode_core(alac_b200_engine *e, const alac_b200_enc_config *cfg,
                            uint64_t num_sample_frames, int32_t pcm_mem, const alac_b200_stream *streams,
                            uint64_t n_streams, void *packets_out, uint64_t packets_cap, uint32_t *packet_sizes,
                            uint64_t sizes_cap, int32_t out_mem, int16_t *coef_state, uint64_t *out_num_packets,
-                           uint64_t *out_bytes, alac_b200_stats *stats, const alac_b200_placement *pl, uint64_t *out_base)
+                           uint64_t *out_bytes, alac_b200_stats *stats, const alac_b200_placement *pl, uint64_t *out_base,
+                           void **out_local = nullptr)
 {
     if (!e) return ALAC_B200_PARAM_ERROR;
     e->err.clear();
     if (!valid_cfg(cfg) || (!pcm && num_sample_frames) || (!packets_out && !pl) || !packet_sizes) return ALAC_B200_PARAM_ERROR;
     if (pl && (!pl->dst_packets || !pl->exchange || pl->n_ranks == 0 || pl->n_ranks > ALAC_B200_MAX_RANKS || pl->rank >= pl->n_ranks ||
-               pl->home_rank >= pl->n_ranks || pl->epoch == 0 || coef_state))
+               pl->home_rank >= pl->n_ranks || pl->epoch == 0 || coef_state || (pl->staging && (pl->home_rank != 0 || !pl->slot_offsets))))
         return ALAC_B200_PARAM_ERROR;
+    // placement forms: `direct` = the assemble kernel stores at the final offsets (after every rank's scan);
+    // `staged` = chunk pipeline, packets leave for the rank's reserved slot while later chunks compute, the home rank compacts
+    const bool staged = pl && pl->staging != nullptr, direct = pl && !staged;
+    const bool is_home = pl && pl->rank == pl->home_rank;
+    const bool to_slot = staged && !is_home;            // this rank's chunks travel to its slot of the home GPU's staging area
+    if (out_local) *out_local = nullptr;
     if (out_num_packets) *out_num_packets = 0;
     if (out_bytes) *out_bytes = 0;
     if (out_base) *out_base = 0;
@@ -544,7 +551,7 @@ static int32_t encode_core(alac_b200_engine *e, const alac_b200_enc_config *cfg,
     // default: as many packets as fit an 8 GB slab budget (bigger launches fill the GPU more evenly)
     uint64_t chunk_target = scratch_chunk_packets();
     if (!chunk_target) chunk_target = std::max<uint64_t>(4096, (8ull << 30) / ((uint64_t)L.chains_per_packet * cap_words * 4));
-    const bool multi = in_host || out_host;             // host buffers: chunks run on several compute streams
+    const bool multi = in_host || out_host || staged;   // host buffers / staged placement: chunks run on several compute streams
     if (multi) chunk_target /= 8;
     const bool taper = multi && P >= 4096;
     struct Chunk { uint32_t s0, s1, p0, cnt; uint64_t f_lo, f_hi; };
@@ -576,7 +583,7 @@ static int32_t encode_core(alac_b200_engine *e, const alac_b200_enc_config *cfg,
     // stream is ONE chunk and must not reserve eight whole-stream slabs).  Placed output: assembly waits for the other
     // ranks' totals, i.e. for every chunk's scan, so no slot is reused.  Otherwise chunks run back to back in one slot.
     const uint32_t nstreams_used = multi ? (uint32_t)std::min<size_t>(8, std::max<size_t>(chunks.size(), 1)) : 1u;
-    const uint32_t nslots = pl ? (uint32_t)std::max<size_t>(chunks.size(), 1) : nstreams_used;
+    const uint32_t nslots = direct ? (uint32_t)std::max<size_t>(chunks.size(), 1) : nstreams_used;
 
     // ---- device buffers ----
     CU_CHECK(e, e->pkt_frame.reserve((size_t)P * 8 + 8));
@@ -608,9 +615,9 @@ static int32_t encode_core(alac_b200_engine *e, const alac_b200_enc_config *cfg,
         d_pcm = static_cast<const uint8_t *>(pcm);
     }
     uint8_t *d_out;
-    if (pl) {
-        d_out = static_cast<uint8_t *>(pl->dst_packets);
-    } else if (out_host) {
+    if (direct || (staged && is_home)) {
+        d_out = static_cast<uint8_t *>(pl->dst_packets);        // (the home rank of a staged job owns offset 0: no detour)
+    } else if (out_host || to_slot) {
         CU_CHECK(e, e->out.reserve((size_t)need_bytes + 64));
         d_out = e->out.as<uint8_t>();
     } else {
@@ -680,7 +687,7 @@ static int32_t encode_core(alac_b200_engine *e, const alac_b200_enc_config *cfg,
         B.sizes = e->sizes.as<uint32_t>();
         B.offsets = e->offsets.as<uint64_t>();
         B.out = d_out;
-        B.base = pl ? d_base : nullptr;
+        B.base = direct ? d_base : nullptr;
         B.pkt_base = c.p0;
         B.num_packets = c.cnt;
         B.lay = L;
@@ -739,17 +746,17 @@ static int32_t encode_core(alac_b200_engine *e, const alac_b200_enc_config *cfg,
                     d_max, ci == 0 ? 0 : 1, &e->h_totals[ci]);
         tile_at += scan_tiles_for(c.cnt);
         if (multi) scan_done.push_back(e->event_on(cs));
-        if (!pl) {
+        if (!direct) {
             assemble_chunk(ci, cs);
             // running byte total after this chunk -> pinned host word; the host needs it to size the chunk's D2H
             comp_done.push_back(e->event_on(cs));
         }
     }
-    if (pl) {
+    Exchange *x = pl ? static_cast<Exchange *>(pl->exchange) : nullptr;
+    if (direct) {
         // ---- the cross-GPU step: publish this rank's byte total, wait (on the device) for the ranks in front, then
         //      every chunk's packets go straight to their final place in the destination GPU's buffer
         if (multi) for (cudaEvent_t ev : scan_done) CU_CHECK(e, cudaStreamWaitEvent(st, ev, 0));
-        Exchange *x = static_cast<Exchange *>(pl->exchange);
         xchg_publish_resolve_kernel<<<1, 32, 0, st>>>(x, pl->rank, pl->epoch, e->offsets.as<uint64_t>() + P, d_base, d_xerr);
         e->launches++;
         for (size_t ci = 0; ci < chunks.size(); ci++) assemble_chunk(ci, st);
@@ -765,22 +772,51 @@ static int32_t encode_core(alac_b200_engine *e, const alac_b200_enc_config *cfg,
     }
     e->cur = nullptr;
     CU_CHECK(e, cudaGetLastError());
-    if (multi && !pl) for (cudaEvent_t ev : comp_done) CU_CHECK(e, cudaStreamWaitEvent(st, ev, 0));     // join the lanes
+    if (multi && !direct) for (cudaEvent_t ev : comp_done) CU_CHECK(e, cudaStreamWaitEvent(st, ev, 0));     // join the lanes
     CU_CHECK(e, cudaEventRecord(e->ev[2], st));
 
     // ---- results (copy-out stream) ----
     uint64_t total = 0, copied = 0;
+    uint8_t *far_out = out_host ? static_cast<uint8_t *>(packets_out)
+                                : to_slot ? static_cast<uint8_t *>(pl->staging) + pl->slot_offsets[pl->rank] : nullptr;
     for (size_t ci = 0; ci < comp_done.size(); ci++) {
         CU_CHECK(e, cudaEventSynchronize(comp_done[ci]));       // all later GPU work is already queued
-        if (pl) break;
+        if (direct) break;
         total = e->h_totals[ci];
-        if (out_host && total > copied) {
-            CU_CHECK(e, cudaMemcpyAsync(static_cast<uint8_t *>(packets_out) + copied, d_out + copied, (size_t)(total - copied),
-                                        cudaMemcpyDeviceToHost, e->copy_out));
+        if (far_out && total > copied) {
+            // host output: D2H; staged placement: a peer copy into this rank's slot on the home GPU (NVLink), while the
+            // lanes work on the later chunks
+            CU_CHECK(e, cudaMemcpyAsync(far_out + copied, d_out + copied, (size_t)(total - copied), cudaMemcpyDefault, e->copy_out));
             copied = total;
         }
     }
     if (pl && !chunks.empty()) total = e->h_totals[chunks.size() - 1];
+    std::vector<unsigned long long> h_tot;
+    if (staged) {
+        // the exchange closes the call: this rank's total, the offset of its block, and "my slot is complete";
+        // the home rank then waits for every rank and closes the gaps between the slots inside its own memory
+        cudaStream_t xs = is_home ? st : e->copy_out;
+        if (pl->dst_sizes && P) CU_CHECK(e, cudaMemcpyAsync(pl->dst_sizes + pl->first_packet, e->sizes.p, (size_t)P * 4, cudaMemcpyDefault, xs));
+        xchg_publish_resolve_kernel<<<1, 32, 0, xs>>>(x, pl->rank, pl->epoch, e->offsets.as<uint64_t>() + P, d_base, d_xerr);
+        xchg_done_kernel<<<1, 1, 0, xs>>>(x, pl->rank, pl->epoch);
+        e->launches += 2;
+        if (is_home) {
+            xchg_wait_all_kernel<<<1, 32, 0, xs>>>(x, pl->n_ranks, pl->epoch, d_job_total, d_xerr);
+            e->launches++;
+            h_tot.resize(16);
+            CU_CHECK(e, cudaMemcpyAsync(h_tot.data(), x->total[pl->epoch & 1u], 16 * 8, cudaMemcpyDeviceToHost, xs));
+            CU_CHECK(e, cudaStreamSynchronize(xs));
+            uint64_t at = h_tot[0];
+            for (uint32_t r = 1; r < pl->n_ranks; r++) {
+                if (at + h_tot[r] > pl->dst_capacity) { e->err = "dst_packets capacity exceeded"; return ALAC_B200_PARAM_ERROR; }
+                if (h_tot[r])
+                    CU_CHECK(e, cudaMemcpyAsync(static_cast<uint8_t *>(pl->dst_packets) + at, static_cast<uint8_t *>(pl->staging) + pl->slot_offsets[r],
+                                                (size_t)h_tot[r], cudaMemcpyDeviceToDevice, xs));
+                at += h_tot[r];
+            }
+            CU_CHECK(e, cudaEventRecord(e->ev[2], xs));      // the job's buffer is complete: end of the kernel phase
+        }
+    }
     if (P) CU_CHECK(e, cudaMemcpyAsync(packet_sizes, e->sizes.p, (size_t)P * 4, sizes_host ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice, e->copy_out));
     CU_CHECK(e, cudaMemcpyAsync(h_counters, e->counters.p, 32, cudaMemcpyDeviceToHost, e->copy_out));
     if (pl) CU_CHECK(e, cudaMemcpyAsync(h_place, d_base, 16, cudaMemcpyDeviceToHost, e->copy_out));
@@ -795,9 +831,10 @@ static int32_t encode_core(alac_b200_engine *e, const alac_b200_enc_config *cfg,
         if (h_counters[2] & 0xffffffffull) { e->err = "cross-GPU exchange timed out (a rank of the job did not arrive)"; return ALAC_B200_CUDA_ERROR; }
         if (h_place[0] + total > pl->dst_capacity) { e->err = "dst_packets capacity exceeded"; return ALAC_B200_PARAM_ERROR; }
         if (out_base) *out_base = h_place[0];
+        if (out_local) *out_local = to_slot ? static_cast<void *>(d_out) : static_cast<void *>(static_cast<uint8_t *>(pl->dst_packets) + h_place[0]);
     }
 
-    if (getenv("ALAC_B200_TRACE") && !pl) {        // developer aid: per-chunk timeline in ms since the call started
+    if (getenv("ALAC_B200_TRACE") && !direct) {        // developer aid: per-chunk timeline in ms since the call started
         for (size_t ci = 0; ci < chunks.size(); ci++) {
             float a = 0, b = 0, c = 0, d = 0;
             if (in_host) cudaEventElapsedTime(&a, e->ev[0], h2d_done[ci]);
@@ -922,6 +959,7 @@ static int32_t multi_encode(alac_b200_engine *e, const alac_b200_enc_config *cfg
                 alac_b200_placement pl;
                 pl.dst_packets = packets_out; pl.dst_capacity = packets_cap; pl.dst_sizes = nullptr; pl.first_packet = h.first_packet;
                 pl.exchange = e->xchg.p; pl.rank = d; pl.n_ranks = m; pl.home_rank = 0; pl.epoch = epoch;
+                pl.staging = nullptr; pl.slot_offsets = nullptr;
                 h.rc = encode_core(se, cfg, pcm, num_sample_frames, pcm_mem, h.streams.data(), h.streams.size(), nullptr, 0,
                                    packet_sizes + h.first_packet, h.packets, ALAC_B200_MEM_DEVICE, nullptr, &h.np, &h.bytes, &h.st, &pl, &h.base);
             } else {
@@ -979,11 +1017,11 @@ extern "C" int32_t alac_b200_encode_placed(alac_b200_engine *e, const alac_b200_
                                            uint64_t num_sample_frames, int32_t pcm_mem, const alac_b200_stream *streams,
                                            uint64_t n_streams, const alac_b200_placement *placement, uint32_t *packet_sizes,
                                            uint64_t sizes_cap, int32_t out_mem, uint64_t *out_num_packets, uint64_t *out_bytes,
-                                           uint64_t *out_base, alac_b200_stats *stats)
+                                           uint64_t *out_base, void **out_local_block, alac_b200_stats *stats)
 {
     if (!e || !placement || e->subs.size() > 1) return ALAC_B200_PARAM_ERROR;
     return encode_core(e, cfg, pcm, num_sample_frames, pcm_mem, streams, n_streams, nullptr, 0, packet_sizes, sizes_cap, out_mem, nullptr,
-                       out_num_packets, out_bytes, stats, placement, out_base);
+                       out_num_packets, out_bytes, stats, placement, out_base, out_local_block);
 }
 
 extern "C" int32_t alac_b200_engine_create_multi(const int32_t *devices, uint32_t n_devices, alac_b200_engine **out_engine)

@@ -62,7 +62,7 @@ class Placement(C.Structure):
     """alac_b200_placement (include/alac_b200.h): where one rank's packet block goes inside a job's single buffer."""
     _fields_ = [("dst_packets", C.c_void_p), ("dst_capacity", C.c_uint64), ("dst_sizes", C.c_void_p),
                 ("first_packet", C.c_uint64), ("exchange", C.c_void_p), ("rank", C.c_uint32), ("n_ranks", C.c_uint32),
-                ("home_rank", C.c_uint32), ("epoch", C.c_uint32)]
+                ("home_rank", C.c_uint32), ("epoch", C.c_uint32), ("staging", C.c_void_p), ("slot_offsets", C.POINTER(C.c_uint64))]
 
 
 EXCHANGE_BYTES = 1024
@@ -110,7 +110,7 @@ def load_library():
     lib.alac_b200_engine_num_devices.argtypes = [vp]
     lib.alac_b200_engine_num_devices.restype = u32
     lib.alac_b200_encode_placed.argtypes = [vp, C.POINTER(_EncConfig), vp, u64, i32, C.POINTER(_Stream), u64, C.POINTER(Placement),
-                                            vp, u64, i32, C.POINTER(u64), C.POINTER(u64), C.POINTER(u64), C.POINTER(Stats)]
+                                            vp, u64, i32, C.POINTER(u64), C.POINTER(u64), C.POINTER(u64), C.POINTER(vp), C.POINTER(Stats)]
     lib.alac_b200_encode_placed.restype = i32
     lib.alac_b200_device_alloc.argtypes = [vp, u64, C.POINTER(vp)]
     lib.alac_b200_device_alloc.restype = i32
@@ -277,7 +277,8 @@ class Engine:
     def encode_placed(self, pcm, cfg: EncoderConfig, placement: Placement, streams=None, out_sizes=None):
         """This rank's share of a job several GPUs encode together (alac_b200_encode_placed): the packets go straight
         to their final offset in the job's buffer (placement.dst_packets, usually another GPU's memory).  Returns
-        (sizes of this rank's packets, num_packets, bytes, byte offset of the block, stats)."""
+        (sizes of this rank's packets, num_packets, bytes, byte offset of the block, DevicePtr of the rank's own copy of
+        the block, stats)."""
         ptr, nbytes, mem = _buf(pcm)
         self._follow_torch_stream(pcm)
         bpf = cfg.bytes_per_frame
@@ -298,12 +299,13 @@ class Engine:
             else:
                 out_sizes = np.empty(max_packets, np.uint32)
         sptr, scap, smem = _buf(out_sizes)
-        npk, nb, base, stats = C.c_uint64(0), C.c_uint64(0), C.c_uint64(0), Stats()
+        npk, nb, base, stats, local = C.c_uint64(0), C.c_uint64(0), C.c_uint64(0), Stats(), C.c_void_p()
         st = self.lib.alac_b200_encode_placed(self.h, C.byref(ccfg), C.c_void_p(ptr), nsf, mem, arr, n_streams, C.byref(placement),
-                                              C.c_void_p(sptr), scap // 4, smem, C.byref(npk), C.byref(nb), C.byref(base), C.byref(stats))
+                                              C.c_void_p(sptr), scap // 4, smem, C.byref(npk), C.byref(nb), C.byref(base), C.byref(local),
+                                              C.byref(stats))
         if st:
             raise AlacError(st, self._err())
-        return out_sizes[:npk.value], npk.value, nb.value, base.value, stats.as_dict()
+        return out_sizes[:npk.value], npk.value, nb.value, base.value, DevicePtr(local.value or 0, nb.value), stats.as_dict()
 
     def close(self):
         if getattr(self, "h", None):

@@ -141,20 +141,34 @@ class SharedJob:
     """The single output buffer of a multi-rank encode job.
 
     capacity_bytes / total_packets size the packet buffer and the size table (worst case of the whole job).
+    slot_bytes: per-rank worst-case block sizes (encode bounds) -> the staged form of alac_b200_placement: the home rank
+    also owns a staging area with one reserved slot per rank, so packets travel while the ranks still compute; None
+    selects the direct form (the assemble kernels store at the final offsets once every rank has been scanned).
     Every rank calls `placement(first_packet)` once per encode call (it advances the epoch in lock step)."""
 
-    def __init__(self, engine, device, capacity_bytes: int, total_packets: int, home: int = 0, group=None):
+    def __init__(self, engine, device, capacity_bytes: int, total_packets: int, home: int = 0, group=None, slot_bytes=None):
+        import ctypes as C
+        import torch
         import torch.distributed as dist
-        from .engine import EXCHANGE_BYTES
+        from .engine import EXCHANGE_BYTES, DevicePtr
         self.engine, self.device, self.home = engine, device, home
         self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
         self.capacity, self.total_packets = int(capacity_bytes), int(total_packets)
         self.epoch = 0
+        self.slot_offsets = None
+        staging_bytes = 0
+        if slot_bytes is not None:
+            offs, at = [], 0
+            for b in slot_bytes:
+                offs.append(at)
+                at += (int(b) + 255) // 256 * 256
+            staging_bytes = at
+            self.slot_offsets = (C.c_uint64 * len(offs))(*offs)
         sizes_bytes = 4 * max(self.total_packets, 1)
         if self.rank == home:
-            self._ptrs = [engine.device_alloc(self.capacity), engine.device_alloc(sizes_bytes), engine.device_alloc(EXCHANGE_BYTES)]
+            self._ptrs = [engine.device_alloc(self.capacity), engine.device_alloc(sizes_bytes), engine.device_alloc(EXCHANGE_BYTES),
+                          engine.device_alloc(max(staging_bytes, 256))]
             tensor_from_pointer(self._ptrs[2], EXCHANGE_BYTES, device).zero_()
-            import torch
             torch.cuda.synchronize(device)
             handles = [engine.ipc_export(p) for p in self._ptrs]
         else:
@@ -163,9 +177,8 @@ class SharedJob:
         dist.broadcast_object_list(box, src=home, group=group)
         if self.rank != home:
             self._ptrs = [engine.ipc_open(h) for h in box[0]]
-        self.packets_ptr, self.sizes_ptr, self.exchange_ptr = self._ptrs
-        from .engine import DevicePtr
-        # every rank may read the job's buffer (peer loads); torch views exist only where the memory is local
+        self.packets_ptr, self.sizes_ptr, self.exchange_ptr, self.staging_ptr = self._ptrs
+        # torch views exist only where the memory is local (the home rank)
         self.packets_region = DevicePtr(self.packets_ptr, self.capacity)
         self.packets = self.sizes = None
         if self.rank == home:
@@ -175,8 +188,10 @@ class SharedJob:
     def placement(self, first_packet: int):
         from .engine import Placement
         self.epoch += 1
+        staged = self.slot_offsets is not None
         return Placement(self.packets_ptr, self.capacity, self.sizes_ptr, int(first_packet), self.exchange_ptr,
-                         self.rank, self.world, self.home, self.epoch)
+                         self.rank, self.world, self.home, self.epoch, self.staging_ptr if staged else None,
+                         self.slot_offsets if staged else None)
 
     def close(self):
         if getattr(self, "_ptrs", None) is None:

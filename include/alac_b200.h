@@ -149,16 +149,26 @@ typedef struct alac_b200_placement {
     void     *exchange;        /* device pointer, local or peer: ALAC_B200_EXCHANGE_BYTES, zeroed once */
     uint32_t  rank, n_ranks, home_rank;
     uint32_t  epoch;           /* > 0 */
+    /* Staged form (staging != NULL; home_rank must be 0).  A rank's final offset depends on every byte of the ranks in
+       front of it, so direct placement can only start when all ranks have finished computing.  Staged placement moves the
+       bytes DURING the computation instead: the call runs as a pipeline of chunks, each chunk's packets leave for the
+       rank's reserved slot staging + slot_offsets[rank] over NVLink (asynchronous peer copies) while the next chunk's
+       kernels run, and when every rank is done the home rank closes the gaps between the slots with copies inside its
+       own memory.  slot_offsets: n_ranks entries (host memory), slot r at least as large as rank r's encode bound. */
+    void           *staging;        /* device pointer in the home GPU's memory (local or peer), or NULL = direct form */
+    const uint64_t *slot_offsets;
 } alac_b200_placement;
 /* Same arguments as alac_b200_encode for this rank's PCM; packet_sizes[] (the rank's own entries) stays local
-   (out_mem says where); *out_base receives the byte offset of the rank's block inside dst_packets. */
+   (out_mem says where); *out_base receives the byte offset of the rank's block inside dst_packets.  *out_local_block
+   (optional) receives a device pointer to the rank's own copy of its block (staged form: engine scratch, valid until the
+   engine's next encode call; direct form and the home rank: the block's place inside dst_packets). */
 int32_t alac_b200_encode_placed(alac_b200_engine *engine, const alac_b200_enc_config *cfg,
                                 const void *pcm, uint64_t num_sample_frames, int32_t pcm_mem,
                                 const alac_b200_stream *streams, uint64_t n_streams,
                                 const alac_b200_placement *placement,
                                 uint32_t *packet_sizes, uint64_t sizes_cap, int32_t out_mem,
                                 uint64_t *out_num_packets, uint64_t *out_bytes, uint64_t *out_base,
-                                alac_b200_stats *stats);
+                                void **out_local_block, alac_b200_stats *stats);
 
 /* device memory that can be shared with other processes (plain cudaMalloc on the engine's device) and the
    cudaIpc* wrappers a one-process-per-GPU launcher needs; handle = 64 bytes (cudaIpcMemHandle_t) */

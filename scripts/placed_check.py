@@ -26,18 +26,23 @@ plan = shard.plan_frame_shards(frames, F, world, K)
 pk_plan = shard.plan_packet_shards((frames + F - 1) // F, world, K)
 a, n = plan[rank]
 pcm = synth.corpus_torch(a, n, ch, depth, dev, seed=0)
-job = shard.SharedJob(eng, dev, alac_b200.encode_bound(cfg, frames, world), (frames + F - 1) // F)
+form = sys.argv[2] if len(sys.argv) > 2 else "staged"
+slots = [alac_b200.encode_bound(cfg, nn) for _, nn in plan] if form == "staged" else None
+job = shard.SharedJob(eng, dev, alac_b200.encode_bound(cfg, frames, world), (frames + F - 1) // F, slot_bytes=slots)
 ok = True
 for it in range(3):                                  # several epochs through the same exchange block
     dist.barrier()
     torch.cuda.synchronize()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
-    sizes, npk, nb, base, stats = eng.encode_placed(pcm, cfg, job.placement(pk_plan[rank][0]))
+    sizes, npk, nb, base, mine, stats = eng.encode_placed(pcm, cfg, job.placement(pk_plan[rank][0]))
     ev1.record()
     torch.cuda.synchronize()
     ms = ev0.elapsed_time(ev1)
-    # decode this rank's block straight out of the shared buffer
+    # decode this rank's block: its own copy, and straight out of the shared buffer (peer loads)
+    dec = eng.decode(alac_b200.magic_cookie(cfg), mine, sizes)
+    ok = ok and dec.status == 0 and torch.equal(dec.pcm, pcm)
+    dist.barrier()          # (the shared buffer is complete once the home rank's call has returned)
     dec = eng.decode(alac_b200.magic_cookie(cfg), job.packets_region[base:base + nb], sizes)
     ok = ok and dec.status == 0 and torch.equal(dec.pcm, pcm)
     tot = torch.tensor([nb], dtype=torch.int64, device=dev)
@@ -48,7 +53,7 @@ for it in range(3):                                  # several epochs through th
         same = int(tot.item()) == whole.nbytes and torch.equal(job.packets[:whole.nbytes], whole.packets) and \
             torch.equal(job.sizes[:whole.num_packets], torch.as_tensor(whole.sizes, device=dev).to(torch.int32))
         ok = ok and same
-        print(f"[{it}] placed encode over {world} ranks, {depth}-bit: {'OK' if same else 'MISMATCH'}; {int(tot.item())} bytes, rank 0 call {ms:.2f} ms "
+        print(f"[{it}] {form} placed encode over {world} ranks, {depth}-bit: {'OK' if same else 'MISMATCH'}; {int(tot.item())} bytes, rank 0 call {ms:.2f} ms "
               f"(kernels {stats['ms_kernels']:.2f} ms)", flush=True)
         job.packets[:whole.nbytes].zero_()
     dist.barrier()

@@ -61,7 +61,7 @@ constexpr uint32_t kDecClasses = 16;
 constexpr uint32_t kRegularClasses = 4;     // classes below this are taken by dec_fused_kernel
 
 // walk element tags until the first SCE/LFE/CPE and return its sample count
-__global__ void dec_header_kernel(DecArgs A)
+static __global__ void dec_header_kernel(DecArgs A)
 {
     const uint32_t local = blockIdx.x * blockDim.x + threadIdx.x;
     if (local >= A.num_packets) return;
@@ -117,7 +117,7 @@ __global__ void dec_header_kernel(DecArgs A)
 }
 
 // perm[first slot of the packet's class + its rank inside the class] = packet
-__global__ void dec_perm_kernel(DecArgs A)
+static __global__ void dec_perm_kernel(DecArgs A)
 {
     const uint32_t local = blockIdx.x * blockDim.x + threadIdx.x;
     if (local >= A.num_packets) return;
@@ -461,7 +461,7 @@ __device__ __forceinline__ void unpc_rows_any(uint32_t mode, PredState &s, int32
 
 // any numactive 0..31, any denShift, mode != 0 (codec/dp_dec.c:67-95, :335-380; codec/ALACDecoder.cu:686-694):
 // in place on the lane's column of the channel tile in global memory
-__device__ __noinline__ void unpc_general(int32_t *col, uint32_t n, DecChanHdr h, uint32_t chanshift)
+static __device__ __noinline__ void unpc_general(int32_t *col, uint32_t n, DecChanHdr h, uint32_t chanshift)
 {
     int32_t ring[32];
     for (int k = 0; k < 32; k++) ring[k] = 0;
@@ -841,13 +841,13 @@ __global__ void __launch_bounds__(64) dec_fused_kernel(DecArgs A)
 // scan of the marks numbers the entries; ber_value_kernel assembles each entry from the <= 5 bytes that end at
 // its mark; ber_count_kernel finds where the reference's decode loop would stop (a zero size, or a packet that
 // no longer fits the data chunk, convert-utility/main.cu:717).
-__global__ void ber_flag_kernel(const uint8_t *table, uint64_t nbytes, uint32_t *flags)
+static __global__ void ber_flag_kernel(const uint8_t *table, uint64_t nbytes, uint32_t *flags)
 {
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < nbytes) flags[i] = (table[i] & 0x80u) ? 0u : 1u;
 }
 
-__global__ void ber_value_kernel(const uint8_t *table, uint64_t nbytes, const uint64_t *entry_of_byte, uint32_t *sizes, uint64_t cap)
+static __global__ void ber_value_kernel(const uint8_t *table, uint64_t nbytes, const uint64_t *entry_of_byte, uint32_t *sizes, uint64_t cap)
 {
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= nbytes || (table[i] & 0x80u)) return;
@@ -862,7 +862,7 @@ __global__ void ber_value_kernel(const uint8_t *table, uint64_t nbytes, const ui
     sizes[k] = v;
 }
 
-__global__ void ber_count_kernel(const uint32_t *sizes, const uint64_t *offsets, uint64_t entries, uint64_t data_bytes,
+static __global__ void ber_count_kernel(const uint32_t *sizes, const uint64_t *offsets, uint64_t entries, uint64_t data_bytes,
                                  unsigned long long *first_bad)
 {
     const uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -872,7 +872,7 @@ __global__ void ber_count_kernel(const uint32_t *sizes, const uint64_t *offsets,
 
 // the other direction: packet sizes -> BER bytes (convert-utility/CAFFileALAC.cpp:189-222 WriteBERInteger).
 // ber_len_kernel gives each entry's byte count (1..5), an exclusive scan places it, ber_emit_kernel writes it.
-__global__ void ber_len_kernel(const uint32_t *sizes, uint64_t n, uint32_t *lens)
+static __global__ void ber_len_kernel(const uint32_t *sizes, uint64_t n, uint32_t *lens)
 {
     const uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= n) return;
@@ -880,7 +880,7 @@ __global__ void ber_len_kernel(const uint32_t *sizes, uint64_t n, uint32_t *lens
     lens[k] = v < (1u << 7) ? 1u : v < (1u << 14) ? 2u : v < (1u << 21) ? 3u : v < (1u << 28) ? 4u : 5u;
 }
 
-__global__ void ber_emit_kernel(const uint32_t *sizes, const uint64_t *offsets, uint64_t n, uint8_t *table)
+static __global__ void ber_emit_kernel(const uint32_t *sizes, const uint64_t *offsets, uint64_t n, uint8_t *table)
 {
     const uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= n) return;
@@ -892,5 +892,44 @@ __global__ void ber_emit_kernel(const uint32_t *sizes, const uint64_t *offsets, 
         p[i] = (uint8_t)(((v >> sh) & 0x7fu) | (i + 1u < len ? 0x80u : 0u));
     }
 }
+
+
+// ---- host-side launchers (one translation unit per bit depth, see alac_encode.cuh) ---------------------------------
+// The decode kernels keep their tiles / rings in static shared memory and want 8-9 CTAs per SM resident (one
+// wave for the 1-hour workload).  With the default carve-out the driver leaves most of the 228 KB to L1 and only
+// about half of those CTAs fit, so ask for the maximum shared-memory carve-out once per device.
+template <int DEPTH>
+void dec_configure()
+{
+    cudaFuncSetAttribute(dec_fused_kernel<DEPTH>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    cudaFuncSetAttribute(dec_finish_kernel<DEPTH>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    cudaFuncSetAttribute(dec_entropy_kernel<DEPTH>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+}
+
+// the three main kernels of one chunk; ev: optional {after fused, after entropy} events.  Returns kernels launched.
+template <int DEPTH>
+uint32_t dec_launch_main(cudaStream_t s, const DecArgs &A, cudaEvent_t *ev)
+{
+    const uint32_t lgrid = (A.num_packets + kRingStride - 1) / kRingStride;
+    const uint32_t groups = (A.num_packets + 31) / 32;
+    uint32_t launches = 2;
+    // regular mono / stereo groups: entropy and finish warps side by side in one kernel
+    if (A.fused) { dec_fused_kernel<DEPTH><<<groups, 64, 0, s>>>(A); launches++; }
+    if (ev) cudaEventRecord(ev[0], s);
+    // everything else (multichannel, escapes, other predictor set-ups): the two general kernels; groups the
+    // fused kernel took return at once
+    dec_entropy_kernel<DEPTH><<<lgrid, kRingStride, 0, s>>>(A);
+    if (ev) cudaEventRecord(ev[1], s);
+    dec_finish_kernel<DEPTH><<<groups * A.num_channels, 64, 0, s>>>(A);
+    return launches;
+}
+
+#ifndef ALAC_INSTANTIATE_DEPTH
+#define ALAC_DEC_EXTERN(D)                                                              \
+    extern template void dec_configure<D>();                                             \
+    extern template uint32_t dec_launch_main<D>(cudaStream_t, const DecArgs &, cudaEvent_t *);
+ALAC_DEC_EXTERN(16) ALAC_DEC_EXTERN(20) ALAC_DEC_EXTERN(24) ALAC_DEC_EXTERN(32)
+#undef ALAC_DEC_EXTERN
+#endif
 
 }  // namespace alacb

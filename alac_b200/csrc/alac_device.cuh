@@ -196,7 +196,7 @@ struct NoSink {
 };
 
 // exact n / (2^k - 1) for n < 9 * (2^k - 1): floor(2^32 / m) + 1, k = 0..15 (k = 0 unused)
-__constant__ uint32_t c_div_magic[16] = {
+static __constant__ uint32_t c_div_magic[16] = {
     0u, 0u /* m = 1 handled apart */, 1431655766u, 613566757u, 286331154u, 138547333u, 68174085u, 33818641u,
     16843010u, 8405025u, 4198405u, 2098178u, 1048833u, 524353u, 262161u, 131077u
 };
@@ -223,7 +223,7 @@ __device__ __forceinline__ uint2 ag_run_code_inline(uint32_t mb, uint32_t n)
     return make_uint2(len, value);
 }
 
-__device__ __noinline__ uint2 ag_run_code(uint32_t mb, uint32_t n) { return ag_run_code_inline(mb, n); }
+static __device__ __noinline__ uint2 ag_run_code(uint32_t mb, uint32_t n) { return ag_run_code_inline(mb, n); }
 
 template <bool EMIT, class Sink>
 __device__ __forceinline__ void ag_flush_run(AgEnc &s, Sink &sink, uint32_t zmode_after)

@@ -692,7 +692,7 @@ enc_final_kernel(EncArgs A, JobLists Q, uint32_t ctas_per_list)
 // Finishes each element record (post-check of codec/ALACEncoder.cu:537-543 / :952-958, fast mode
 // :703-725: a compressed element that is not smaller than the escape form is sent as escape) and
 // sums the element bits of a packet.
-__global__ void enc_size_kernel(ElemRec *recs, EncLayout lay, uint32_t depth, const uint32_t *pkt_samples,
+static __global__ void enc_size_kernel(ElemRec *recs, EncLayout lay, uint32_t depth, const uint32_t *pkt_samples,
                                 uint32_t num_packets, uint32_t *sizes, unsigned long long *escapes)
 {
     const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
@@ -745,7 +745,7 @@ __device__ __forceinline__ uint64_t block_sum_u64(uint64_t x, uint64_t *warp_sum
     return s;                       // every thread holds the block total
 }
 
-__global__ void __launch_bounds__(1024) scan_tile_sums_kernel(const uint32_t *in, uint64_t n, uint64_t *tile_sums)
+static __global__ void __launch_bounds__(1024) scan_tile_sums_kernel(const uint32_t *in, uint64_t n, uint64_t *tile_sums)
 {
     __shared__ uint64_t warp_sums[32];
     const uint64_t i0 = (uint64_t)blockIdx.x * kScanTile + 4ull * threadIdx.x;
@@ -758,7 +758,7 @@ __global__ void __launch_bounds__(1024) scan_tile_sums_kernel(const uint32_t *in
 
 // chain_base: continue from out[0], which the previous chunk's scan left as its grand total (tile 0 rewrites out[0]
 // with that same value, so tiles reading it concurrently see one value either way).
-__global__ void __launch_bounds__(1024) scan_u32_to_u64_kernel(const uint32_t *in, uint64_t *out, uint64_t n, const uint64_t *tile_sums,
+static __global__ void __launch_bounds__(1024) scan_u32_to_u64_kernel(const uint32_t *in, uint64_t *out, uint64_t n, const uint64_t *tile_sums,
                                                                uint32_t *max_out, int chain_base, uint64_t *host_total = nullptr)
 {
     __shared__ uint64_t warp_sums[32];
@@ -865,7 +865,7 @@ __device__ __forceinline__ bool spin_until(const uint32_t *flag, uint32_t epoch)
 }
 
 // one warp: publish this rank's total (*total_word = offsets[P] of the rank's scan), then sum the totals in front
-__global__ void xchg_publish_resolve_kernel(Exchange *x, uint32_t rank, uint32_t epoch, const uint64_t *total_word, uint64_t *base_out,
+static __global__ void xchg_publish_resolve_kernel(Exchange *x, uint32_t rank, uint32_t epoch, const uint64_t *total_word, uint64_t *base_out,
                                             uint32_t *err)
 {
     const uint32_t slot = epoch & 1u, lane = threadIdx.x;
@@ -890,14 +890,14 @@ __global__ void xchg_publish_resolve_kernel(Exchange *x, uint32_t rank, uint32_t
 }
 
 // after the rank's last assemble launch: its block (and sizes) are in place
-__global__ void xchg_done_kernel(Exchange *x, uint32_t rank, uint32_t epoch)
+static __global__ void xchg_done_kernel(Exchange *x, uint32_t rank, uint32_t epoch)
 {
     __threadfence_system();
     st_release_sys_u32(&x->done[epoch & 1u][rank], epoch);
 }
 
 // home rank: every rank's block is in place; also totals the job (sum of all ranks' bytes)
-__global__ void xchg_wait_all_kernel(Exchange *x, uint32_t n_ranks, uint32_t epoch, uint64_t *job_total, uint32_t *err)
+static __global__ void xchg_wait_all_kernel(Exchange *x, uint32_t n_ranks, uint32_t epoch, uint64_t *job_total, uint32_t *err)
 {
     const uint32_t slot = epoch & 1u, lane = threadIdx.x;
     bool ok = true;
@@ -1123,5 +1123,79 @@ __global__ void __launch_bounds__(kAsmWarps * 32) enc_assemble_kernel(AsmArgs A)
         }
     }
 }
+
+
+// ---- host-side launchers ------------------------------------------------------------------------------------------
+// The kernels above are templates on the bit depth; each depth is instantiated in its own translation unit
+// (alac_kernels_d16.cu ...), so the four compile in parallel and the engine's translation unit holds no kernel code.
+// ev: optional events recorded around the kernels -- {before, between search and final, after} for the pair launch,
+// then the same three for the mono launch (split form only).  Returns the number of kernels launched.
+template <int DEPTH, bool PACKED, bool WRAP>
+static uint32_t enc_launch_search_v(cudaStream_t s, const EncArgs &A, uint32_t mono_mask, uint32_t pair_mask, const JobLists *split, cudaEvent_t *ev)
+{
+    const uint32_t pairs = __builtin_popcount(pair_mask), monos = __builtin_popcount(mono_mask);
+    uint32_t launches = 0;
+    if (pairs) {
+        const uint64_t threads = (uint64_t)A.num_segments * pairs * 2;
+        if (split) {
+            const uint32_t ctas = (uint32_t)((threads + 31) / 32);
+            if (ev) cudaEventRecord(ev[0], s);
+            enc_search_split_kernel<DEPTH, true, PACKED, WRAP><<<ctas, 32, 0, s>>>(A, pairs, pair_mask, *split);
+            if (ev) cudaEventRecord(ev[1], s);
+            enc_final_kernel<DEPTH, true, PACKED, WRAP><<<2 * ctas, 32, 0, s>>>(A, *split, ctas);
+            if (ev) cudaEventRecord(ev[2], s);
+            launches += 2;
+        } else {
+            enc_search_kernel<DEPTH, true, PACKED, WRAP>
+                <<<(uint32_t)((threads + kChainThreads - 1) / kChainThreads), kSearchThreads, 0, s>>>(A, pairs, pair_mask);
+            launches += 1;
+        }
+    }
+    if (monos) {
+        const uint64_t threads = (uint64_t)A.num_segments * monos;
+        if (split) {
+            const uint32_t ctas = (uint32_t)((threads + 31) / 32);
+            JobLists Qm = *split;
+            Qm.counts += 2;     // the mono launch has its own pair of counters
+            if (ev) cudaEventRecord(ev[3], s);
+            enc_search_split_kernel<DEPTH, false, false, WRAP><<<ctas, 32, 0, s>>>(A, monos, mono_mask, Qm);
+            if (ev) cudaEventRecord(ev[4], s);
+            enc_final_kernel<DEPTH, false, false, WRAP><<<2 * ctas, 32, 0, s>>>(A, Qm, ctas);
+            if (ev) cudaEventRecord(ev[5], s);
+            launches += 2;
+        } else {
+            enc_search_kernel<DEPTH, false, false, WRAP>
+                <<<(uint32_t)((threads + kChainThreads - 1) / kChainThreads), kSearchThreads, 0, s>>>(A, monos, mono_mask);
+            launches += 1;
+        }
+    }
+    return launches;
+}
+
+// packed: pure stereo PCM at 8-byte alignment (one wide load per sample-frame);
+// wrap: the int16 coefficient range could be left during a segment, so every update re-wraps
+template <int DEPTH>
+uint32_t enc_launch_search(cudaStream_t s, const EncArgs &A, uint32_t mono_mask, uint32_t pair_mask, bool packed, bool wrap,
+                           const JobLists *split, cudaEvent_t *ev)
+{
+    if (packed) return wrap ? enc_launch_search_v<DEPTH, true, true>(s, A, mono_mask, pair_mask, split, ev)
+                            : enc_launch_search_v<DEPTH, true, false>(s, A, mono_mask, pair_mask, split, ev);
+    return wrap ? enc_launch_search_v<DEPTH, false, true>(s, A, mono_mask, pair_mask, split, ev)
+                : enc_launch_search_v<DEPTH, false, false>(s, A, mono_mask, pair_mask, split, ev);
+}
+
+template <int DEPTH>
+void enc_launch_assemble(cudaStream_t s, const AsmArgs &A)
+{
+    enc_assemble_kernel<DEPTH><<<(A.num_packets + kAsmWarps - 1) / kAsmWarps, kAsmWarps * 32, 0, s>>>(A);
+}
+
+#ifndef ALAC_INSTANTIATE_DEPTH
+#define ALAC_ENC_EXTERN(D)                                                                                                            \
+    extern template uint32_t enc_launch_search<D>(cudaStream_t, const EncArgs &, uint32_t, uint32_t, bool, bool, const JobLists *, cudaEvent_t *); \
+    extern template void enc_launch_assemble<D>(cudaStream_t, const AsmArgs &);
+ALAC_ENC_EXTERN(16) ALAC_ENC_EXTERN(20) ALAC_ENC_EXTERN(24) ALAC_ENC_EXTERN(32)
+#undef ALAC_ENC_EXTERN
+#endif
 
 }  // namespace alacb

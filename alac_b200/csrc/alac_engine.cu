@@ -67,6 +67,13 @@ struct alac_b200_engine {
     std::vector<alac_b200_engine *> subs;
     DevBuf xchg, m_out, m_sizes, m_aux;      // home: exchange block; every sub: its block of a host-output / decode call
     uint32_t epoch = 0;
+    // asynchronous forms (alac_b200_*_submit / alac_b200_wait): one call in flight on a worker thread
+    std::thread worker;
+    bool async_busy = false;
+    int32_t async_rc = 0;
+    alac_b200_enc_config async_cfg;
+    std::vector<alac_b200_stream> async_streams;
+    std::vector<uint8_t> async_cookie;
     // encode geometry tables of the previous call (see alac_b200_encode)
     std::vector<uint64_t> h_pkt_frame;
     std::vector<uint32_t> h_pkt_samples, h_seg_first, h_seg_count, h_seg_stream;
@@ -88,6 +95,15 @@ struct alac_b200_engine {
         cudaEvent_t ev = timers[timers_used++];
         cudaEventRecord(ev, s);
         return ev;
+    }
+    cudaEvent_t new_event()         // not recorded yet
+    {
+        if (timers_used == timers.size()) {
+            cudaEvent_t ev = nullptr;
+            cudaEventCreate(&ev);
+            timers.push_back(ev);
+        }
+        return timers[timers_used++];
     }
     cudaEvent_t timer()
     {
@@ -264,6 +280,7 @@ int32_t alac_b200_engine_create(int32_t device, alac_b200_engine **out_engine)
 void alac_b200_engine_destroy(alac_b200_engine *e)
 {
     if (!e) return;
+    if (e->worker.joinable()) e->worker.join();
     for (size_t i = 1; i < e->subs.size(); i++) alac_b200_engine_destroy(e->subs[i]);
     e->subs.clear();
     cudaSetDevice(e->device);
@@ -364,68 +381,6 @@ int32_t alac_b200_copy_to_device(void *dst, const void *src, uint64_t bytes)
 // ------------------------------------------------------------------------------------------------
 // encode
 // ------------------------------------------------------------------------------------------------
-template <int DEPTH, bool PACKED, bool WRAP>
-static void launch_search_v(alac_b200_engine *e, const EncArgs &A, uint32_t mono_mask, uint32_t pair_mask, const JobLists *split)
-{
-    const uint32_t pairs = __builtin_popcount(pair_mask), monos = __builtin_popcount(mono_mask);
-    if (pairs) {
-        const uint64_t threads = (uint64_t)A.num_segments * pairs * 2;
-        if (split) {
-            const uint32_t ctas = (uint32_t)((threads + 31) / 32);
-            e->t_mid.push_back(e->timer());
-            enc_search_split_kernel<DEPTH, true, PACKED, WRAP><<<ctas, 32, 0, e->cur>>>(A, pairs, pair_mask, *split);
-            e->t_mid.push_back(e->timer());
-            enc_final_kernel<DEPTH, true, PACKED, WRAP><<<2 * ctas, 32, 0, e->cur>>>(A, *split, ctas);
-            e->t_mid.push_back(e->timer());
-            e->launches++;
-        } else {
-            enc_search_kernel<DEPTH, true, PACKED, WRAP>
-                <<<(uint32_t)((threads + kChainThreads - 1) / kChainThreads), kSearchThreads, 0, e->cur>>>(A, pairs, pair_mask);
-        }
-        e->launches++;
-    }
-    if (monos) {
-        const uint64_t threads = (uint64_t)A.num_segments * monos;
-        if (split) {
-            const uint32_t ctas = (uint32_t)((threads + 31) / 32);
-            JobLists Qm = *split;
-            Qm.counts += 2;     // the mono launch has its own pair of counters
-            e->t_mid.push_back(e->timer());
-            enc_search_split_kernel<DEPTH, false, false, WRAP><<<ctas, 32, 0, e->cur>>>(A, monos, mono_mask, Qm);
-            e->t_mid.push_back(e->timer());
-            enc_final_kernel<DEPTH, false, false, WRAP><<<2 * ctas, 32, 0, e->cur>>>(A, Qm, ctas);
-            e->t_mid.push_back(e->timer());
-            e->launches++;
-        } else {
-            enc_search_kernel<DEPTH, false, false, WRAP>
-                <<<(uint32_t)((threads + kChainThreads - 1) / kChainThreads), kSearchThreads, 0, e->cur>>>(A, monos, mono_mask);
-        }
-        e->launches++;
-    }
-}
-
-// packed: pure stereo PCM at 8-byte alignment (one wide load per sample-frame);
-// wrap: the int16 coefficient range could be left during a segment, so every update re-wraps
-template <int DEPTH>
-static void launch_search(alac_b200_engine *e, const EncArgs &A, uint32_t mono_mask, uint32_t pair_mask, bool packed, bool wrap,
-                          const JobLists *split)
-{
-    if (packed) {
-        if (wrap) launch_search_v<DEPTH, true, true>(e, A, mono_mask, pair_mask, split);
-        else launch_search_v<DEPTH, true, false>(e, A, mono_mask, pair_mask, split);
-    } else {
-        if (wrap) launch_search_v<DEPTH, false, true>(e, A, mono_mask, pair_mask, split);
-        else launch_search_v<DEPTH, false, false>(e, A, mono_mask, pair_mask, split);
-    }
-}
-
-template <int DEPTH>
-static void launch_assemble(alac_b200_engine *e, const AsmArgs &A)
-{
-    enc_assemble_kernel<DEPTH><<<(A.num_packets + kAsmWarps - 1) / kAsmWarps, kAsmWarps * 32, 0, e->cur>>>(A);
-    e->launches++;
-}
-
 // Synchronises every stream a call may have used when the call returns early (CU_CHECK, capacity errors): queued
 // kernels and copies must not outlive the call -- they use engine scratch the next call reuses and write to locals
 // (pinned counters, status vectors) that are destroyed on return.  Declare it AFTER those locals.
@@ -694,11 +649,12 @@ static int32_t encode_core(alac_b200_engine *e, const alac_b200_enc_config *cfg,
         e->cur = cs;
         t_asm.push_back(e->timer());
         switch (cfg->bit_depth) {
-        case 16: launch_assemble<16>(e, B); break;
-        case 20: launch_assemble<20>(e, B); break;
-        case 24: launch_assemble<24>(e, B); break;
-        default: launch_assemble<32>(e, B); break;
+        case 16: enc_launch_assemble<16>(cs, B); break;
+        case 20: enc_launch_assemble<20>(cs, B); break;
+        case 24: enc_launch_assemble<24>(cs, B); break;
+        default: enc_launch_assemble<32>(cs, B); break;
         }
+        e->launches++;
         t_asm.push_back(e->timer());
     };
     for (size_t ci = 0; ci < chunks.size(); ci++) {
@@ -730,11 +686,19 @@ static int32_t encode_core(alac_b200_engine *e, const alac_b200_enc_config *cfg,
         Q.jobs = split ? e->jobs.as<FinalJob>() + 2 * jobs_per_slot * slot : nullptr;
         Q.counts = split ? e->job_counts.as<uint32_t>() + 4 * ci : nullptr;
         t_search.push_back(e->timer());
+        // (before, between search and final, after) events of the pair launch and of the mono launch (split form)
+        cudaEvent_t mid[6];
+        for (auto &m : mid) m = e->new_event();
+        const JobLists *Qp = split ? &Q : nullptr;
         switch (cfg->bit_depth) {
-        case 16: launch_search<16>(e, A, mono_mask, pair_mask, packed, wrap, split ? &Q : nullptr); break;
-        case 20: launch_search<20>(e, A, mono_mask, pair_mask, packed, wrap, split ? &Q : nullptr); break;
-        case 24: launch_search<24>(e, A, mono_mask, pair_mask, packed, wrap, split ? &Q : nullptr); break;
-        default: launch_search<32>(e, A, mono_mask, pair_mask, packed, wrap, split ? &Q : nullptr); break;
+        case 16: e->launches += enc_launch_search<16>(cs, A, mono_mask, pair_mask, packed, wrap, Qp, mid); break;
+        case 20: e->launches += enc_launch_search<20>(cs, A, mono_mask, pair_mask, packed, wrap, Qp, mid); break;
+        case 24: e->launches += enc_launch_search<24>(cs, A, mono_mask, pair_mask, packed, wrap, Qp, mid); break;
+        default: e->launches += enc_launch_search<32>(cs, A, mono_mask, pair_mask, packed, wrap, Qp, mid); break;
+        }
+        if (split) {
+            if (pair_mask) for (int i = 0; i < 3; i++) e->t_mid.push_back(mid[i]);
+            if (mono_mask) for (int i = 3; i < 6; i++) e->t_mid.push_back(mid[i]);
         }
         t_search.push_back(e->timer());
         enc_size_kernel<<<(c.cnt + 255) / 256, 256, 0, cs>>>(A.recs, L, cfg->bit_depth, A.pkt_samples + c.p0, c.cnt,
@@ -1112,21 +1076,9 @@ extern "C" int32_t alac_b200_ipc_close(alac_b200_engine *e, void *ptr)
 // ------------------------------------------------------------------------------------------------
 // decode
 // ------------------------------------------------------------------------------------------------
-// The decode kernels keep their tiles / rings in static shared memory and want 8-9 CTAs per SM resident (one
-// wave for the 1-hour workload).  With the default carve-out the driver leaves most of the 228 KB to L1 and only
-// about half of those CTAs fit, so ask for the maximum shared-memory carve-out once per device.
-template <class K> static void prefer_max_shared(K kernel)
-{
-    cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-}
 static void configure_decode_kernels()
 {
-    prefer_max_shared(dec_fused_kernel<16>); prefer_max_shared(dec_fused_kernel<20>);
-    prefer_max_shared(dec_fused_kernel<24>); prefer_max_shared(dec_fused_kernel<32>);
-    prefer_max_shared(dec_finish_kernel<16>); prefer_max_shared(dec_finish_kernel<20>);
-    prefer_max_shared(dec_finish_kernel<24>); prefer_max_shared(dec_finish_kernel<32>);
-    prefer_max_shared(dec_entropy_kernel<16>); prefer_max_shared(dec_entropy_kernel<20>);
-    prefer_max_shared(dec_entropy_kernel<24>); prefer_max_shared(dec_entropy_kernel<32>);
+    dec_configure<16>(); dec_configure<20>(); dec_configure<24>(); dec_configure<32>();
 }
 
 static int32_t decode_core(alac_b200_engine *e, const void *cookie, uint32_t cookie_size, const void *packets,
@@ -1284,41 +1236,21 @@ static int32_t decode_core(alac_b200_engine *e, const void *cookie, uint32_t coo
             if (e->h_totals[ci] * bpf > pcm_cap) { e->err = "pcm capacity exceeded"; return ALAC_B200_PARAM_ERROR; }
         }
         t_dec.push_back(e->timer());
-        const uint32_t lgrid = (c.cnt + kRingStride - 1) / kRingStride;
-        const uint32_t groups_c = (c.cnt + 31) / 32;
-        const uint32_t fgrid = groups_c * nch;
-        // regular mono / stereo groups: entropy and finish warps side by side in one kernel.  Not for the depths with
+        // regular mono / stereo groups go to the fused kernel (entropy and finish warps side by side).  Not for the depths with
         // shift bytes (24 / 32 bit): there the parallel phase re-reads the packet for every sample, which the single
         // finish warp of the fused kernel cannot hide (24-bit: 4.2 ms either way; 32-bit: 5.3 ms fused against 4.8 ms)
         static const int fused_mode = [] { const char *v = getenv("ALAC_B200_FUSED"); return v ? atoi(v) : -1; }();   // developer override: 0 never, 1 always
         A.fused = (nch <= 2 && (fused_mode < 0 ? (depth == 16 || depth == 20) : fused_mode != 0)) ? 1u : 0u;
-        if (A.fused) {
-            switch (depth) {
-            case 16: dec_fused_kernel<16><<<groups_c, 64, 0, cs>>>(A); break;
-            case 20: dec_fused_kernel<20><<<groups_c, 64, 0, cs>>>(A); break;
-            case 24: dec_fused_kernel<24><<<groups_c, 64, 0, cs>>>(A); break;
-            default: dec_fused_kernel<32><<<groups_c, 64, 0, cs>>>(A); break;
-            }
-            e->launches += 1;
-        }
-        e->t_mid.push_back(e->timer());
-        // everything else (multichannel, escapes, other predictor set-ups): the two general kernels; groups the
-        // fused kernel took return at once
+        cudaEvent_t mid[2] = {e->new_event(), e->new_event()};
         switch (depth) {
-        case 16: dec_entropy_kernel<16><<<lgrid, kRingStride, 0, cs>>>(A); break;
-        case 20: dec_entropy_kernel<20><<<lgrid, kRingStride, 0, cs>>>(A); break;
-        case 24: dec_entropy_kernel<24><<<lgrid, kRingStride, 0, cs>>>(A); break;
-        default: dec_entropy_kernel<32><<<lgrid, kRingStride, 0, cs>>>(A); break;
+        case 16: e->launches += dec_launch_main<16>(cs, A, mid); break;
+        case 20: e->launches += dec_launch_main<20>(cs, A, mid); break;
+        case 24: e->launches += dec_launch_main<24>(cs, A, mid); break;
+        default: e->launches += dec_launch_main<32>(cs, A, mid); break;
         }
-        e->t_mid.push_back(e->timer());
-        switch (depth) {
-        case 16: dec_finish_kernel<16><<<fgrid, 64, 0, cs>>>(A); break;
-        case 20: dec_finish_kernel<20><<<fgrid, 64, 0, cs>>>(A); break;
-        case 24: dec_finish_kernel<24><<<fgrid, 64, 0, cs>>>(A); break;
-        default: dec_finish_kernel<32><<<fgrid, 64, 0, cs>>>(A); break;
-        }
+        e->t_mid.push_back(mid[0]);
+        e->t_mid.push_back(mid[1]);
         t_dec.push_back(e->timer());
-        e->launches += 2;
         comp_done.push_back(e->event_on(cs));
     }
     e->cur = nullptr;
@@ -1493,6 +1425,50 @@ extern "C" int32_t alac_b200_decode(alac_b200_engine *e, const void *cookie, uin
                             packet_status, out_mem, out_sample_frames, stats);
     return decode_core(e, cookie, cookie_size, packets, packet_sizes, num_packets, in_mem, pcm_out, pcm_cap, packet_samples,
                        packet_status, out_mem, out_sample_frames, stats);
+}
+
+// ---- asynchronous forms: the synchronous call on a worker thread of the engine ------------------------------------
+extern "C" int32_t alac_b200_encode_submit(alac_b200_engine *e, const alac_b200_enc_config *cfg, const void *pcm,
+                                           uint64_t num_sample_frames, int32_t pcm_mem, const alac_b200_stream *streams,
+                                           uint64_t n_streams, void *packets_out, uint64_t packets_cap, uint32_t *packet_sizes,
+                                           uint64_t sizes_cap, int32_t out_mem, int16_t *coef_state, uint64_t *out_num_packets,
+                                           uint64_t *out_bytes, alac_b200_stats *stats)
+{
+    if (!e || !cfg || e->async_busy) return ALAC_B200_PARAM_ERROR;
+    if (e->worker.joinable()) e->worker.join();
+    e->async_cfg = *cfg;
+    e->async_streams.clear();
+    if (streams) e->async_streams.assign(streams, streams + n_streams);
+    e->async_busy = true;
+    e->worker = std::thread([=] {
+        e->async_rc = alac_b200_encode(e, &e->async_cfg, pcm, num_sample_frames, pcm_mem, streams ? e->async_streams.data() : nullptr, n_streams,
+                                       packets_out, packets_cap, packet_sizes, sizes_cap, out_mem, coef_state, out_num_packets, out_bytes, stats);
+    });
+    return ALAC_B200_OK;
+}
+
+extern "C" int32_t alac_b200_decode_submit(alac_b200_engine *e, const void *cookie, uint32_t cookie_size, const void *packets,
+                                           const uint32_t *packet_sizes, uint64_t num_packets, int32_t in_mem, void *pcm_out,
+                                           uint64_t pcm_cap, uint32_t *packet_samples, int32_t *packet_status, int32_t out_mem,
+                                           uint64_t *out_sample_frames, alac_b200_stats *stats)
+{
+    if (!e || !cookie || e->async_busy) return ALAC_B200_PARAM_ERROR;
+    if (e->worker.joinable()) e->worker.join();
+    e->async_cookie.assign(static_cast<const uint8_t *>(cookie), static_cast<const uint8_t *>(cookie) + cookie_size);
+    e->async_busy = true;
+    e->worker = std::thread([=] {
+        e->async_rc = alac_b200_decode(e, e->async_cookie.data(), cookie_size, packets, packet_sizes, num_packets, in_mem, pcm_out, pcm_cap,
+                                       packet_samples, packet_status, out_mem, out_sample_frames, stats);
+    });
+    return ALAC_B200_OK;
+}
+
+extern "C" int32_t alac_b200_wait(alac_b200_engine *e)
+{
+    if (!e || !e->async_busy) return ALAC_B200_PARAM_ERROR;
+    if (e->worker.joinable()) e->worker.join();
+    e->async_busy = false;
+    return e->async_rc;
 }
 
 // ------------------------------------------------------------------------------------------------

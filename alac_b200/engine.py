@@ -105,6 +105,12 @@ def load_library():
     lib.alac_b200_ber_table_sizes.restype = i32
     lib.alac_b200_ber_table_build.argtypes = [vp, vp, u64, i32, vp, u64, i32, C.POINTER(u64)]
     lib.alac_b200_ber_table_build.restype = i32
+    lib.alac_b200_encode_submit.argtypes = lib.alac_b200_encode.argtypes
+    lib.alac_b200_encode_submit.restype = i32
+    lib.alac_b200_decode_submit.argtypes = lib.alac_b200_decode.argtypes
+    lib.alac_b200_decode_submit.restype = i32
+    lib.alac_b200_wait.argtypes = [vp]
+    lib.alac_b200_wait.restype = i32
     lib.alac_b200_engine_create_multi.argtypes = [C.POINTER(i32), u32, C.POINTER(vp)]
     lib.alac_b200_engine_create_multi.restype = i32
     lib.alac_b200_engine_num_devices.argtypes = [vp]
@@ -332,8 +338,17 @@ class Engine:
             self.set_stream(torch.cuda.current_stream(tensor.device).cuda_stream or CUDA_STREAM_LEGACY)
 
     # ------------------------------------------------------------------ encode
+    def encode_submit(self, pcm, cfg: EncoderConfig, **kw):
+        """Asynchronous encode (alac_b200_encode_submit): returns a function that waits for the call and gives the
+        EncodeResult.  One call per engine may be in flight; the buffers must stay alive until then."""
+        return self.encode(pcm, cfg, _submit=True, **kw)
+
+    def decode_submit(self, cookie: bytes, packets, sizes, **kw):
+        """Asynchronous decode (alac_b200_decode_submit): returns a function that waits and gives the DecodeResult."""
+        return self.decode(cookie, packets, sizes, _submit=True, **kw)
+
     def encode(self, pcm, cfg: EncoderConfig, streams: Optional[Sequence[Tuple[int, int]]] = None,
-               coef_state: Optional[np.ndarray] = None, out=None, out_sizes=None) -> EncodeResult:
+               coef_state: Optional[np.ndarray] = None, out=None, out_sizes=None, _submit: bool = False) -> EncodeResult:
         """Encode interleaved PCM (uint8 view; numpy = host, torch CUDA tensor = device).
 
         streams: optional [(first_sample_frame, num_sample_frames), ...]; default one stream over
@@ -377,13 +392,24 @@ class Engine:
                 raise ValueError("coef_state must be contiguous int16 [n_streams, 256]")
             state_ptr = coef_state.ctypes.data
         npk, nb, stats = C.c_uint64(0), C.c_uint64(0), Stats()
-        st = self.lib.alac_b200_encode(self.h, C.byref(ccfg), C.c_void_p(ptr), nsf, mem, arr, n_streams,
-                                       C.c_void_p(optr), ocap, C.c_void_p(sptr), scap // 4, mem,
-                                       C.c_void_p(state_ptr) if state_ptr else None,
-                                       C.byref(npk), C.byref(nb), C.byref(stats))
+        fn = self.lib.alac_b200_encode_submit if _submit else self.lib.alac_b200_encode
+        st = fn(self.h, C.byref(ccfg), C.c_void_p(ptr), nsf, mem, arr, n_streams,
+                C.c_void_p(optr), ocap, C.c_void_p(sptr), scap // 4, mem,
+                C.c_void_p(state_ptr) if state_ptr else None,
+                C.byref(npk), C.byref(nb), C.byref(stats))
         if st:
             raise AlacError(st, self._err())
-        return EncodeResult(magic_cookie(cfg), out[:nb.value], out_sizes[:npk.value], npk.value, nb.value, stats.as_dict())
+
+        def finish(wait: bool = True):
+            if wait:
+                rc = self.lib.alac_b200_wait(self.h)
+                if rc:
+                    raise AlacError(rc, self._err())
+            keep = (pcm, arr, ccfg, coef_state)     # (alive until the call has ended)
+            del keep
+            return EncodeResult(magic_cookie(cfg), out[:nb.value], out_sizes[:npk.value], npk.value, nb.value, stats.as_dict())
+
+        return finish if _submit else finish(False)
 
     # ------------------------------------------------------------------ CAF packet table
     def ber_table_sizes(self, table, data_bytes: int):
@@ -421,7 +447,7 @@ class Engine:
         return out[:nb.value]
 
     # ------------------------------------------------------------------ decode
-    def decode(self, cookie: bytes, packets, sizes, out=None, raise_on_error: bool = True) -> DecodeResult:
+    def decode(self, cookie: bytes, packets, sizes, out=None, raise_on_error: bool = True, _submit: bool = False) -> DecodeResult:
         """Decode packets laid back to back (uint8) with per-packet sizes (uint32/int32)."""
         cfgd = parse_cookie(cookie)
         bpf = {16: 2, 20: 3, 24: 3, 32: 4}[cfgd["bit_depth"]] * cfgd["num_channels"]
@@ -451,9 +477,20 @@ class Engine:
             raise ValueError("output must live in the same memory kind as the input")
         ck = (C.c_uint8 * len(cookie)).from_buffer_copy(cookie)
         nsf, stats = C.c_uint64(0), Stats()
-        st = self.lib.alac_b200_decode(self.h, ck, len(cookie), C.c_void_p(pptr), C.c_void_p(sptr), n, mem,
-                                       C.c_void_p(optr), ocap, C.c_void_p(_buf(psamp)[0]), C.c_void_p(_buf(pstat)[0]), mem,
-                                       C.byref(nsf), C.byref(stats))
-        if st not in (ALAC_OK, ALAC_PARAM_ERROR) or (st and raise_on_error):
+        fn = self.lib.alac_b200_decode_submit if _submit else self.lib.alac_b200_decode
+        st = fn(self.h, ck, len(cookie), C.c_void_p(pptr), C.c_void_p(sptr), n, mem,
+                C.c_void_p(optr), ocap, C.c_void_p(_buf(psamp)[0]), C.c_void_p(_buf(pstat)[0]), mem,
+                C.byref(nsf), C.byref(stats))
+        if _submit and st:
             raise AlacError(st, self._err())
-        return DecodeResult(out[:nsf.value * bpf], nsf.value, psamp[:n], pstat[:n], st, stats.as_dict())
+
+        def finish(rc):
+            if rc not in (ALAC_OK, ALAC_PARAM_ERROR) or (rc and raise_on_error):
+                raise AlacError(rc, self._err())
+            keep = (packets, sizes, ck)             # (alive until the call has ended)
+            del keep
+            return DecodeResult(out[:nsf.value * bpf], nsf.value, psamp[:n], pstat[:n], rc, stats.as_dict())
+
+        if _submit:
+            return lambda: finish(self.lib.alac_b200_wait(self.h))
+        return finish(st)

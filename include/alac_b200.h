@@ -196,6 +196,30 @@ int32_t alac_b200_decode(alac_b200_engine *engine, const void *cookie, uint32_t 
                          uint64_t *out_sample_frames,
                          alac_b200_stats *stats);
 
+/* ---- asynchronous forms ------------------------------------------------------------------------------------------
+ * Same arguments as alac_b200_encode / alac_b200_decode; the call runs on a worker thread of the engine and
+ * alac_b200_wait returns its status (every output, *out_* word and stats struct is valid only after the wait).
+ * One call per engine may be in flight; the config, stream list and cookie are copied at submit, the data buffers must
+ * stay valid until the wait.  Two engines on one GPU thereby overlap an encode with a decode: the PCM going up for the
+ * next encode shares the PCIe link with the PCM coming down from the previous decode (the link is full duplex), which a
+ * strictly alternating caller of the synchronous forms cannot do. */
+int32_t alac_b200_encode_submit(alac_b200_engine *engine, const alac_b200_enc_config *cfg,
+                                const void *pcm, uint64_t num_sample_frames, int32_t pcm_mem,
+                                const alac_b200_stream *streams, uint64_t n_streams,
+                                void *packets_out, uint64_t packets_cap,
+                                uint32_t *packet_sizes, uint64_t sizes_cap, int32_t out_mem,
+                                int16_t *coef_state,
+                                uint64_t *out_num_packets, uint64_t *out_bytes,
+                                alac_b200_stats *stats);
+int32_t alac_b200_decode_submit(alac_b200_engine *engine, const void *cookie, uint32_t cookie_size,
+                                const void *packets, const uint32_t *packet_sizes, uint64_t num_packets,
+                                int32_t in_mem,
+                                void *pcm_out, uint64_t pcm_cap,
+                                uint32_t *packet_samples, int32_t *packet_status, int32_t out_mem,
+                                uint64_t *out_sample_frames,
+                                alac_b200_stats *stats);
+int32_t alac_b200_wait(alac_b200_engine *engine);
+
 /* ---- CAF packet table on the device ------------------------------------------------ */
 /*
  * Turns the BER-coded size table of a CAF 'pakt' chunk (convert-utility/CAFFileALAC.cpp:189-258) into

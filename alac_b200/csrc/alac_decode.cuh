@@ -633,22 +633,6 @@ __global__ void __launch_bounds__(64) dec_finish_kernel(DecArgs A)
 // "Regular" (classes 0..3 of dec_header_kernel) means: exactly one element that matches the channel count, compressed,
 // predictor mode 0, denShift 9, 4 or 8 taps.  Every lane of the entropy warp then executes the same tile loop, which the
 // barrier protocol needs; groups holding any other packet are left to dec_entropy_kernel + dec_finish_kernel.
-enum : uint32_t { BAR_FULL0 = 1, BAR_EMPTY0 = 3 };      // + buffer index
-
-// Barrier numbers are immediates (a register operand makes ptxas reserve all 16 barriers for the CTA, which caps
-// the SM at 4 resident CTAs); `second` selects buffer 1.
-template <uint32_t ID> __device__ __forceinline__ void bar_sync64() { asm volatile("bar.sync %0, 64;" ::"n"(ID) : "memory"); }
-template <uint32_t ID> __device__ __forceinline__ void bar_arrive64() { asm volatile("bar.arrive %0, 64;" ::"n"(ID) : "memory"); }
-template <uint32_t ID0> __device__ __forceinline__ void named_sync(bool second)
-{
-    if (second) bar_sync64<ID0 + 1>(); else bar_sync64<ID0>();
-}
-template <uint32_t ID0> __device__ __forceinline__ void named_arrive(bool second)
-{
-    __threadfence_block();      // what this warp wrote to the buffer is visible to the warp that waits
-    if (second) bar_arrive64<ID0 + 1>(); else bar_arrive64<ID0>();
-}
-
 template <int DEPTH>
 __global__ void __launch_bounds__(64) dec_fused_kernel(DecArgs A)
 {

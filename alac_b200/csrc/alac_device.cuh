@@ -548,4 +548,22 @@ struct AgDec {
     }
 };
 
+// ---- named barriers: FULL / EMPTY hand-off of shared-memory tiles between the two warps of a 64-thread CTA ----------
+enum : uint32_t { BAR_FULL0 = 1, BAR_EMPTY0 = 3 };      // + buffer index
+
+// Barrier numbers are immediates (a register operand makes ptxas reserve all 16 barriers for the CTA, which caps
+// the SM at 4 resident CTAs); `second` selects buffer 1.
+template <uint32_t ID> __device__ __forceinline__ void bar_sync64() { asm volatile("bar.sync %0, 64;" ::"n"(ID) : "memory"); }
+template <uint32_t ID> __device__ __forceinline__ void bar_arrive64() { asm volatile("bar.arrive %0, 64;" ::"n"(ID) : "memory"); }
+template <uint32_t ID0> __device__ __forceinline__ void named_sync(bool second)
+{
+    if (second) bar_sync64<ID0 + 1>(); else bar_sync64<ID0>();
+}
+template <uint32_t ID0> __device__ __forceinline__ void named_arrive(bool second)
+{
+    __threadfence_block();      // what this warp wrote to the buffer is visible to the warp that waits
+    if (second) bar_arrive64<ID0 + 1>(); else bar_arrive64<ID0>();
+}
+
+
 }  // namespace alacb

@@ -16,6 +16,7 @@
 //                       escape samples into the packet at its scanned offset (32-bit stores).
 #pragma once
 #include "alac_device.cuh"
+#include <type_traits>
 
 namespace alacb {
 
@@ -688,6 +689,264 @@ enc_final_kernel(EncArgs A, JobLists Q, uint32_t ctas_per_list)
     *J.bits_out = es.ag.bits;
 }
 
+// ---- two-warp form of the final pass: predictor warp -> residual tiles -> Golomb warp ------------------------------
+// One lane per job as in enc_final_kernel, but the two serial chains of a job -- the sign-LMS predictor and the
+// adaptive Golomb coder -- run on two warps of a 64-thread CTA, lane = job in both, handing tiles of 32 residuals per
+// lane through shared memory (FULL / EMPTY named barriers per buffer, as dec_fused_kernel does on the decode side).
+// The per-sample critical path becomes max(predictor, coder) instead of their sum, twice as many warps are in
+// flight, and each warp's loop body is about half as long.
+//
+// "Dense" elements only: a mono or stereo stream whose element is the whole sample-frame (no other channels in
+// between) and whose packets start on 4-byte boundaries.  Then a lane's PCM is one contiguous run of 32-bit words and
+// streams through a word ring in shared memory -- word w of lane l at [w mod kQuadRingWords][l], so every warp access
+// is conflict-free -- filled by 4-byte cp.async kQuadAhead quads (4 sample-frames each) ahead of the arithmetic.
+// 24-bit frames (6 bytes) unpack from the ring with one PRMT per sample (bytes o+1, o+2 and the sign of o+2: the
+// predictor input is sample >> 8); the per-sample byte loads of the generic path are gone.
+template <int DEPTH, bool STEREO> struct DenseElem {
+    static constexpr uint32_t kFrameBytes = DepthTraits<DEPTH>::kBytes * (STEREO ? 2u : 1u);
+    static constexpr uint32_t kQuadWords = kFrameBytes;          // 4 sample-frames = kFrameBytes 32-bit words
+};
+constexpr uint32_t kQuadRingWords = 32;     // per lane; >= (kQuadAhead + 1) quads of the widest element (8 words)
+constexpr uint32_t kQuadAhead = 3;
+constexpr uint32_t kEncTileRows = 32;
+
+// sign-extended 16-bit value at byte offset o (0..3) + 1 of the word pair (lo, hi): bytes o+1, o+2 -> (b2 << 8 | b1)
+template <uint32_t O> __device__ __forceinline__ int32_t prmt_s16_at(uint32_t lo, uint32_t hi)
+{
+    constexpr uint32_t b1 = O + 1u, b2 = O + 2u;                 // byte indices into {lo: 0..3, hi: 4..7}
+    constexpr uint32_t sel = b1 | (b2 << 4) | ((b2 | 8u) << 8) | ((b2 | 8u) << 12);     // nibble msb = replicate the byte's sign
+    uint32_t d;
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(lo), "r"(hi), "n"(sel));       // (__byte_perm ignores the msb of a nibble)
+    return (int32_t)d;
+}
+// 24-bit container at byte offset O of the word pair, as a left-justified 32-bit word (sample << 8)
+template <uint32_t O> __device__ __forceinline__ uint32_t prmt_u24hi_at(uint32_t lo, uint32_t hi)
+{
+    constexpr uint32_t sel = (O << 4) | ((O + 1u) << 8) | ((O + 2u) << 12);   // byte 0 <- lo.b0 (garbage, shifted out below)
+    return __byte_perm(lo, hi, sel) & 0xffffff00u;
+}
+
+// the four (left, right) -- or four mono -- samples of a quad, after the depth's shift (what the predictor sees)
+template <int DEPTH, bool STEREO>
+__device__ __forceinline__ void unpack_quad(const uint32_t (&w)[DenseElem<DEPTH, STEREO>::kQuadWords], int32_t (&l)[4], int32_t (&r)[4])
+{
+    constexpr uint32_t sh = DepthTraits<DEPTH>::kShift;
+    if (DEPTH == 16) {
+        if (STEREO) {
+#pragma unroll
+            for (int i = 0; i < 4; i++) { l[i] = (int32_t)(int16_t)(w[i] & 0xffffu); r[i] = (int32_t)w[i] >> 16; }
+        } else {
+            l[0] = (int32_t)(int16_t)(w[0] & 0xffffu); l[1] = (int32_t)w[0] >> 16;
+            l[2] = (int32_t)(int16_t)(w[1] & 0xffffu); l[3] = (int32_t)w[1] >> 16;
+        }
+    } else if (DEPTH == 32) {
+        if (STEREO) {
+#pragma unroll
+            for (int i = 0; i < 4; i++) { l[i] = (int32_t)w[2 * i] >> sh; r[i] = (int32_t)w[2 * i + 1] >> sh; }
+        } else {
+#pragma unroll
+            for (int i = 0; i < 4; i++) l[i] = (int32_t)w[i] >> sh;
+        }
+    } else if (DEPTH == 24) {
+        // sample >> 8 = the sign-extended 16-bit value at byte offset + 1
+        if (STEREO) {           // L at bytes 0, 6, 12, 18; R at 3, 9, 15, 21 of the quad's 6 words
+            l[0] = prmt_s16_at<0>(w[0], w[1]); r[0] = prmt_s16_at<3>(w[0], w[1]);
+            l[1] = prmt_s16_at<2>(w[1], w[2]); r[1] = prmt_s16_at<1>(w[2], w[3]);
+            l[2] = prmt_s16_at<0>(w[3], w[4]); r[2] = prmt_s16_at<3>(w[3], w[4]);
+            l[3] = prmt_s16_at<2>(w[4], w[5]); r[3] = prmt_s16_at<1>(w[5], w[5]);
+        } else {                // samples at bytes 0, 3, 6, 9 of the quad's 3 words
+            l[0] = prmt_s16_at<0>(w[0], w[1]); l[1] = prmt_s16_at<3>(w[0], w[1]);
+            l[2] = prmt_s16_at<2>(w[1], w[2]); l[3] = prmt_s16_at<1>(w[2], w[2]);
+        }
+    } else {                    // 20-bit, left-justified in 3 bytes: (w24 << 8) >> 12
+        if (STEREO) {
+            l[0] = (int32_t)prmt_u24hi_at<0>(w[0], w[1]) >> 12; r[0] = (int32_t)prmt_u24hi_at<3>(w[0], w[1]) >> 12;
+            l[1] = (int32_t)prmt_u24hi_at<2>(w[1], w[2]) >> 12; r[1] = (int32_t)prmt_u24hi_at<1>(w[2], w[3]) >> 12;
+            l[2] = (int32_t)prmt_u24hi_at<0>(w[3], w[4]) >> 12; r[2] = (int32_t)prmt_u24hi_at<3>(w[3], w[4]) >> 12;
+            l[3] = (int32_t)prmt_u24hi_at<2>(w[4], w[5]) >> 12; r[3] = (int32_t)prmt_u24hi_at<1>(w[5], w[5]) >> 12;
+        } else {
+            l[0] = (int32_t)prmt_u24hi_at<0>(w[0], w[1]) >> 12; l[1] = (int32_t)prmt_u24hi_at<3>(w[0], w[1]) >> 12;
+            l[2] = (int32_t)prmt_u24hi_at<2>(w[1], w[2]) >> 12; l[3] = (int32_t)prmt_u24hi_at<1>(w[2], w[2]) >> 12;
+        }
+    }
+}
+
+// One lane's word ring over its packet's PCM (see above).
+template <int DEPTH, bool STEREO>
+struct QuadRing {
+    static constexpr uint32_t WQ = DenseElem<DEPTH, STEREO>::kQuadWords;
+    const uint32_t *base;       // word 0 = sample-frame 0 of the packet (4-byte aligned)
+    uint32_t ring;              // shared-memory address of this lane's column
+    uint32_t words;             // words that hold the packet's n frames, rounded up
+    uint32_t last_bytes;        // packet bytes inside the last word (1..4)
+    __device__ __forceinline__ void start(const uint8_t *packet, uint32_t n, uint32_t *ring_column)
+    {
+        base = reinterpret_cast<const uint32_t *>(packet);
+        ring = (uint32_t)__cvta_generic_to_shared(ring_column);
+        const uint32_t nbytes = n * DenseElem<DEPTH, STEREO>::kFrameBytes;
+        words = (nbytes + 3u) >> 2;
+        last_bytes = ((nbytes - 1u) & 3u) + 1u;
+    }
+    __device__ __forceinline__ uint32_t slot(uint32_t w) const { return ring + (w & (kQuadRingWords - 1u)) * 128u; }
+    // request the WQ words of quad q; words past the packet read nothing and arrive as zero
+    __device__ __forceinline__ void request(uint32_t q)
+    {
+#pragma unroll
+        for (uint32_t i = 0; i < WQ; i++) {
+            const uint32_t w = q * WQ + i;
+            const bool in = w < words;
+            cp_async_word(slot(w), base + (in ? w : 0u), in ? (w + 1u == words ? last_bytes : 4u) : 0u);
+        }
+        cp_async_commit();
+    }
+    __device__ __forceinline__ void read(uint32_t q, uint32_t (&w)[WQ]) const
+    {
+#pragma unroll
+        for (uint32_t i = 0; i < WQ; i++) w[i] = lds_u32(slot(q * WQ + i));
+    }
+};
+
+// SPLIT = true: the two-warp form (64-thread CTAs).  SPLIT = false: the same dense PCM path with predictor and coder
+// on ONE warp (32-thread CTAs, no residual tiles, no barriers): once a launch holds several waves of jobs the GPU is
+// throughput-bound, the coder warp's idle half only costs occupancy, and the one-warp form is the faster one
+// (10-hour 24/96 corpus: 44 ms against 52 ms; 1-hour 16/44.1: 2.9 ms against 2.6 ms).  The engine picks by job count.
+template <int DEPTH, bool STEREO, bool WRAP, bool SPLIT>
+__global__ void __launch_bounds__(SPLIT ? 64 : 32, SPLIT ? 12 : 24)
+enc_final2_kernel(EncArgs A, JobLists Q, uint32_t ctas_per_list)
+{
+    __shared__ uint32_t s_ring[kQuadRingWords][32];
+    __shared__ int32_t s_res[SPLIT ? 2 : 1][SPLIT ? kEncTileRows : 1][32];
+
+    const uint32_t w = threadIdx.x >> 5, lane = threadIdx.x & 31u;
+    const uint32_t list = blockIdx.x < ctas_per_list ? 1u : 0u;
+    const uint32_t idx = (blockIdx.x - (list ? 0u : ctas_per_list)) * 32u + lane;
+    const uint32_t count = Q.counts[list];
+    if ((blockIdx.x - (list ? 0u : ctas_per_list)) * 32u >= count) return;     // CTA-uniform
+    const bool have = idx < count;
+    FinalJob J;
+    if (have) J = Q.jobs[(size_t)list * Q.max_jobs + idx];
+    else { J.base = nullptr; J.slab = nullptr; J.bits_out = nullptr; J.n = 0; J.flags = 0; }
+    constexpr uint32_t shift = DepthTraits<DEPTH>::kShift;
+    const uint32_t chan_bits = DEPTH - shift + (STEREO ? 1u : 0u);
+    const uint32_t chanshift = 32u - chan_bits;
+    const uint32_t n = J.n;
+    const uint32_t n_max = __reduce_max_sync(0xffffffffu, n);
+    const uint32_t tiles = (n_max + kEncTileRows - 1u) / kEncTileRows;
+
+    EmitSink es;
+    es.ag.start(n);
+    es.bit_size = chan_bits;
+    es.bits.start(J.slab, A.cap_words);
+    if (SPLIT && w == 1) {
+        // ================= Golomb warp =================
+        for (uint32_t b = 0; b < min(tiles, 2u); b++) named_arrive<BAR_EMPTY0>(b != 0);     // both buffers start empty
+        for (uint32_t t = 0; t < tiles; t++) {
+            const uint32_t b = t & 1u;
+            named_sync<BAR_FULL0>(b != 0);
+            const int32_t *col = &s_res[SPLIT ? b : 0][0][lane];
+            const uint32_t j0 = t * kEncTileRows;
+            if (j0 + kEncTileRows <= n) {
+#pragma unroll 2
+                for (uint32_t r = 0; r < kEncTileRows; r++) ag_put<true>(es.ag, col[r * 32u], chan_bits, es.bits);
+            } else {
+                for (uint32_t r = 0; r < kEncTileRows && j0 + r < n; r++) ag_put<true>(es.ag, col[r * 32u], chan_bits, es.bits);
+            }
+            __syncwarp();
+            if (t + 2 < tiles) named_arrive<BAR_EMPTY0>(b != 0);
+        }
+        if (have) {
+            es.bits.finish();
+            *J.bits_out = es.ag.bits;
+        }
+        return;
+    }
+
+    // ================= predictor warp (SPLIT) / the whole pass (one-warp form) =================
+    MixSrc<DEPTH, STEREO, true> src;        // the scalar path for the warm-up samples and the odd frames at either end
+    src.base = J.base; src.stride = DenseElem<DEPTH, STEREO>::kFrameBytes;
+    src.set_mix((int32_t)(J.flags >> 1), (J.flags & 1u) != 0);
+    src.valid = n;
+    QuadRing<DEPTH, STEREO> ring;
+    ring.start(have ? J.base : reinterpret_cast<const uint8_t *>(s_ring), n, &s_ring[0][lane]);
+    const uint32_t nq = n >> 2;             // whole quads of the packet
+    auto run = [&](auto taps_tag) {
+        constexpr int TAPS = decltype(taps_tag)::value;
+        int32_t a[TAPS], hist[TAPS + 1];
+#pragma unroll
+        for (int k = 0; k < TAPS; k++) a[k] = J.coef[k];
+#pragma unroll
+        for (int k = 0; k <= TAPS; k++) hist[k] = 0;
+        // quads q_first .. q_first + kQuadAhead - 1 are requested up front; the warm-up samples and the frames up to
+        // the first quad boundary after them go through the scalar path
+        constexpr uint32_t q_first = (TAPS + 1 + 3) / 4;         // first quad that is all predictor steps (3 for 8 taps, 2 for 4)
+#pragma unroll
+        for (uint32_t d = 0; d < kQuadAhead; d++) ring.request(q_first + d);
+        int32_t *col = &s_res[0][0][lane];
+        // residual of sample-frame j0 + r: to the tile (two-warp form) or straight into the coder
+        auto put = [&](uint32_t r, uint32_t j, int32_t err) {
+            if (SPLIT) col[r * 32u] = err;
+            else if (j < n) ag_put<true>(es.ag, err, chan_bits, es.bits);
+        };
+        int32_t prev = 0;
+        for (uint32_t t = 0; t < tiles; t++) {
+            const uint32_t b = t & 1u;
+            if (SPLIT) {
+                named_sync<BAR_EMPTY0>(b != 0);
+                col = &s_res[SPLIT ? b : 0][0][lane];
+            }
+            const uint32_t j0 = t * kEncTileRows;
+            uint32_t r = 0;
+            if (t == 0) {
+                // warm-up: pc[0] = x[0], pc[1..TAPS] = first differences, written regardless of n (dp_enc.c:108-112)
+                prev = src.get(0);
+                put(0, 0, prev);
+                hist[TAPS] = prev;
+#pragma unroll
+                for (int j = 1; j <= TAPS; j++) {
+                    const int32_t x = src.get((uint32_t)j);
+                    put((uint32_t)j, (uint32_t)j, sext_bits(x - prev, chanshift));
+                    hist[TAPS - j] = x;
+                    prev = x;
+                }
+                for (r = TAPS + 1; r < q_first * 4u && r < n; r++) put(r, r, predict_enc_step<TAPS, WRAP>(src.get(r), hist, a, chanshift));
+                r = q_first * 4u;
+            }
+            // whole quads of this tile
+            for (; r < kEncTileRows; r += 4) {
+                const uint32_t q = (j0 + r) >> 2;
+                if (q < nq) {
+                    ring.request(q + kQuadAhead);
+                    cp_async_wait<kQuadAhead>();            // quad q is in
+                    uint32_t wq[QuadRing<DEPTH, STEREO>::WQ];
+                    ring.read(q, wq);
+                    int32_t l[4], rr[4];
+                    unpack_quad<DEPTH, STEREO>(wq, l, rr);
+#pragma unroll
+                    for (int i = 0; i < 4; i++) {
+                        const int32_t x = STEREO ? ((src.cl * l[i] + src.cr * rr[i]) >> src.sh_mix) : l[i];
+                        put(r + i, j0 + r + i, predict_enc_step<TAPS, WRAP>(x, hist, a, chanshift));
+                    }
+                } else {
+                    // the odd frames after the last whole quad (and nothing at all past n)
+                    for (uint32_t i = 0; i < 4 && j0 + r + i < n; i++)
+                        put(r + i, j0 + r + i, predict_enc_step<TAPS, WRAP>(src.get(j0 + r + i), hist, a, chanshift));
+                }
+            }
+            if (SPLIT) {
+                __syncwarp();
+                named_arrive<BAR_FULL0>(b != 0);
+            }
+        }
+        cp_async_wait<0>();
+    };
+    if (list == 0) run(std::integral_constant<int, 4>{});
+    else run(std::integral_constant<int, 8>{});
+    if (!SPLIT && have) {
+        es.bits.finish();
+        *J.bits_out = es.ag.bits;
+    }
+}
+
 // ---- packet sizes ------------------------------------------------------------------------------------
 // Finishes each element record (post-check of codec/ALACEncoder.cu:537-543 / :952-958, fast mode
 // :703-725: a compressed element that is not smaller than the escape form is sent as escape) and
@@ -1131,7 +1390,8 @@ __global__ void __launch_bounds__(kAsmWarps * 32) enc_assemble_kernel(AsmArgs A)
 // ev: optional events recorded around the kernels -- {before, between search and final, after} for the pair launch,
 // then the same three for the mono launch (split form only).  Returns the number of kernels launched.
 template <int DEPTH, bool PACKED, bool WRAP>
-static uint32_t enc_launch_search_v(cudaStream_t s, const EncArgs &A, uint32_t mono_mask, uint32_t pair_mask, const JobLists *split, cudaEvent_t *ev)
+static uint32_t enc_launch_search_v(cudaStream_t s, const EncArgs &A, uint32_t mono_mask, uint32_t pair_mask, const JobLists *split, cudaEvent_t *ev,
+                                    int dense)
 {
     const uint32_t pairs = __builtin_popcount(pair_mask), monos = __builtin_popcount(mono_mask);
     uint32_t launches = 0;
@@ -1142,7 +1402,9 @@ static uint32_t enc_launch_search_v(cudaStream_t s, const EncArgs &A, uint32_t m
             if (ev) cudaEventRecord(ev[0], s);
             enc_search_split_kernel<DEPTH, true, PACKED, WRAP><<<ctas, 32, 0, s>>>(A, pairs, pair_mask, *split);
             if (ev) cudaEventRecord(ev[1], s);
-            enc_final_kernel<DEPTH, true, PACKED, WRAP><<<2 * ctas, 32, 0, s>>>(A, *split, ctas);
+            if (dense == 2) enc_final2_kernel<DEPTH, true, WRAP, true><<<2 * ctas, 64, 0, s>>>(A, *split, ctas);
+            else if (dense) enc_final2_kernel<DEPTH, true, WRAP, false><<<2 * ctas, 32, 0, s>>>(A, *split, ctas);
+            else enc_final_kernel<DEPTH, true, PACKED, WRAP><<<2 * ctas, 32, 0, s>>>(A, *split, ctas);
             if (ev) cudaEventRecord(ev[2], s);
             launches += 2;
         } else {
@@ -1160,7 +1422,9 @@ static uint32_t enc_launch_search_v(cudaStream_t s, const EncArgs &A, uint32_t m
             if (ev) cudaEventRecord(ev[3], s);
             enc_search_split_kernel<DEPTH, false, false, WRAP><<<ctas, 32, 0, s>>>(A, monos, mono_mask, Qm);
             if (ev) cudaEventRecord(ev[4], s);
-            enc_final_kernel<DEPTH, false, false, WRAP><<<2 * ctas, 32, 0, s>>>(A, Qm, ctas);
+            if (dense == 2) enc_final2_kernel<DEPTH, false, WRAP, true><<<2 * ctas, 64, 0, s>>>(A, Qm, ctas);
+            else if (dense) enc_final2_kernel<DEPTH, false, WRAP, false><<<2 * ctas, 32, 0, s>>>(A, Qm, ctas);
+            else enc_final_kernel<DEPTH, false, false, WRAP><<<2 * ctas, 32, 0, s>>>(A, Qm, ctas);
             if (ev) cudaEventRecord(ev[5], s);
             launches += 2;
         } else {
@@ -1173,15 +1437,17 @@ static uint32_t enc_launch_search_v(cudaStream_t s, const EncArgs &A, uint32_t m
 }
 
 // packed: pure stereo PCM at 8-byte alignment (one wide load per sample-frame);
-// wrap: the int16 coefficient range could be left during a segment, so every update re-wraps
+// wrap: the int16 coefficient range could be left during a segment, so every update re-wraps;
+// dense: 1 or 2 = a mono or stereo stream (the element is the whole sample-frame) with every packet on a 4-byte boundary: the
+//        split form then runs its final pass through the word ring, 2 = as the two-warp kernel (launches that do not fill the GPU)
 template <int DEPTH>
 uint32_t enc_launch_search(cudaStream_t s, const EncArgs &A, uint32_t mono_mask, uint32_t pair_mask, bool packed, bool wrap,
-                           const JobLists *split, cudaEvent_t *ev)
+                           const JobLists *split, cudaEvent_t *ev, int dense)
 {
-    if (packed) return wrap ? enc_launch_search_v<DEPTH, true, true>(s, A, mono_mask, pair_mask, split, ev)
-                            : enc_launch_search_v<DEPTH, true, false>(s, A, mono_mask, pair_mask, split, ev);
-    return wrap ? enc_launch_search_v<DEPTH, false, true>(s, A, mono_mask, pair_mask, split, ev)
-                : enc_launch_search_v<DEPTH, false, false>(s, A, mono_mask, pair_mask, split, ev);
+    if (packed) return wrap ? enc_launch_search_v<DEPTH, true, true>(s, A, mono_mask, pair_mask, split, ev, dense)
+                            : enc_launch_search_v<DEPTH, true, false>(s, A, mono_mask, pair_mask, split, ev, dense);
+    return wrap ? enc_launch_search_v<DEPTH, false, true>(s, A, mono_mask, pair_mask, split, ev, dense)
+                : enc_launch_search_v<DEPTH, false, false>(s, A, mono_mask, pair_mask, split, ev, dense);
 }
 
 template <int DEPTH>
@@ -1192,7 +1458,7 @@ void enc_launch_assemble(cudaStream_t s, const AsmArgs &A)
 
 #ifndef ALAC_INSTANTIATE_DEPTH
 #define ALAC_ENC_EXTERN(D)                                                                                                            \
-    extern template uint32_t enc_launch_search<D>(cudaStream_t, const EncArgs &, uint32_t, uint32_t, bool, bool, const JobLists *, cudaEvent_t *); \
+    extern template uint32_t enc_launch_search<D>(cudaStream_t, const EncArgs &, uint32_t, uint32_t, bool, bool, const JobLists *, cudaEvent_t *, int); \
     extern template void enc_launch_assemble<D>(cudaStream_t, const AsmArgs &);
 ALAC_ENC_EXTERN(16) ALAC_ENC_EXTERN(20) ALAC_ENC_EXTERN(24) ALAC_ENC_EXTERN(32)
 #undef ALAC_ENC_EXTERN

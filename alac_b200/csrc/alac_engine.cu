@@ -620,6 +620,13 @@ static int32_t encode_core(alac_b200_engine *e, const alac_b200_enc_config *cfg,
     // starting from init_coefs (|a| <= 1216) the int16 range cannot be left within K frames if this holds
     const bool wrap = coef_state != nullptr || K == 0 || (uint64_t)K * 2u * F + 1216u > 32767u;
     const bool packed = cfg->channels == 2 && (reinterpret_cast<uintptr_t>(d_pcm) & 7u) == 0;
+    // dense: a mono or stereo stream whose packets all start on 4-byte boundaries (see enc_final2_kernel)
+    bool dense = cfg->channels <= 2 && (reinterpret_cast<uintptr_t>(d_pcm) & 3u) == 0 && (F == 1 || ((uint64_t)F * bpf) % 4 == 0 || P == n_streams);
+    for (uint64_t s = 0; s < n_streams && dense; s++) dense = (streams[s].first_sample_frame * bpf) % 4 == 0;
+    if (dense && ((uint64_t)F * bpf) % 4 != 0) for (uint32_t p = 0; p < P && dense; p++) dense = (h_pkt_frame[p] * bpf) % 4 == 0;
+    // developer override: 0 = the generic final pass, 1 = dense one-warp form, 2 = dense two-warp form, default = by job count
+    static const int final2_mode = [] { const char *v = getenv("ALAC_B200_FINAL2"); return v ? atoi(v) : -1; }();
+    if (final2_mode == 0) dense = false;
     unsigned long long *d_escapes = e->counters.as<unsigned long long>();
     uint32_t *d_max = reinterpret_cast<uint32_t *>(e->counters.as<uint8_t>() + 8);
     uint64_t *d_base = reinterpret_cast<uint64_t *>(e->counters.as<uint8_t>() + 32);       // placed: where this rank's block starts
@@ -685,16 +692,19 @@ static int32_t encode_core(alac_b200_engine *e, const alac_b200_enc_config *cfg,
         Q.max_jobs = (uint32_t)jobs_per_slot;
         Q.jobs = split ? e->jobs.as<FinalJob>() + 2 * jobs_per_slot * slot : nullptr;
         Q.counts = split ? e->job_counts.as<uint32_t>() + 4 * ci : nullptr;
+        // two-warp final pass while the launch's jobs do not fill the GPU (about one wave of one-warp CTAs: 148 SMs x 24 x 32 jobs)
+        const uint64_t jobs_in_launch = (uint64_t)c.cnt * L.chains_per_packet;
+        const int dense_form = !dense ? 0 : final2_mode > 0 ? final2_mode : (jobs_in_launch <= 148ull * 24 * 32 ? 2 : 1);
         t_search.push_back(e->timer());
         // (before, between search and final, after) events of the pair launch and of the mono launch (split form)
         cudaEvent_t mid[6];
         for (auto &m : mid) m = e->new_event();
         const JobLists *Qp = split ? &Q : nullptr;
         switch (cfg->bit_depth) {
-        case 16: e->launches += enc_launch_search<16>(cs, A, mono_mask, pair_mask, packed, wrap, Qp, mid); break;
-        case 20: e->launches += enc_launch_search<20>(cs, A, mono_mask, pair_mask, packed, wrap, Qp, mid); break;
-        case 24: e->launches += enc_launch_search<24>(cs, A, mono_mask, pair_mask, packed, wrap, Qp, mid); break;
-        default: e->launches += enc_launch_search<32>(cs, A, mono_mask, pair_mask, packed, wrap, Qp, mid); break;
+        case 16: e->launches += enc_launch_search<16>(cs, A, mono_mask, pair_mask, packed, wrap, Qp, mid, dense_form); break;
+        case 20: e->launches += enc_launch_search<20>(cs, A, mono_mask, pair_mask, packed, wrap, Qp, mid, dense_form); break;
+        case 24: e->launches += enc_launch_search<24>(cs, A, mono_mask, pair_mask, packed, wrap, Qp, mid, dense_form); break;
+        default: e->launches += enc_launch_search<32>(cs, A, mono_mask, pair_mask, packed, wrap, Qp, mid, dense_form); break;
         }
         if (split) {
             if (pair_mask) for (int i = 0; i < 3; i++) e->t_mid.push_back(mid[i]);

@@ -7,7 +7,7 @@
 #include "alac_encode.cuh"
 
 namespace alacb {
-template uint32_t enc_launch_search<ALAC_INSTANTIATE_DEPTH>(cudaStream_t, const EncArgs &, uint32_t, uint32_t, bool, bool, const JobLists *, cudaEvent_t *);
+template uint32_t enc_launch_search<ALAC_INSTANTIATE_DEPTH>(cudaStream_t, const EncArgs &, uint32_t, uint32_t, bool, bool, const JobLists *, cudaEvent_t *, int);
 template void enc_launch_assemble<ALAC_INSTANTIATE_DEPTH>(cudaStream_t, const AsmArgs &);
 template void dec_configure<ALAC_INSTANTIATE_DEPTH>();
 template uint32_t dec_launch_main<ALAC_INSTANTIATE_DEPTH>(cudaStream_t, const DecArgs &, cudaEvent_t *);

@@ -137,6 +137,27 @@ def tensor_from_pointer(ptr: int, count: int, device, typestr: str = "|u1"):
     return torch.as_tensor(_RawDevice(ptr, count, typestr), device=device)
 
 
+def staging_slots(slot_bytes, align: int = 256):
+    """Offsets of the per-rank slots of a staged placement (alac_b200_placement.slot_offsets) and the staging size:
+    slot r starts on an `align` boundary and holds at least slot_bytes[r] (rank r's worst-case block)."""
+    offs, at = [], 0
+    for b in slot_bytes:
+        offs.append(at)
+        at += (int(b) + align - 1) // align * align
+    return offs, at
+
+
+def compaction_plan(totals, slot_offsets):
+    """What the home rank does when every rank has reported its byte total: [(src offset in staging, dst offset in
+    the job's buffer, bytes)] for ranks 1.. (rank 0 writes its block at offset 0 itself)."""
+    out, at = [], int(totals[0])
+    for r in range(1, len(totals)):
+        if totals[r]:
+            out.append((int(slot_offsets[r]), at, int(totals[r])))
+        at += int(totals[r])
+    return out, at
+
+
 class SharedJob:
     """The single output buffer of a multi-rank encode job.
 
@@ -158,11 +179,7 @@ class SharedJob:
         self.slot_offsets = None
         staging_bytes = 0
         if slot_bytes is not None:
-            offs, at = [], 0
-            for b in slot_bytes:
-                offs.append(at)
-                at += (int(b) + 255) // 256 * 256
-            staging_bytes = at
+            offs, staging_bytes = staging_slots(slot_bytes)
             self.slot_offsets = (C.c_uint64 * len(offs))(*offs)
         sizes_bytes = 4 * max(self.total_packets, 1)
         if self.rank == home:

@@ -458,8 +458,8 @@ def run_cuda(args):
     n_slices = (m.frames_rank + slice_frames - 1) // slice_frames
     slice_pk = (slice_frames + FRAME - 1) // FRAME
     pcm_h = torch.empty(slice_frames * W.bpf, dtype=torch.uint8).pin_memory()
-    pk_hs = [torch.empty(alac_b200.encode_bound(cfg, slice_frames), dtype=torch.uint8).pin_memory() for _ in range(2)]
-    sz_hs = [torch.empty(slice_pk, dtype=torch.int32).pin_memory() for _ in range(2)]
+    pk_hs = [torch.empty(alac_b200.encode_bound(cfg, slice_frames), dtype=torch.uint8).pin_memory() for _ in range(3)]
+    sz_hs = [torch.empty(slice_pk, dtype=torch.int32).pin_memory() for _ in range(3)]
     out_h = torch.empty(slice_frames * W.bpf, dtype=torch.uint8).pin_memory()
     pcm_np, out_np = pcm_h.numpy(), out_h.numpy()
     pk_np = [t.numpy() for t in pk_hs]
@@ -474,16 +474,22 @@ def run_cuda(args):
         return e_, d_
 
     def pipeline_host(n):
-        """n slices through two engines: the encode of slice i+1 (alac_b200_encode_submit) overlaps the decode of slice i,
-        so PCM going up and PCM coming down share the full-duplex link.  Every slice still goes host -> device -> host
-        (packets) -> device -> host (PCM), all inside the timed region."""
+        """n slices through two engines, both kept busy: the encode engine starts slice i+1 as soon as it has finished slice i
+        (alac_b200_encode_submit), the decode engine takes slice i as soon as it has finished slice i-1
+        (alac_b200_decode_submit); three packet buffers rotate between them.  PCM going up for the next encode and PCM coming
+        down from the previous decode share the full-duplex link.  Every slice still goes host -> device -> host (packets)
+        -> device -> host (PCM), all inside the timed region."""
         wait_enc = eng.encode_submit(pcm_np, cfg, out=pk_np[0], out_sizes=sz_np[0])
+        wait_dec = None
         d_ = None
         for i in range(n):
             e_ = wait_enc()
             if i + 1 < n:
-                wait_enc = eng.encode_submit(pcm_np, cfg, out=pk_np[(i + 1) % 2], out_sizes=sz_np[(i + 1) % 2])
-            d_ = eng_dec.decode(e_.cookie, e_.packets, e_.sizes, out=out_np)
+                wait_enc = eng.encode_submit(pcm_np, cfg, out=pk_np[(i + 1) % 3], out_sizes=sz_np[(i + 1) % 3])
+            if wait_dec is not None:
+                d_ = wait_dec()
+            wait_dec = eng_dec.decode_submit(e_.cookie, e_.packets, e_.sizes, out=out_np)
+        d_ = wait_dec()
         return e_, d_
 
     e_, d_ = step_host()

@@ -66,3 +66,64 @@ def test_sharded_encode_is_byte_identical(oracle, K, world):
         assert p.exitcode == 0
     assert np.array_equal(sz.astype(np.uint32), whole.sizes)
     assert np.array_equal(pk, whole.packets)
+
+
+# ---- staged placement: the host-side arithmetic of alac_b200_encode_placed's staged form, under gloo ------------------
+def test_staging_slots_and_compaction_plan():
+    offs, total = shard.staging_slots([1000, 0, 257, 4096])
+    assert offs == [0, 1024, 1024, 1536] and total == 1536 + 4096
+    plan, end = shard.compaction_plan([700, 0, 200, 50], offs)
+    assert plan == [(1024, 700, 200), (1536, 900, 50)] and end == 950
+
+
+def _staged_worker(rank, world, port, pcm, ch, depth, K, q):
+    """Every rank encodes its frame range (oracle), writes its block into ITS SLOT of rank 0's staging area
+    (send/recv stands in for the NVLink peer copy), reports its total; rank 0 compacts."""
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from oracle import oracle as O
+    bpf = O.bytes_per_sample(depth) * ch
+    plan = shard.plan_frame_shards(pcm.nbytes // bpf, 4096, world, K)
+    a, n = plan[rank]
+    es = O.Encoder(ch, depth).encode_stream(pcm[a * bpf:(a + n) * bpf], K)
+    bounds = [nn * bpf + ((nn + 4095) // 4096 + 1) * (7 * ch + 1) for _, nn in plan]
+    offs, staging_bytes = shard.staging_slots(bounds)
+    tot = torch.tensor([es.packets.nbytes], dtype=torch.int64)
+    totals = [torch.zeros_like(tot) for _ in range(world)]
+    dist.all_gather(totals, tot)                    # (the 1 KB exchange block on the device)
+    totals = [int(t.item()) for t in totals]
+    if rank != 0:
+        dist.send(torch.from_numpy(es.packets.copy()), 0)
+    else:
+        staging = np.zeros(staging_bytes, np.uint8)
+        out = np.zeros(sum(totals), np.uint8)
+        out[:totals[0]] = es.packets                # the home rank owns offset 0
+        for r in range(1, world):
+            buf = torch.empty(totals[r], dtype=torch.uint8)
+            dist.recv(buf, r)
+            staging[offs[r]:offs[r] + totals[r]] = buf.numpy()
+        moves, end = shard.compaction_plan(totals, offs)
+        for src, dst, nb in moves:
+            out[dst:dst + nb] = staging[src:src + nb]
+        assert end == out.nbytes
+        q.put(out)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_staged_placement_is_byte_identical(oracle):
+    ch, depth, K, world = 2, 24, 1, 2
+    pcm = synth.make("music", 4096 * 5 + 77, ch, depth, seed=9)
+    whole = oracle.Encoder(ch, depth).encode_stream(pcm, K)
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_staged_worker, args=(r, world, port, pcm, ch, depth, K, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    out = q.get(timeout=120)
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    assert np.array_equal(out, whole.packets)

@@ -1086,7 +1086,9 @@ struct Exchange {
     unsigned long long total[2][16];
     uint32_t ready[2][16];
     uint32_t done[2][16];
+    uint32_t released;          // staged form: the last epoch whose slots the home rank has emptied
 };
+struct SlotOffsets { unsigned long long v[16]; };
 static_assert(sizeof(Exchange) <= 1024, "ALAC_B200_EXCHANGE_BYTES");
 constexpr unsigned long long kExchangeTimeoutNs = 20ull * 1000 * 1000 * 1000;
 
@@ -1171,6 +1173,76 @@ static __global__ void xchg_wait_all_kernel(Exchange *x, uint32_t n_ranks, uint3
     if (lane == 0) {
         if (job_total) *job_total = mine;
         if (!all_ok) *err = 2u;
+    }
+}
+
+// staged form, home rank: every rank's slot is complete -> close the gaps.  Block r (r >= 1) moves from its slot of the
+// staging area to the sum of the totals in front of it inside the job's buffer; the destination is written in aligned
+// 32-bit words (two aligned source words and a funnel shift each), the ragged ends byte by byte.  Then the slots are
+// released for the next epoch.  Runs entirely on the device: the home rank's host thread is free to start decoding.
+static __global__ void __launch_bounds__(256) xchg_compact_kernel(Exchange *x, uint32_t n_ranks, uint32_t epoch, SlotOffsets so,
+                                                                  const uint8_t *staging, uint8_t *dst, unsigned long long cap, uint32_t *err)
+{
+    const uint32_t slot = epoch & 1u;
+    unsigned long long at = x->total[slot][0];
+    const unsigned long long gtid = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x, gsize = (unsigned long long)gridDim.x * blockDim.x;
+    for (uint32_t r = 1; r < n_ranks; r++) {
+        const unsigned long long len = x->total[slot][r];
+        if (at + len > cap) { if (gtid == 0) *err = 3u; return; }
+        const uint8_t *src = staging + so.v[r];
+        uint8_t *d = dst + at;
+        // destination in aligned 16-byte vectors; the ragged ends (< 16 bytes each) byte by byte
+        const unsigned long long head = min((unsigned long long)((16u - (uint32_t)(reinterpret_cast<uintptr_t>(d) & 15u)) & 15u), len);
+        const unsigned long long nvec = (len - head) >> 4;
+        const unsigned long long tail0 = head + (nvec << 4);
+        if (gtid < head) d[gtid] = src[gtid];
+        if (gtid < len - tail0) d[tail0 + gtid] = src[tail0 + gtid];
+        // vector i: destination d + head + 16 i; source src + head + 16 i = aligned vector base + k words + sh bits
+        const uintptr_t s0 = reinterpret_cast<uintptr_t>(src + head);
+        const uint4 *sv = reinterpret_cast<const uint4 *>(s0 & ~(uintptr_t)15);
+        const uint32_t k = (uint32_t)(s0 & 15u) >> 2, sh = (uint32_t)(s0 & 3u) * 8u;
+        uint4 *dv = reinterpret_cast<uint4 *>(d + head);
+        const bool exact = (s0 & 15u) == 0;
+        // (when the source is not vector-aligned the last vector reads one source vector past its own: slots are
+        //  256-byte aligned and at least 16 bytes of slack follow every block inside the staging area)
+        for (unsigned long long i0 = gtid; i0 < nvec; i0 += 4 * gsize) {
+            uint4 lo[4], hi[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const unsigned long long i = i0 + (unsigned long long)u * gsize;
+                if (i < nvec) { lo[u] = __ldg(sv + i); if (!exact) hi[u] = __ldg(sv + i + 1); }
+            }
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const unsigned long long i = i0 + (unsigned long long)u * gsize;
+                if (i >= nvec) continue;
+                uint4 o = lo[u];
+                if (!exact) {
+                    const uint32_t w[9] = {lo[u].x, lo[u].y, lo[u].z, lo[u].w, hi[u].x, hi[u].y, hi[u].z, hi[u].w, 0u};
+                    uint32_t q[5];
+#pragma unroll
+                    for (int j = 0; j < 5; j++) q[j] = k == 0 ? w[j] : k == 1 ? w[j + 1] : k == 2 ? w[j + 2] : w[j + 3];
+                    o.x = __funnelshift_r(q[0], q[1], sh); o.y = __funnelshift_r(q[1], q[2], sh);
+                    o.z = __funnelshift_r(q[2], q[3], sh); o.w = __funnelshift_r(q[3], q[4], sh);
+                }
+                dv[i] = o;
+            }
+        }
+        at += len;
+    }
+}
+static __global__ void xchg_release_kernel(Exchange *x, uint32_t epoch)
+{
+    __threadfence_system();
+    st_release_sys_u32(&x->released, epoch);
+}
+// a rank may only refill its slot once the home rank has emptied it (the previous epoch's compaction)
+static __global__ void xchg_wait_released_kernel(Exchange *x, uint32_t want, uint32_t *err)
+{
+    const unsigned long long t0 = global_timer_ns();
+    while ((int32_t)(ld_acquire_sys_u32(&x->released) - want) < 0) {
+        if (global_timer_ns() - t0 > kExchangeTimeoutNs) { *err = 4u; return; }
+        __nanosleep(200);
     }
 }
 

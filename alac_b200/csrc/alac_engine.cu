@@ -52,6 +52,8 @@ struct alac_b200_engine {
     cudaStream_t stream = nullptr;
     cudaStream_t own_stream = nullptr;
     cudaStream_t copy_in = nullptr, copy_out = nullptr;     // transfer streams of the host-buffer pipeline
+    cudaStream_t side = nullptr;                            // staged placement, home rank: wait-for-all + compaction
+    bool finish_pending = false;
     cudaStream_t lanes[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   // compute streams of the host-buffer pipeline
     cudaStream_t cur = nullptr;                             // stream the launch helpers / timers use right now
     uint64_t *h_totals = nullptr;                           // pinned: running byte / frame totals per chunk
@@ -65,7 +67,7 @@ struct alac_b200_engine {
     bool decode_configured = false;
     // several GPUs (alac_b200_engine_create_multi): subs[0] is this engine itself (the home device)
     std::vector<alac_b200_engine *> subs;
-    DevBuf xchg, m_out, m_sizes, m_aux;      // home: exchange block; every sub: its block of a host-output / decode call
+    DevBuf xchg, m_out, m_sizes, m_aux, xwords;      // home: exchange block; every sub: its block of a host-output / decode call
     uint32_t epoch = 0;
     // asynchronous forms (alac_b200_*_submit / alac_b200_wait): one call in flight on a worker thread
     std::thread worker;
@@ -263,6 +265,7 @@ int32_t alac_b200_engine_create(int32_t device, alac_b200_engine **out_engine)
     for (auto &ln : e->lanes) lanes_ok = lanes_ok && cudaStreamCreateWithFlags(&ln, cudaStreamNonBlocking) == cudaSuccess;
     if (!lanes_ok || cudaStreamCreateWithFlags(&e->copy_in, cudaStreamNonBlocking) != cudaSuccess ||
         cudaStreamCreateWithFlags(&e->copy_out, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&e->side, cudaStreamNonBlocking) != cudaSuccess ||
         cudaHostAlloc(&e->h_totals, kMaxChunks * sizeof(uint64_t), cudaHostAllocDefault) != cudaSuccess) {
         delete e;
         return ALAC_B200_CUDA_ERROR;
@@ -284,7 +287,7 @@ void alac_b200_engine_destroy(alac_b200_engine *e)
     for (size_t i = 1; i < e->subs.size(); i++) alac_b200_engine_destroy(e->subs[i]);
     e->subs.clear();
     cudaSetDevice(e->device);
-    e->xchg.release(); e->m_out.release(); e->m_sizes.release(); e->m_aux.release();
+    e->xchg.release(); e->m_out.release(); e->m_sizes.release(); e->m_aux.release(); e->xwords.release();
     cudaStreamSynchronize(e->stream);
     DevBuf *bufs[] = {&e->pcm, &e->pkt_frame, &e->pkt_samples, &e->seg_first, &e->seg_count, &e->seg_stream, &e->recs,
                       &e->scratch, &e->sizes, &e->offsets, &e->out, &e->state, &e->counters, &e->scan_tiles, &e->d_packets, &e->d_sizes,
@@ -297,6 +300,7 @@ void alac_b200_engine_destroy(alac_b200_engine *e)
     if (e->copy_in) cudaStreamDestroy(e->copy_in);
     for (auto &ln : e->lanes) if (ln) cudaStreamDestroy(ln);
     if (e->copy_out) cudaStreamDestroy(e->copy_out);
+    if (e->side) cudaStreamDestroy(e->side);
     if (e->h_totals) cudaFreeHost(e->h_totals);
     delete e;
 }
@@ -394,8 +398,10 @@ struct DrainGuard {
         cudaStreamSynchronize(e->stream);
         cudaStreamSynchronize(e->copy_in);
         cudaStreamSynchronize(e->copy_out);
+        cudaStreamSynchronize(e->side);
         for (auto &ln : e->lanes) cudaStreamSynchronize(ln);
         e->cur = nullptr;
+        e->finish_pending = false;
     }
 };
 
@@ -433,6 +439,7 @@ static int32_t encode_core(alac_b200_engine *e, const alac_b200_enc_config *cfg,
     if (out_base) *out_base = 0;
     if (stats) memset(stats, 0, sizeof(*stats));
     CU_CHECK(e, cudaSetDevice(e->device));
+    if (e->finish_pending) { CU_CHECK(e, cudaStreamSynchronize(e->side)); e->finish_pending = false; }     // (an unfinished deferred job)
     e->launches = 0;
     e->timers_used = 0;
     e->t_mid.clear();
@@ -553,6 +560,7 @@ static int32_t encode_core(alac_b200_engine *e, const alac_b200_enc_config *cfg,
     CU_CHECK(e, e->sizes.reserve((size_t)P * 4 + 4));
     CU_CHECK(e, e->offsets.reserve(((size_t)P + 1) * 8));
     CU_CHECK(e, e->counters.reserve(128));
+    CU_CHECK(e, e->xwords.reserve(64));
     CU_CHECK(e, e->scan_tiles.reserve((scan_tiles_for(P) + chunks.size() + 1) * 8));
     // every segment is a single frame and no state is handed over: search and final pass run as two kernels
     const bool split = K == 1 && coef_state == nullptr;
@@ -581,7 +589,7 @@ static int32_t encode_core(alac_b200_engine *e, const alac_b200_enc_config *cfg,
 
     cudaStream_t st = e->stream;
     unsigned long long h_counters[4] = {0, 0, 0, 0};        // (locals the copy-out stream writes: declared before the guard)
-    unsigned long long h_place[2] = {0, 0};
+    unsigned long long h_place[3] = {0, 0, 0};
     DrainGuard guard(e);
     CU_CHECK(e, cudaEventRecord(e->ev[0], st));
     // small tables first: they share the H2D copy engine with the PCM chunks and must not queue behind them
@@ -600,6 +608,7 @@ static int32_t encode_core(alac_b200_engine *e, const alac_b200_enc_config *cfg,
         d_state = e->state.as<int16_t>();
     }
     CU_CHECK(e, cudaMemsetAsync(e->counters.p, 0, 128, st));
+    if (pl) CU_CHECK(e, cudaMemsetAsync(e->xwords.p, 0, 64, st));
     if (P == 0) CU_CHECK(e, cudaMemsetAsync(e->offsets.p, 0, 8, st));       // a rank with no packets still publishes a total
     if (split) CU_CHECK(e, cudaMemsetAsync(e->job_counts.p, 0, chunks.size() * 16 + 16, st));
     // copy-in stream: PCM chunks, each followed by an event the compute stream waits on
@@ -629,9 +638,11 @@ static int32_t encode_core(alac_b200_engine *e, const alac_b200_enc_config *cfg,
     if (final2_mode == 0) dense = false;
     unsigned long long *d_escapes = e->counters.as<unsigned long long>();
     uint32_t *d_max = reinterpret_cast<uint32_t *>(e->counters.as<uint8_t>() + 8);
-    uint64_t *d_base = reinterpret_cast<uint64_t *>(e->counters.as<uint8_t>() + 32);       // placed: where this rank's block starts
-    uint64_t *d_job_total = reinterpret_cast<uint64_t *>(e->counters.as<uint8_t>() + 40);  // placed, home rank: bytes of the whole job
-    uint32_t *d_xerr = reinterpret_cast<uint32_t *>(e->counters.as<uint8_t>() + 16);
+    // placement words live in their own buffer: a deferred finish (side stream) may still write them while the engine's
+    // next call (a decode) reuses the counters
+    uint64_t *d_base = e->xwords.as<uint64_t>();            // placed: where this rank's block starts
+    uint64_t *d_job_total = e->xwords.as<uint64_t>() + 1;   // placed, home rank: bytes of the whole job
+    uint32_t *d_xerr = reinterpret_cast<uint32_t *>(e->xwords.as<uint64_t>() + 2);
     std::vector<cudaEvent_t> comp_done, scan_done;
     const bool trace = getenv("ALAC_B200_TRACE") != nullptr;
     const auto host_t0 = std::chrono::steady_clock::now();
@@ -753,6 +764,11 @@ static int32_t encode_core(alac_b200_engine *e, const alac_b200_enc_config *cfg,
     uint64_t total = 0, copied = 0;
     uint8_t *far_out = out_host ? static_cast<uint8_t *>(packets_out)
                                 : to_slot ? static_cast<uint8_t *>(pl->staging) + pl->slot_offsets[pl->rank] : nullptr;
+    if (to_slot && pl->epoch > 1) {
+        // this rank's slot must have been emptied by the home rank's compaction of the previous epoch
+        xchg_wait_released_kernel<<<1, 1, 0, e->copy_out>>>(x, pl->epoch - 1u, d_xerr);
+        e->launches++;
+    }
     for (size_t ci = 0; ci < comp_done.size(); ci++) {
         CU_CHECK(e, cudaEventSynchronize(comp_done[ci]));       // all later GPU work is already queued
         if (direct) break;
@@ -765,7 +781,6 @@ static int32_t encode_core(alac_b200_engine *e, const alac_b200_enc_config *cfg,
         }
     }
     if (pl && !chunks.empty()) total = e->h_totals[chunks.size() - 1];
-    std::vector<unsigned long long> h_tot;
     if (staged) {
         // the exchange closes the call: this rank's total, the offset of its block, and "my slot is complete";
         // the home rank then waits for every rank and closes the gaps between the slots inside its own memory
@@ -775,25 +790,30 @@ static int32_t encode_core(alac_b200_engine *e, const alac_b200_enc_config *cfg,
         xchg_done_kernel<<<1, 1, 0, xs>>>(x, pl->rank, pl->epoch);
         e->launches += 2;
         if (is_home) {
-            xchg_wait_all_kernel<<<1, 32, 0, xs>>>(x, pl->n_ranks, pl->epoch, d_job_total, d_xerr);
-            e->launches++;
-            h_tot.resize(16);
-            CU_CHECK(e, cudaMemcpyAsync(h_tot.data(), x->total[pl->epoch & 1u], 16 * 8, cudaMemcpyDeviceToHost, xs));
-            CU_CHECK(e, cudaStreamSynchronize(xs));
-            uint64_t at = h_tot[0];
-            for (uint32_t r = 1; r < pl->n_ranks; r++) {
-                if (at + h_tot[r] > pl->dst_capacity) { e->err = "dst_packets capacity exceeded"; return ALAC_B200_PARAM_ERROR; }
-                if (h_tot[r])
-                    CU_CHECK(e, cudaMemcpyAsync(static_cast<uint8_t *>(pl->dst_packets) + at, static_cast<uint8_t *>(pl->staging) + pl->slot_offsets[r],
-                                                (size_t)h_tot[r], cudaMemcpyDeviceToDevice, xs));
-                at += h_tot[r];
+            // wait for every rank, close the gaps between the slots, release the slots -- all on the device, on a side
+            // stream, so that with defer_finish the host returns as soon as this rank's own block is placed
+            CU_CHECK(e, cudaEventRecord(e->ev[2], xs));
+            CU_CHECK(e, cudaStreamWaitEvent(e->side, e->ev[2], 0));
+            CU_CHECK(e, cudaStreamWaitEvent(e->copy_out, e->ev[2], 0));         // (the result words are read on the copy-out stream)
+            SlotOffsets so;
+            for (uint32_t r = 0; r < 16; r++) so.v[r] = r < pl->n_ranks ? pl->slot_offsets[r] : 0ull;
+            xchg_wait_all_kernel<<<1, 32, 0, e->side>>>(x, pl->n_ranks, pl->epoch, d_job_total, d_xerr);
+            static const int compact_ctas = [] { const char *v = getenv("ALAC_B200_COMPACT_CTAS"); return v ? atoi(v) : 148 * 8; }();
+            xchg_compact_kernel<<<compact_ctas, 256, 0, e->side>>>(x, pl->n_ranks, pl->epoch, so, static_cast<const uint8_t *>(pl->staging),
+                                                             static_cast<uint8_t *>(pl->dst_packets), pl->dst_capacity, d_xerr);
+            xchg_release_kernel<<<1, 1, 0, e->side>>>(x, pl->epoch);
+            e->launches += 3;
+            e->finish_pending = true;
+            if (!pl->defer_finish) {
+                CU_CHECK(e, cudaStreamSynchronize(e->side));
+                e->finish_pending = false;
+                CU_CHECK(e, cudaEventRecord(e->ev[2], xs));      // the job's buffer is complete: end of the kernel phase
             }
-            CU_CHECK(e, cudaEventRecord(e->ev[2], xs));      // the job's buffer is complete: end of the kernel phase
         }
     }
     if (P) CU_CHECK(e, cudaMemcpyAsync(packet_sizes, e->sizes.p, (size_t)P * 4, sizes_host ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice, e->copy_out));
-    CU_CHECK(e, cudaMemcpyAsync(h_counters, e->counters.p, 32, cudaMemcpyDeviceToHost, e->copy_out));
-    if (pl) CU_CHECK(e, cudaMemcpyAsync(h_place, d_base, 16, cudaMemcpyDeviceToHost, e->copy_out));
+    CU_CHECK(e, cudaMemcpyAsync(h_counters, e->counters.p, 16, cudaMemcpyDeviceToHost, e->copy_out));
+    if (pl) CU_CHECK(e, cudaMemcpyAsync(h_place, d_base, 24, cudaMemcpyDeviceToHost, e->copy_out));
     if (coef_state) {
         CU_CHECK(e, cudaMemcpyAsync(coef_state, e->state.p, (size_t)n_streams * ALAC_B200_STATE_INT16S * 2, cudaMemcpyDeviceToHost, e->copy_out));
     }
@@ -802,7 +822,7 @@ static int32_t encode_core(alac_b200_engine *e, const alac_b200_enc_config *cfg,
     CU_CHECK(e, cudaStreamSynchronize(st));
     guard.armed = false;
     if (pl) {
-        if (h_counters[2] & 0xffffffffull) { e->err = "cross-GPU exchange timed out (a rank of the job did not arrive)"; return ALAC_B200_CUDA_ERROR; }
+        if (h_place[2] & 0xffffffffull) { e->err = "cross-GPU exchange timed out (a rank of the job did not arrive)"; return ALAC_B200_CUDA_ERROR; }
         if (h_place[0] + total > pl->dst_capacity) { e->err = "dst_packets capacity exceeded"; return ALAC_B200_PARAM_ERROR; }
         if (out_base) *out_base = h_place[0];
         if (out_local) *out_local = to_slot ? static_cast<void *>(d_out) : static_cast<void *>(static_cast<uint8_t *>(pl->dst_packets) + h_place[0]);
@@ -933,7 +953,7 @@ static int32_t multi_encode(alac_b200_engine *e, const alac_b200_enc_config *cfg
                 alac_b200_placement pl;
                 pl.dst_packets = packets_out; pl.dst_capacity = packets_cap; pl.dst_sizes = nullptr; pl.first_packet = h.first_packet;
                 pl.exchange = e->xchg.p; pl.rank = d; pl.n_ranks = m; pl.home_rank = 0; pl.epoch = epoch;
-                pl.staging = nullptr; pl.slot_offsets = nullptr;
+                pl.staging = nullptr; pl.slot_offsets = nullptr; pl.defer_finish = 0;
                 h.rc = encode_core(se, cfg, pcm, num_sample_frames, pcm_mem, h.streams.data(), h.streams.size(), nullptr, 0,
                                    packet_sizes + h.first_packet, h.packets, ALAC_B200_MEM_DEVICE, nullptr, &h.np, &h.bytes, &h.st, &pl, &h.base);
             } else {
@@ -996,6 +1016,24 @@ extern "C" int32_t alac_b200_encode_placed(alac_b200_engine *e, const alac_b200_
     if (!e || !placement || e->subs.size() > 1) return ALAC_B200_PARAM_ERROR;
     return encode_core(e, cfg, pcm, num_sample_frames, pcm_mem, streams, n_streams, nullptr, 0, packet_sizes, sizes_cap, out_mem, nullptr,
                        out_num_packets, out_bytes, stats, placement, out_base, out_local_block);
+}
+
+extern "C" int32_t alac_b200_placed_finish(alac_b200_engine *e, uint64_t *out_job_bytes)
+{
+    if (!e) return ALAC_B200_PARAM_ERROR;
+    if (out_job_bytes) *out_job_bytes = 0;
+    if (!e->finish_pending) return ALAC_B200_OK;
+    CU_CHECK(e, cudaSetDevice(e->device));
+    CU_CHECK(e, cudaStreamSynchronize(e->side));
+    e->finish_pending = false;
+    unsigned long long h[3] = {0, 0, 0};
+    CU_CHECK(e, cudaMemcpy(h, e->xwords.p, 24, cudaMemcpyDeviceToHost));
+    if (h[2] & 0xffffffffull) {
+        e->err = (h[2] & 0xffffffffull) == 3 ? "dst_packets capacity exceeded" : "cross-GPU exchange timed out (a rank of the job did not arrive)";
+        return (h[2] & 0xffffffffull) == 3 ? ALAC_B200_PARAM_ERROR : ALAC_B200_CUDA_ERROR;
+    }
+    if (out_job_bytes) *out_job_bytes = h[1];
+    return ALAC_B200_OK;
 }
 
 extern "C" int32_t alac_b200_engine_create_multi(const int32_t *devices, uint32_t n_devices, alac_b200_engine **out_engine)

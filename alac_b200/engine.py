@@ -62,7 +62,7 @@ class Placement(C.Structure):
     """alac_b200_placement (include/alac_b200.h): where one rank's packet block goes inside a job's single buffer."""
     _fields_ = [("dst_packets", C.c_void_p), ("dst_capacity", C.c_uint64), ("dst_sizes", C.c_void_p),
                 ("first_packet", C.c_uint64), ("exchange", C.c_void_p), ("rank", C.c_uint32), ("n_ranks", C.c_uint32),
-                ("home_rank", C.c_uint32), ("epoch", C.c_uint32), ("staging", C.c_void_p), ("slot_offsets", C.POINTER(C.c_uint64))]
+                ("home_rank", C.c_uint32), ("epoch", C.c_uint32), ("staging", C.c_void_p), ("slot_offsets", C.POINTER(C.c_uint64)), ("defer_finish", C.c_uint32)]
 
 
 EXCHANGE_BYTES = 1024
@@ -118,6 +118,8 @@ def load_library():
     lib.alac_b200_encode_placed.argtypes = [vp, C.POINTER(_EncConfig), vp, u64, i32, C.POINTER(_Stream), u64, C.POINTER(Placement),
                                             vp, u64, i32, C.POINTER(u64), C.POINTER(u64), C.POINTER(u64), C.POINTER(vp), C.POINTER(Stats)]
     lib.alac_b200_encode_placed.restype = i32
+    lib.alac_b200_placed_finish.argtypes = [vp, C.POINTER(u64)]
+    lib.alac_b200_placed_finish.restype = i32
     lib.alac_b200_device_alloc.argtypes = [vp, u64, C.POINTER(vp)]
     lib.alac_b200_device_alloc.restype = i32
     lib.alac_b200_device_free.argtypes = [vp, vp]
@@ -279,6 +281,14 @@ class Engine:
 
     def ipc_close(self, ptr: int):
         self.lib.alac_b200_ipc_close(self.h, C.c_void_p(ptr))
+
+    def placed_finish(self) -> int:
+        """Ends a staged job whose home-rank call used defer_finish (alac_b200_placed_finish); returns the job's bytes."""
+        nb = C.c_uint64(0)
+        st = self.lib.alac_b200_placed_finish(self.h, C.byref(nb))
+        if st:
+            raise AlacError(st, self._err())
+        return nb.value
 
     def encode_placed(self, pcm, cfg: EncoderConfig, placement: Placement, streams=None, out_sizes=None):
         """This rank's share of a job several GPUs encode together (alac_b200_encode_placed): the packets go straight

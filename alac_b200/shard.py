@@ -184,7 +184,7 @@ class SharedJob:
         sizes_bytes = 4 * max(self.total_packets, 1)
         if self.rank == home:
             self._ptrs = [engine.device_alloc(self.capacity), engine.device_alloc(sizes_bytes), engine.device_alloc(EXCHANGE_BYTES),
-                          engine.device_alloc(max(staging_bytes, 256))]
+                          engine.device_alloc(max(staging_bytes, 256) + 256)]       # (32 bytes of slack after the last slot, see alac_b200.h)
             tensor_from_pointer(self._ptrs[2], EXCHANGE_BYTES, device).zero_()
             torch.cuda.synchronize(device)
             handles = [engine.ipc_export(p) for p in self._ptrs]
@@ -202,13 +202,19 @@ class SharedJob:
             self.packets = tensor_from_pointer(self.packets_ptr, self.capacity, device)
             self.sizes = tensor_from_pointer(self.sizes_ptr, max(self.total_packets, 1), device, "<i4")
 
-    def placement(self, first_packet: int):
+    def placement(self, first_packet: int, defer_finish: bool = False):
+        """defer_finish (staged form): the home rank's call returns once its own block is placed; call finish() when
+        the job's buffer is needed (every rank's block at its final offset)."""
         from .engine import Placement
         self.epoch += 1
         staged = self.slot_offsets is not None
         return Placement(self.packets_ptr, self.capacity, self.sizes_ptr, int(first_packet), self.exchange_ptr,
                          self.rank, self.world, self.home, self.epoch, self.staging_ptr if staged else None,
-                         self.slot_offsets if staged else None)
+                         self.slot_offsets if staged else None, 1 if (defer_finish and staged) else 0)
+
+    def finish(self) -> int:
+        """Home rank: wait until the job's buffer is complete (no-op elsewhere / when nothing is pending)."""
+        return self.engine.placed_finish() if self.rank == self.home else 0
 
     def close(self):
         if getattr(self, "_ptrs", None) is None:

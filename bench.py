@@ -335,10 +335,12 @@ def measure_device(W: Work, ctx, steps: int, warmup: int, sampler=None):
             enc = eng.encode(m.pcm_d, cfg, out=m.pk_d, out_sizes=m.sz_d)
             dec = eng.decode(cookie, enc.packets, enc.sizes, out=out_d)
             return enc.stats, dec, enc.nbytes
-        sizes, _, nb, base, mine, st = eng.encode_placed(m.pcm_d, cfg, m.job.placement(first_packet), out_sizes=m.sz_d)
+        sizes, _, nb, base, mine, st = eng.encode_placed(m.pcm_d, cfg, m.job.placement(first_packet, defer_finish=os.environ.get('ALAC_B200_DEFER', '1') != '0'), out_sizes=m.sz_d)
         # every rank decodes its own packet range (its own copy of the block: the concatenation on GPU 0 is the job's
-        # only cross-GPU step, BASELINE.json north_star)
+        # only cross-GPU step, BASELINE.json north_star).  On GPU 0 "wait for every rank, close the gaps" runs on the
+        # device meanwhile; the step ends when the job's buffer is complete.
         dec = eng.decode(cookie, mine, sizes, out=out_d)
+        m.job.finish()
         return st, dec, nb
 
     # ---- parity in the same run: round-trip identity on this rank's whole range

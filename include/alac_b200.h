@@ -154,9 +154,14 @@ typedef struct alac_b200_placement {
        bytes DURING the computation instead: the call runs as a pipeline of chunks, each chunk's packets leave for the
        rank's reserved slot staging + slot_offsets[rank] over NVLink (asynchronous peer copies) while the next chunk's
        kernels run, and when every rank is done the home rank closes the gaps between the slots with copies inside its
-       own memory.  slot_offsets: n_ranks entries (host memory), slot r at least as large as rank r's encode bound. */
+       own memory.  slot_offsets: n_ranks entries (host memory), 16-byte aligned, slot r at least as large as rank r's encode
+       bound; the staging area extends at least 32 bytes past the last slot. */
     void           *staging;        /* device pointer in the home GPU's memory (local or peer), or NULL = direct form */
     const uint64_t *slot_offsets;
+    /* staged form, home rank: 0 = the call returns when the job's buffer is complete; 1 = it returns when the home
+       rank's own block is in place and leaves "wait for every rank, close the gaps" running on the device -- the caller
+       does other work on this GPU (decoding its own shard) and ends the job with alac_b200_placed_finish(). */
+    uint32_t        defer_finish;
 } alac_b200_placement;
 /* Same arguments as alac_b200_encode for this rank's PCM; packet_sizes[] (the rank's own entries) stays local
    (out_mem says where); *out_base receives the byte offset of the rank's block inside dst_packets.  *out_local_block
@@ -169,6 +174,10 @@ int32_t alac_b200_encode_placed(alac_b200_engine *engine, const alac_b200_enc_co
                                 uint32_t *packet_sizes, uint64_t sizes_cap, int32_t out_mem,
                                 uint64_t *out_num_packets, uint64_t *out_bytes, uint64_t *out_base,
                                 void **out_local_block, alac_b200_stats *stats);
+
+/* ends a staged job whose home-rank call was made with defer_finish = 1: returns when every rank's block is at its final
+   offset of dst_packets; *out_job_bytes (optional) = the job's total packet bytes.  A no-op (status 0) otherwise. */
+int32_t alac_b200_placed_finish(alac_b200_engine *engine, uint64_t *out_job_bytes);
 
 /* device memory that can be shared with other processes (plain cudaMalloc on the engine's device) and the
    cudaIpc* wrappers a one-process-per-GPU launcher needs; handle = 64 bytes (cudaIpcMemHandle_t) */

@@ -35,14 +35,15 @@ for it in range(3):                                  # several epochs through th
     torch.cuda.synchronize()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
-    sizes, npk, nb, base, mine, stats = eng.encode_placed(pcm, cfg, job.placement(pk_plan[rank][0]))
+    sizes, npk, nb, base, mine, stats = eng.encode_placed(pcm, cfg, job.placement(pk_plan[rank][0], defer_finish=(it == 1)))
     ev1.record()
     torch.cuda.synchronize()
     ms = ev0.elapsed_time(ev1)
     # decode this rank's block: its own copy, and straight out of the shared buffer (peer loads)
     dec = eng.decode(alac_b200.magic_cookie(cfg), mine, sizes)
     ok = ok and dec.status == 0 and torch.equal(dec.pcm, pcm)
-    dist.barrier()          # (the shared buffer is complete once the home rank's call has returned)
+    job.finish()
+    dist.barrier()          # (the shared buffer is complete once the home rank's call -- or its finish() -- has returned)
     dec = eng.decode(alac_b200.magic_cookie(cfg), job.packets_region[base:base + nb], sizes)
     ok = ok and dec.status == 0 and torch.equal(dec.pcm, pcm)
     tot = torch.tensor([nb], dtype=torch.int64, device=dev)

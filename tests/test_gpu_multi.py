@@ -56,8 +56,10 @@ def test_placed_encode_single_rank_job(engine, form):
     slots = (C.c_uint64 * 1)(0)
     for epoch in (1, 2, 3):
         pl = alac_b200.Placement(dst.data_ptr(), cap, dsz.data_ptr(), 0, xchg.data_ptr(), 0, 1, 0, epoch,
-                                 stg.data_ptr() if form == "staged" else None, slots if form == "staged" else None)
+                                 stg.data_ptr() if form == "staged" else None, slots if form == "staged" else None,
+                                 1 if (form == "staged" and epoch == 2) else 0)
         sizes, npk, nb, base, mine, _ = engine.encode_placed(pcm, cfg, pl)
+        assert engine.placed_finish() in (0, want.nbytes)
         torch.cuda.synchronize()
         assert (npk, nb, base) == (want.num_packets, want.nbytes, 0)
         assert torch.equal(dst[:nb], want.packets) and torch.equal(dsz, torch.as_tensor(want.sizes, device=dev).to(torch.int32))

@@ -231,56 +231,87 @@ __device__ __forceinline__ void flush_tile(const DecArgs &A, uint32_t metas, con
         }
         return;
     }
-    for (uint32_t pr = pr0; pr < 32; pr += pr_step) {
-        const uint4 q = lds_meta(metas + pr * (uint32_t)sizeof(FinMeta));       // out0, n, {kind, shift, mix_bits, mix_res}
-        const uint32_t n = q.z, kind = q.w & 0xffu, shift = (q.w >> 8) & 0xffu, mix_bits = (q.w >> 16) & 0xffu;
-        const int32_t mix_res = (int32_t)q.w >> 24;
-        if (kind == CH_PAIR_V || j >= n) continue;
-        uint8_t *out = reinterpret_cast<uint8_t *>(((uint64_t)q.y << 32) | q.x) + (size_t)j * stride;
-        if (kind == CH_ZERO) {
-            for (uint32_t cc = 0; cc < zero_chans; cc++) store_sample<DEPTH>(out + cc * bps, 0);
-            continue;
-        }
-        int32_t l = bu[lane * kTilePitch + pr];
-        // this sample's shifted-off low bits (mono: `shift` bits, pair: L then R, 2 * shift bits) straight from the packet
-        uint32_t low = 0;
-        if (shift) {
+    // Packets in batches of kBatch: the batch's shift-region words (two aligned loads per sample: addresses come from the
+    // packets' metadata, so nothing can be requested earlier) are all requested before the first one is used -- one
+    // round trip to L2 / HBM per batch instead of one per packet.
+    constexpr uint32_t kBatch = 4;
+    for (uint32_t prb = pr0; prb < 32; prb += kBatch * pr_step) {
+        uint4 qs[kBatch];
+        uint32_t w0[kBatch], w1[kBatch], sh_bit[kBatch], sh_mode[kBatch];      // sh_mode: 0 none, 1 the two words, 2 bounds-checked reader
+#pragma unroll
+        for (uint32_t u = 0; u < kBatch; u++) {
+            const uint32_t pr = prb + u * pr_step;
+            sh_mode[u] = 0; w0[u] = w1[u] = 0; sh_bit[u] = 0;
+            qs[u] = make_uint4(0u, 0u, 0u, (uint32_t)CH_PAIR_V);                 // (skipped below)
+            if (pr >= 32) continue;
+            const uint4 q = lds_meta(metas + pr * (uint32_t)sizeof(FinMeta));   // out0, n, {kind, shift, mix_bits, mix_res}
+            qs[u] = q;
+            const uint32_t n = q.z, kind = q.w & 0xffu, shift = (q.w >> 8) & 0xffu;
+            if (kind == CH_PAIR_V || kind == CH_ZERO || j >= n || !shift) continue;
+            // this sample's shifted-off low bits (mono: `shift` bits, pair: L then R, 2 * shift bits) straight from the packet
             const uint4 q2 = lds_meta(metas + pr * (uint32_t)sizeof(FinMeta) + 16u);    // pkt, pkt_size, shift_pos
             const uint64_t addr = ((uint64_t)q2.y << 32) | q2.x;
             const uint32_t W = (kind == CH_MONO) ? shift : 2u * shift;                  // <= 32
             const uint32_t bias = (uint32_t)(addr & 3u) * 8u;
             const uint32_t abs_bit = bias + q2.w + j * W, i = abs_bit >> 5;
+            sh_bit[u] = abs_bit & 31u;
             if ((i + 2u) * 32u <= bias + q2.z * 8u) {
                 // both words lie inside the packet: two aligned loads and a funnel shift
                 const uint32_t *base = reinterpret_cast<const uint32_t *>(addr & ~(uint64_t)3);
-                low = __funnelshift_l(bswap32(__ldg(base + i + 1)), bswap32(__ldg(base + i)), abs_bit & 31u) >> (32u - W);
+                w0[u] = __ldg(base + i);
+                w1[u] = __ldg(base + i + 1);
+                sh_mode[u] = 1;
             } else {
-                BitPeek bp;                                                             // near the end: the bounds-checked reader
-                bp.start(reinterpret_cast<const uint8_t *>(addr), q2.z);
-                low = bp.bits_at(q2.w + j * W, W);
+                sh_mode[u] = 2;                                                         // near the end: the bounds-checked reader
             }
         }
-        if (kind == CH_MONO) {
-            if (shift) l = (int32_t)(((uint32_t)l << shift) | low);                     // :436-495
-            store_sample<DEPTH>(out, l);
-        } else {
-            const int32_t v = bv[lane * kTilePitch + pr];
-            int32_t r;
-            if (mix_res != 0) {                         // :193-223
-                l = l + v - ((mix_res * v) >> (mix_bits & 31u));    // an out-of-range mixBits shifts like the reference's int32 shift on x86
-                r = l - v;
-            } else {
-                r = v;
+#pragma unroll
+        for (uint32_t u = 0; u < kBatch; u++) {
+            const uint32_t pr = prb + u * pr_step;
+            const uint4 q = qs[u];
+            const uint32_t n = q.z, kind = q.w & 0xffu, shift = (q.w >> 8) & 0xffu, mix_bits = (q.w >> 16) & 0xffu;
+            const int32_t mix_res = (int32_t)q.w >> 24;
+            if (kind == CH_PAIR_V || j >= n) continue;
+            uint8_t *out = reinterpret_cast<uint8_t *>(((uint64_t)q.y << 32) | q.x) + (size_t)j * stride;
+            if (kind == CH_ZERO) {
+                for (uint32_t cc = 0; cc < zero_chans; cc++) store_sample<DEPTH>(out + cc * bps, 0);
+                continue;
             }
-            if (shift) {                                // :282-383
-                l = (int32_t)(((uint32_t)l << shift) | (low >> shift));
-                r = (int32_t)(((uint32_t)r << shift) | (low & ((1u << shift) - 1u)));
+            int32_t l = bu[lane * kTilePitch + pr];
+            uint32_t low = 0;
+            if (shift) {
+                const uint32_t W = (kind == CH_MONO) ? shift : 2u * shift;
+                if (sh_mode[u] == 1) {
+                    low = __funnelshift_l(bswap32(w1[u]), bswap32(w0[u]), sh_bit[u]) >> (32u - W);
+                } else {
+                    const uint4 q2 = lds_meta(metas + pr * (uint32_t)sizeof(FinMeta) + 16u);
+                    BitPeek bp;
+                    bp.start(reinterpret_cast<const uint8_t *>(((uint64_t)q2.y << 32) | q2.x), q2.z);
+                    low = bp.bits_at(q2.w + j * W, W);
+                }
             }
-            if (DEPTH == 16 && out_pair32) {
-                *reinterpret_cast<uint32_t *>(out) = ((uint32_t)l & 0xffffu) | ((uint32_t)r << 16);
-            } else {
+            if (kind == CH_MONO) {
+                if (shift) l = (int32_t)(((uint32_t)l << shift) | low);                     // :436-495
                 store_sample<DEPTH>(out, l);
-                store_sample<DEPTH>(out + bps, r);
+            } else {
+                const int32_t v = bv[lane * kTilePitch + pr];
+                int32_t r;
+                if (mix_res != 0) {                         // :193-223
+                    l = l + v - ((mix_res * v) >> (mix_bits & 31u));    // an out-of-range mixBits shifts like the reference's int32 shift on x86
+                    r = l - v;
+                } else {
+                    r = v;
+                }
+                if (shift) {                                // :282-383
+                    l = (int32_t)(((uint32_t)l << shift) | (low >> shift));
+                    r = (int32_t)(((uint32_t)r << shift) | (low & ((1u << shift) - 1u)));
+                }
+                if (DEPTH == 16 && out_pair32) {
+                    *reinterpret_cast<uint32_t *>(out) = ((uint32_t)l & 0xffffu) | ((uint32_t)r << 16);
+                } else {
+                    store_sample<DEPTH>(out, l);
+                    store_sample<DEPTH>(out + bps, r);
+                }
             }
         }
     }

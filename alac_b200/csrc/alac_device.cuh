@@ -94,22 +94,25 @@ template <int TAPS, bool WRAP>
 __device__ __forceinline__ void lms_adapt(int32_t (&a)[TAPS], const int32_t (&b)[TAPS], int32_t err)
 {
     // codec/dp_enc.c:236-329.  Branch-free ladder: the walk goes from the last tap to the first and
-    // stops once the running error `left` reaches or crosses zero; "live" masks the taps after that.
-    //   err > 0:  sgn =  sign(b);  a -= sgn;  left -= w * ((sgn * b) >> 9);  go on while left > 0
-    //   err < 0:  sgn = -sign(b);  a -= sgn;  left -= w * ((sgn * b) >> 9);  go on while left < 0
-    // (sgn * b) is +|b| or -|b|; the arithmetic shift of -|b| rounds toward -inf as in dp_enc.c:288.
-    // With m = err >> 31 the loop test is (left ^ m) > m for both signs.
+    // stops once the running error reaches or crosses zero.
+    //   err > 0:  sgn = sign(b);  a -= sgn;  del0 -= w * (( sgn * b) >> 9);  go on while del0 > 0
+    //   err < 0:  sgn = sign(b);  a += sgn;  del0 -= w * ((-sgn * b) >> 9);  go on while del0 < 0
+    // sgn * b = |b|, and the arithmetic shift of -|b| rounds toward -inf (dp_enc.c:288): (-|b|) >> 9 = -((|b| + 511) >> 9).
+    // Both signs therefore are ONE walk on left = |del0|:  left -= w * ((|b| + c) >> 9) with c = 0 or 511, go on while
+    // left > 0.  left never grows, so "tap k is reached" is simply left > 0 at that point (no chain of conditions), and
+    // the update is a predicated multiply-add.  Per tap: two min/max, two IMAD, a shift, a compare and the predicated
+    // IMAD -- the integer ALU pipe and the IMAD pipe issue every other cycle each, so the instruction count and its split
+    // over the two pipes is what bounds these kernels.
     const int32_t m = err >> 31;
-    const int32_t sg = m | 1;
-    int32_t left = err;
-    bool live = (err != 0);
+    const int32_t nsg = -2 * m - 1;                        // +1 for err < 0, -1 otherwise
+    const int32_t c = m & ((1 << kDenShift) - 1);
+    int32_t left = abs(err);                                // |err| < 2^25: err is a sign-extended chan_bits value
 #pragma unroll
     for (int k = TAPS - 1; k >= 0; k--) {
-        const int32_t s = sign3(b[k]) * sg;
-        const int32_t upd = a[k] - s;
-        a[k] = live ? (WRAP ? sext16(upd) : upd) : a[k];
-        left -= (TAPS - k) * ((s * b[k]) >> kDenShift);
-        live = live && ((left ^ m) > m);
+        const int32_t sb = sign3(b[k]);
+        asm("{\n\t.reg .pred p;\n\tsetp.gt.s32 p, %3, 0;\n\t@p mad.lo.s32 %0, %1, %2, %0;\n\t}" : "+r"(a[k]) : "r"(sb), "r"(nsg), "r"(left));
+        if (WRAP) a[k] = sext16(a[k]);
+        left -= (TAPS - k) * ((sb * b[k] + c) >> kDenShift);
     }
 }
 

@@ -93,6 +93,7 @@ struct MixSrc {
     static constexpr int kAhead = kWords <= 2 ? 4 : 2;      // prefetch distance in samples
     // 16-bit packed stereo: the main loop of predict_pass reads four sample-frames per 16-byte load
     static constexpr bool kWide = STEREO && PACKED && DEPTH == 16;
+    static constexpr bool kDense = false;
     struct Raw { uint32_t w[kWords]; };
 
     const uint8_t *base;    // sample-frame 0 of the packet, first channel of the element
@@ -163,6 +164,167 @@ struct MixSrc {
     }
 };
 
+// ---- dense elements: the word ring (used by the dense search passes and by enc_final2_kernel, see there) ----------
+template <int DEPTH, bool STEREO> struct DenseElem {
+    static constexpr uint32_t kFrameBytes = DepthTraits<DEPTH>::kBytes * (STEREO ? 2u : 1u);
+    static constexpr uint32_t kQuadWords = kFrameBytes;          // 4 sample-frames = kFrameBytes 32-bit words
+};
+#ifndef ALAC_QUAD_AHEAD
+#define ALAC_QUAD_AHEAD 3
+#endif
+constexpr uint32_t kQuadAhead = ALAC_QUAD_AHEAD;
+constexpr uint32_t kEncTileRows = 32;
+
+// sign-extended 16-bit value at byte offset o (0..3) + 1 of the word pair (lo, hi): bytes o+1, o+2 -> (b2 << 8 | b1)
+template <uint32_t O> __device__ __forceinline__ int32_t prmt_s16_at(uint32_t lo, uint32_t hi)
+{
+    constexpr uint32_t b1 = O + 1u, b2 = O + 2u;                 // byte indices into {lo: 0..3, hi: 4..7}
+    constexpr uint32_t sel = b1 | (b2 << 4) | ((b2 | 8u) << 8) | ((b2 | 8u) << 12);     // nibble msb = replicate the byte's sign
+    uint32_t d;
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(lo), "r"(hi), "n"(sel));       // (__byte_perm ignores the msb of a nibble)
+    return (int32_t)d;
+}
+// 24-bit container at byte offset O of the word pair, as a left-justified 32-bit word (sample << 8)
+template <uint32_t O> __device__ __forceinline__ uint32_t prmt_u24hi_at(uint32_t lo, uint32_t hi)
+{
+    constexpr uint32_t sel = (O << 4) | ((O + 1u) << 8) | ((O + 2u) << 12);   // byte 0 <- lo.b0 (garbage, shifted out below)
+    return __byte_perm(lo, hi, sel) & 0xffffff00u;
+}
+
+// the four (left, right) -- or four mono -- samples of a quad, after the depth's shift (what the predictor sees)
+template <int DEPTH, bool STEREO>
+__device__ __forceinline__ void unpack_quad(const uint32_t (&w)[DenseElem<DEPTH, STEREO>::kQuadWords], int32_t (&l)[4], int32_t (&r)[4])
+{
+    constexpr uint32_t sh = DepthTraits<DEPTH>::kShift;
+    if (DEPTH == 16) {
+        if (STEREO) {
+#pragma unroll
+            for (int i = 0; i < 4; i++) { l[i] = (int32_t)(int16_t)(w[i] & 0xffffu); r[i] = (int32_t)w[i] >> 16; }
+        } else {
+            l[0] = (int32_t)(int16_t)(w[0] & 0xffffu); l[1] = (int32_t)w[0] >> 16;
+            l[2] = (int32_t)(int16_t)(w[1] & 0xffffu); l[3] = (int32_t)w[1] >> 16;
+        }
+    } else if (DEPTH == 32) {
+        if (STEREO) {
+#pragma unroll
+            for (int i = 0; i < 4; i++) { l[i] = (int32_t)w[2 * i] >> sh; r[i] = (int32_t)w[2 * i + 1] >> sh; }
+        } else {
+#pragma unroll
+            for (int i = 0; i < 4; i++) l[i] = (int32_t)w[i] >> sh;
+        }
+    } else if (DEPTH == 24) {
+        // sample >> 8 = the sign-extended 16-bit value at byte offset + 1
+        if (STEREO) {           // L at bytes 0, 6, 12, 18; R at 3, 9, 15, 21 of the quad's 6 words
+            l[0] = prmt_s16_at<0>(w[0], w[1]); r[0] = prmt_s16_at<3>(w[0], w[1]);
+            l[1] = prmt_s16_at<2>(w[1], w[2]); r[1] = prmt_s16_at<1>(w[2], w[3]);
+            l[2] = prmt_s16_at<0>(w[3], w[4]); r[2] = prmt_s16_at<3>(w[3], w[4]);
+            l[3] = prmt_s16_at<2>(w[4], w[5]); r[3] = prmt_s16_at<1>(w[5], w[5]);
+        } else {                // samples at bytes 0, 3, 6, 9 of the quad's 3 words
+            l[0] = prmt_s16_at<0>(w[0], w[1]); l[1] = prmt_s16_at<3>(w[0], w[1]);
+            l[2] = prmt_s16_at<2>(w[1], w[2]); l[3] = prmt_s16_at<1>(w[2], w[2]);
+        }
+    } else {                    // 20-bit, left-justified in 3 bytes: (w24 << 8) >> 12
+        if (STEREO) {
+            l[0] = (int32_t)prmt_u24hi_at<0>(w[0], w[1]) >> 12; r[0] = (int32_t)prmt_u24hi_at<3>(w[0], w[1]) >> 12;
+            l[1] = (int32_t)prmt_u24hi_at<2>(w[1], w[2]) >> 12; r[1] = (int32_t)prmt_u24hi_at<1>(w[2], w[3]) >> 12;
+            l[2] = (int32_t)prmt_u24hi_at<0>(w[3], w[4]) >> 12; r[2] = (int32_t)prmt_u24hi_at<3>(w[3], w[4]) >> 12;
+            l[3] = (int32_t)prmt_u24hi_at<2>(w[4], w[5]) >> 12; r[3] = (int32_t)prmt_u24hi_at<1>(w[5], w[5]) >> 12;
+        } else {
+            l[0] = (int32_t)prmt_u24hi_at<0>(w[0], w[1]) >> 12; l[1] = (int32_t)prmt_u24hi_at<3>(w[0], w[1]) >> 12;
+            l[2] = (int32_t)prmt_u24hi_at<2>(w[1], w[2]) >> 12; l[3] = (int32_t)prmt_u24hi_at<1>(w[2], w[2]) >> 12;
+        }
+    }
+}
+
+// One lane's ring over its packet's PCM.  The unit of transfer is a BLOCK: the smallest run of whole quads whose size
+// is a multiple of 16 bytes (16-bit stereo: 1 quad = 16 B; 24-bit stereo: 2 quads = 48 B; 32-bit stereo: 1 quad = 32 B;
+// mono: 2, 4, 1 quads), copied by 16-byte cp.async -- a warp's lanes sit in 32 different packets, so every request
+// costs 32 L1 wavefronts whatever its size, and the encode kernels of the wider depths were bound by exactly that
+// (l1tex 73-87 % busy with 4-byte requests).  kQuadAhead + 1 slots of one block each; granule g of a slot at
+// [slot * G + g][lane] as uint4, so the 128-bit accesses of a warp are conflict-free.  Only whole blocks of the packet
+// are ever read (the odd frames at either end go through the scalar path); a request past them copies nothing.
+// Needs the packet's first byte on a 16-byte boundary.
+template <int DEPTH, bool STEREO>
+struct QuadRing {
+    static constexpr uint32_t WQ = DenseElem<DEPTH, STEREO>::kQuadWords;
+    static constexpr uint32_t QB = (WQ % 4u == 0) ? 1u : (WQ % 2u == 0) ? 2u : 4u;     // quads per block
+    static constexpr uint32_t G = WQ * QB / 4u;                                       // 16-byte granules per block
+    static constexpr uint32_t kBlockFrames = 4u * QB;
+    static constexpr uint32_t kSlots = kQuadAhead + 1u;
+    static constexpr uint32_t kRows = G * kSlots;       // the CTA's ring array is uint4[kRows][32]
+    static_assert((kSlots & (kSlots - 1u)) == 0, "slot index is a mask");
+    const uint4 *base;          // granule 0 = sample-frame 0 of the packet (16-byte aligned)
+    uint32_t ring;              // shared-memory address of this lane's column
+    uint32_t blocks;            // whole blocks in the packet
+    __device__ __forceinline__ void start(const uint8_t *packet, uint32_t n, uint4 *ring_column)
+    {
+        base = reinterpret_cast<const uint4 *>(packet);
+        ring = (uint32_t)__cvta_generic_to_shared(ring_column);
+        blocks = n / kBlockFrames;
+    }
+    __device__ __forceinline__ uint32_t slot(uint32_t b) const { return ring + (b & (kSlots - 1u)) * (G * 512u); }
+    __device__ __forceinline__ void request(uint32_t b) const
+    {
+        if (b < blocks) {
+            const uint32_t dst = slot(b);
+            const uint4 *g = base + (size_t)b * G;
+#pragma unroll
+            for (uint32_t i = 0; i < G; i++)
+#ifndef ALAC_RING_CG
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst + i * 512u), "l"(g + i) : "memory");
+#else
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + i * 512u), "l"(g + i) : "memory");
+#endif
+        }
+        cp_async_commit();
+    }
+    __device__ __forceinline__ void read(uint32_t b, uint32_t (&w)[WQ * QB]) const
+    {
+        const uint32_t src = slot(b);
+#pragma unroll
+        for (uint32_t i = 0; i < G; i++) {
+            const uint4 v = lds_u128(src + i * 512u);
+            w[4 * i] = v.x; w[4 * i + 1] = v.y; w[4 * i + 2] = v.z; w[4 * i + 3] = v.w;
+        }
+    }
+};
+
+// The lane's (mixed) samples of block b, in order: f(i, x) for i = 0 .. kBlockFrames - 1.  The quads of a block run
+// through ONE copy of the caller's four-step body (the words of the later quads move down in registers): the bodies --
+// predictor step plus Golomb step -- are long and these kernels feel instruction-cache pressure.
+template <int DEPTH, bool STEREO, class F>
+__device__ __forceinline__ void ring_block_samples(const QuadRing<DEPTH, STEREO> &ring, uint32_t b, int32_t cl, int32_t cr, uint32_t sh_mix, F &&f)
+{
+    using R = QuadRing<DEPTH, STEREO>;
+    uint32_t w[R::WQ * R::QB];
+    ring.read(b, w);
+#pragma unroll 1
+    for (uint32_t qi = 0; qi < R::QB; qi++) {
+        uint32_t wq[R::WQ];
+#pragma unroll
+        for (uint32_t i = 0; i < R::WQ; i++) wq[i] = w[i];
+        int32_t l[4], rr[4];
+        unpack_quad<DEPTH, STEREO>(wq, l, rr);
+#pragma unroll
+        for (int i = 0; i < 4; i++) f(qi * 4u + (uint32_t)i, STEREO ? ((cl * l[i] + cr * rr[i]) >> sh_mix) : l[i]);
+        if (R::QB > 1) {
+#pragma unroll
+            for (uint32_t i = 0; i + R::WQ < R::WQ * R::QB; i++) w[i] = w[i + R::WQ];
+        }
+    }
+}
+
+// A dense element's sample source for the search passes: the scalar MixSrc (warm-up samples, the odd frames at either
+// end of a pass) plus the lane's word ring, through which predict_pass streams whole quads.
+template <int DEPTH, bool STEREO>
+struct DenseSrc : MixSrc<DEPTH, STEREO, true> {
+    static constexpr bool kWide = false;
+    static constexpr bool kDense = true;
+    static constexpr int kDepth = DEPTH;
+    static constexpr bool kStereo = STEREO;
+    QuadRing<DEPTH, STEREO> q;
+};
+
 // pc_block(in, res, num, coefs, TAPS) streamed: sink(j, residual) is called for j = 0..max(num,TAPS+1)-1
 // exactly as the reference writes pc1[j] (warm-up entries 1..TAPS are written regardless of num,
 // codec/dp_enc.c:108-112).  Requires num <= src.valid (true for every caller), so the main loop
@@ -182,6 +344,35 @@ __device__ __forceinline__ void predict_pass(const Src &src, uint32_t num, int32
         prev = x;
     }
     if (num <= TAPS + 1) return;
+    if constexpr (Src::kDense) {
+        // frames up to the first block boundary after the warm-up one by one, whole blocks through the ring
+        // (kQuadAhead blocks ahead of the arithmetic), then the odd frames after the last whole block of the pass
+        constexpr int DEPTH = Src::kDepth;
+        constexpr bool STEREO = Src::kStereo;
+        using R = QuadRing<DEPTH, STEREO>;
+        constexpr uint32_t b_first = (TAPS + 1 + R::kBlockFrames - 1) / R::kBlockFrames;
+        const uint32_t nb = num / R::kBlockFrames;
+        const R ring = src.q;
+        if (nb > b_first) {
+#pragma unroll
+            for (uint32_t d = 0; d < kQuadAhead; d++) ring.request(b_first + d);
+        }
+        uint32_t j = TAPS + 1;
+#pragma unroll 1
+        for (; j < b_first * R::kBlockFrames && j < num; j++) sink(j, predict_enc_step<TAPS, WRAP>(src.get(j), hist, a, chanshift));
+        if (nb > b_first) {
+            for (uint32_t b = b_first; b < nb; b++, j += R::kBlockFrames) {
+                ring.request(b + kQuadAhead);
+                cp_async_wait<kQuadAhead>();            // block b is in
+                ring_block_samples<DEPTH, STEREO>(ring, b, src.cl, src.cr, src.sh_mix,
+                                                  [&](uint32_t i, int32_t x) { sink(j + i, predict_enc_step<TAPS, WRAP>(x, hist, a, chanshift)); });
+            }
+            cp_async_wait<0>();
+        }
+#pragma unroll 1
+        for (; j < num; j++) sink(j, predict_enc_step<TAPS, WRAP>(src.get(j), hist, a, chanshift));
+        return;
+    }
     if constexpr (Src::kWide) {
         // single frames up to the next 16-byte boundary of the PCM, then blocks of four, then the remaining frames.
         // Head and tail share ONE copy of the scalar loop (two trips of the phase loop): the body -- predictor step
@@ -280,8 +471,8 @@ __device__ __forceinline__ void init_coefs_row(int32_t *a, int n)
 // taps search and the escape estimate of EncodeStereo / EncodeMono.  c4 / c8 are the lane's coefficient rows.
 struct SearchOut { uint32_t best_res, num_mine; int do_escape; };
 
-template <int DEPTH, bool STEREO, bool PACKED, bool WRAP>
-__device__ __forceinline__ SearchOut search_stages(MixSrc<DEPTH, STEREO, PACKED> &src, const EncArgs &A, bool valid, bool is_v, uint32_t n,
+template <int DEPTH, bool STEREO, bool WRAP, class Src>
+__device__ __forceinline__ SearchOut search_stages(Src &src, const EncArgs &A, bool valid, bool is_v, uint32_t n,
                                                    uint32_t partial, uint32_t pair_mask, uint32_t chan_bits, uint32_t chanshift,
                                                    uint32_t *slab, int32_t (&c4)[4], int32_t (&c8)[8])
 {
@@ -454,7 +645,7 @@ enc_search_kernel(EncArgs A, uint32_t elems_of_kind, uint32_t kind_elem0 /* bitm
         src.ring = pcm_ring_addr(s_pcm); src.ring_stride = (uint32_t)sizeof(uint4) * kSearchThreads;
         src.set_mix(0, is_v);
 
-        const SearchOut so = search_stages<DEPTH, STEREO, PACKED, WRAP>(src, A, valid, is_v, n, partial, pair_mask, chan_bits, chanshift, slab, c4, c8);
+        const SearchOut so = search_stages<DEPTH, STEREO, WRAP>(src, A, valid, is_v, n, partial, pair_mask, chan_bits, chanshift, slab, c4, c8);
         const uint32_t best_res = so.best_res, num_mine = so.num_mine;
         const int do_escape = so.do_escape;
 
@@ -561,7 +752,9 @@ struct JobLists {
     uint32_t max_jobs;
 };
 
-template <int DEPTH, bool STEREO, bool PACKED, bool WRAP>
+// DENSE: a dense element (see DenseElem) -- the passes stream their PCM through the lane's word ring instead of
+// per-sample loads (20/24/32-bit and mono streams; 16-bit packed stereo has its own 16-byte ring, MixSrc::kWide).
+template <int DEPTH, bool STEREO, bool PACKED, bool WRAP, bool DENSE = false>
 __global__ void __launch_bounds__(32, 20)
 enc_search_split_kernel(EncArgs A, uint32_t elems_of_kind, uint32_t kind_elem0, JobLists Q)
 {
@@ -600,12 +793,13 @@ enc_search_split_kernel(EncArgs A, uint32_t elems_of_kind, uint32_t kind_elem0, 
     uint32_t *slab = A.scratch + ((size_t)(pkt - A.pkt_base) * A.lay.chains_per_packet + chain) * A.cap_words;
     const uint32_t partial = (n != A.lay.frame_size);
 
-    __shared__ PcmRing<32> s_pcm;
-    MixSrc<DEPTH, STEREO, PACKED> src;
+    __shared__ uint4 s_ring[DENSE ? QuadRing<DEPTH, STEREO>::kRows : kPcmSlots][32];     // DENSE: block ring; else the 16-byte PCM ring of MixSrc::kWide
+    typename std::conditional<DENSE, DenseSrc<DEPTH, STEREO>, MixSrc<DEPTH, STEREO, PACKED>>::type src;
     src.base = base; src.stride = stride; src.valid = n;
-    src.ring = pcm_ring_addr(s_pcm); src.ring_stride = (uint32_t)sizeof(uint4) * 32u;
+    src.ring = (uint32_t)__cvta_generic_to_shared(&s_ring[0][0]) + threadIdx.x * 16u; src.ring_stride = (uint32_t)sizeof(uint4) * 32u;
+    if constexpr (DENSE) src.q.start(valid ? base : reinterpret_cast<const uint8_t *>(&s_ring[0][0]), valid ? n : 0u, &s_ring[0][lane]);
     src.set_mix(0, is_v);
-    const SearchOut so = search_stages<DEPTH, STEREO, PACKED, WRAP>(src, A, valid, is_v, n, partial, pair_mask, chan_bits, chanshift, slab, c4, c8);
+    const SearchOut so = search_stages<DEPTH, STEREO, WRAP>(src, A, valid, is_v, n, partial, pair_mask, chan_bits, chanshift, slab, c4, c8);
     const uint32_t best_res = so.best_res, num_mine = so.num_mine;
     const int do_escape = so.do_escape;
 
@@ -698,114 +892,10 @@ enc_final_kernel(EncArgs A, JobLists Q, uint32_t ctas_per_list)
 //
 // "Dense" elements only: a mono or stereo stream whose element is the whole sample-frame (no other channels in
 // between) and whose packets start on 4-byte boundaries.  Then a lane's PCM is one contiguous run of 32-bit words and
-// streams through a word ring in shared memory -- word w of lane l at [w mod kQuadRingWords][l], so every warp access
+// streams through a word ring in shared memory -- quad q of lane l in rows [(q mod 4) * WQ, + WQ) of column l, so every warp access
 // is conflict-free -- filled by 4-byte cp.async kQuadAhead quads (4 sample-frames each) ahead of the arithmetic.
 // 24-bit frames (6 bytes) unpack from the ring with one PRMT per sample (bytes o+1, o+2 and the sign of o+2: the
 // predictor input is sample >> 8); the per-sample byte loads of the generic path are gone.
-template <int DEPTH, bool STEREO> struct DenseElem {
-    static constexpr uint32_t kFrameBytes = DepthTraits<DEPTH>::kBytes * (STEREO ? 2u : 1u);
-    static constexpr uint32_t kQuadWords = kFrameBytes;          // 4 sample-frames = kFrameBytes 32-bit words
-};
-constexpr uint32_t kQuadRingWords = 32;     // per lane; >= (kQuadAhead + 1) quads of the widest element (8 words)
-constexpr uint32_t kQuadAhead = 3;
-constexpr uint32_t kEncTileRows = 32;
-
-// sign-extended 16-bit value at byte offset o (0..3) + 1 of the word pair (lo, hi): bytes o+1, o+2 -> (b2 << 8 | b1)
-template <uint32_t O> __device__ __forceinline__ int32_t prmt_s16_at(uint32_t lo, uint32_t hi)
-{
-    constexpr uint32_t b1 = O + 1u, b2 = O + 2u;                 // byte indices into {lo: 0..3, hi: 4..7}
-    constexpr uint32_t sel = b1 | (b2 << 4) | ((b2 | 8u) << 8) | ((b2 | 8u) << 12);     // nibble msb = replicate the byte's sign
-    uint32_t d;
-    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(lo), "r"(hi), "n"(sel));       // (__byte_perm ignores the msb of a nibble)
-    return (int32_t)d;
-}
-// 24-bit container at byte offset O of the word pair, as a left-justified 32-bit word (sample << 8)
-template <uint32_t O> __device__ __forceinline__ uint32_t prmt_u24hi_at(uint32_t lo, uint32_t hi)
-{
-    constexpr uint32_t sel = (O << 4) | ((O + 1u) << 8) | ((O + 2u) << 12);   // byte 0 <- lo.b0 (garbage, shifted out below)
-    return __byte_perm(lo, hi, sel) & 0xffffff00u;
-}
-
-// the four (left, right) -- or four mono -- samples of a quad, after the depth's shift (what the predictor sees)
-template <int DEPTH, bool STEREO>
-__device__ __forceinline__ void unpack_quad(const uint32_t (&w)[DenseElem<DEPTH, STEREO>::kQuadWords], int32_t (&l)[4], int32_t (&r)[4])
-{
-    constexpr uint32_t sh = DepthTraits<DEPTH>::kShift;
-    if (DEPTH == 16) {
-        if (STEREO) {
-#pragma unroll
-            for (int i = 0; i < 4; i++) { l[i] = (int32_t)(int16_t)(w[i] & 0xffffu); r[i] = (int32_t)w[i] >> 16; }
-        } else {
-            l[0] = (int32_t)(int16_t)(w[0] & 0xffffu); l[1] = (int32_t)w[0] >> 16;
-            l[2] = (int32_t)(int16_t)(w[1] & 0xffffu); l[3] = (int32_t)w[1] >> 16;
-        }
-    } else if (DEPTH == 32) {
-        if (STEREO) {
-#pragma unroll
-            for (int i = 0; i < 4; i++) { l[i] = (int32_t)w[2 * i] >> sh; r[i] = (int32_t)w[2 * i + 1] >> sh; }
-        } else {
-#pragma unroll
-            for (int i = 0; i < 4; i++) l[i] = (int32_t)w[i] >> sh;
-        }
-    } else if (DEPTH == 24) {
-        // sample >> 8 = the sign-extended 16-bit value at byte offset + 1
-        if (STEREO) {           // L at bytes 0, 6, 12, 18; R at 3, 9, 15, 21 of the quad's 6 words
-            l[0] = prmt_s16_at<0>(w[0], w[1]); r[0] = prmt_s16_at<3>(w[0], w[1]);
-            l[1] = prmt_s16_at<2>(w[1], w[2]); r[1] = prmt_s16_at<1>(w[2], w[3]);
-            l[2] = prmt_s16_at<0>(w[3], w[4]); r[2] = prmt_s16_at<3>(w[3], w[4]);
-            l[3] = prmt_s16_at<2>(w[4], w[5]); r[3] = prmt_s16_at<1>(w[5], w[5]);
-        } else {                // samples at bytes 0, 3, 6, 9 of the quad's 3 words
-            l[0] = prmt_s16_at<0>(w[0], w[1]); l[1] = prmt_s16_at<3>(w[0], w[1]);
-            l[2] = prmt_s16_at<2>(w[1], w[2]); l[3] = prmt_s16_at<1>(w[2], w[2]);
-        }
-    } else {                    // 20-bit, left-justified in 3 bytes: (w24 << 8) >> 12
-        if (STEREO) {
-            l[0] = (int32_t)prmt_u24hi_at<0>(w[0], w[1]) >> 12; r[0] = (int32_t)prmt_u24hi_at<3>(w[0], w[1]) >> 12;
-            l[1] = (int32_t)prmt_u24hi_at<2>(w[1], w[2]) >> 12; r[1] = (int32_t)prmt_u24hi_at<1>(w[2], w[3]) >> 12;
-            l[2] = (int32_t)prmt_u24hi_at<0>(w[3], w[4]) >> 12; r[2] = (int32_t)prmt_u24hi_at<3>(w[3], w[4]) >> 12;
-            l[3] = (int32_t)prmt_u24hi_at<2>(w[4], w[5]) >> 12; r[3] = (int32_t)prmt_u24hi_at<1>(w[5], w[5]) >> 12;
-        } else {
-            l[0] = (int32_t)prmt_u24hi_at<0>(w[0], w[1]) >> 12; l[1] = (int32_t)prmt_u24hi_at<3>(w[0], w[1]) >> 12;
-            l[2] = (int32_t)prmt_u24hi_at<2>(w[1], w[2]) >> 12; l[3] = (int32_t)prmt_u24hi_at<1>(w[2], w[2]) >> 12;
-        }
-    }
-}
-
-// One lane's word ring over its packet's PCM (see above).
-template <int DEPTH, bool STEREO>
-struct QuadRing {
-    static constexpr uint32_t WQ = DenseElem<DEPTH, STEREO>::kQuadWords;
-    const uint32_t *base;       // word 0 = sample-frame 0 of the packet (4-byte aligned)
-    uint32_t ring;              // shared-memory address of this lane's column
-    uint32_t words;             // words that hold the packet's n frames, rounded up
-    uint32_t last_bytes;        // packet bytes inside the last word (1..4)
-    __device__ __forceinline__ void start(const uint8_t *packet, uint32_t n, uint32_t *ring_column)
-    {
-        base = reinterpret_cast<const uint32_t *>(packet);
-        ring = (uint32_t)__cvta_generic_to_shared(ring_column);
-        const uint32_t nbytes = n * DenseElem<DEPTH, STEREO>::kFrameBytes;
-        words = (nbytes + 3u) >> 2;
-        last_bytes = ((nbytes - 1u) & 3u) + 1u;
-    }
-    __device__ __forceinline__ uint32_t slot(uint32_t w) const { return ring + (w & (kQuadRingWords - 1u)) * 128u; }
-    // request the WQ words of quad q; words past the packet read nothing and arrive as zero
-    __device__ __forceinline__ void request(uint32_t q)
-    {
-#pragma unroll
-        for (uint32_t i = 0; i < WQ; i++) {
-            const uint32_t w = q * WQ + i;
-            const bool in = w < words;
-            cp_async_word(slot(w), base + (in ? w : 0u), in ? (w + 1u == words ? last_bytes : 4u) : 0u);
-        }
-        cp_async_commit();
-    }
-    __device__ __forceinline__ void read(uint32_t q, uint32_t (&w)[WQ]) const
-    {
-#pragma unroll
-        for (uint32_t i = 0; i < WQ; i++) w[i] = lds_u32(slot(q * WQ + i));
-    }
-};
-
 // SPLIT = true: the two-warp form (64-thread CTAs).  SPLIT = false: the same dense PCM path with predictor and coder
 // on ONE warp (32-thread CTAs, no residual tiles, no barriers): once a launch holds several waves of jobs the GPU is
 // throughput-bound, the coder warp's idle half only costs occupancy, and the one-warp form is the faster one
@@ -814,7 +904,7 @@ template <int DEPTH, bool STEREO, bool WRAP, bool SPLIT>
 __global__ void __launch_bounds__(SPLIT ? 64 : 32, SPLIT ? 12 : 24)
 enc_final2_kernel(EncArgs A, JobLists Q, uint32_t ctas_per_list)
 {
-    __shared__ uint32_t s_ring[kQuadRingWords][32];
+    __shared__ uint4 s_ring[QuadRing<DEPTH, STEREO>::kRows][32];
     __shared__ int32_t s_res[SPLIT ? 2 : 1][SPLIT ? kEncTileRows : 1][32];
 
     const uint32_t w = threadIdx.x >> 5, lane = threadIdx.x & 31u;
@@ -868,7 +958,9 @@ enc_final2_kernel(EncArgs A, JobLists Q, uint32_t ctas_per_list)
     src.valid = n;
     QuadRing<DEPTH, STEREO> ring;
     ring.start(have ? J.base : reinterpret_cast<const uint8_t *>(s_ring), n, &s_ring[0][lane]);
-    const uint32_t nq = n >> 2;             // whole quads of the packet
+    using R = QuadRing<DEPTH, STEREO>;
+    static_assert(kEncTileRows % R::kBlockFrames == 0, "a tile is a whole number of blocks");
+    const uint32_t nblk = ring.blocks;      // whole blocks of the packet
     auto run = [&](auto taps_tag) {
         constexpr int TAPS = decltype(taps_tag)::value;
         int32_t a[TAPS], hist[TAPS + 1];
@@ -876,11 +968,11 @@ enc_final2_kernel(EncArgs A, JobLists Q, uint32_t ctas_per_list)
         for (int k = 0; k < TAPS; k++) a[k] = J.coef[k];
 #pragma unroll
         for (int k = 0; k <= TAPS; k++) hist[k] = 0;
-        // quads q_first .. q_first + kQuadAhead - 1 are requested up front; the warm-up samples and the frames up to
-        // the first quad boundary after them go through the scalar path
-        constexpr uint32_t q_first = (TAPS + 1 + 3) / 4;         // first quad that is all predictor steps (3 for 8 taps, 2 for 4)
+        // blocks b_first .. b_first + kQuadAhead - 1 are requested up front; the warm-up samples and the frames up to
+        // the first block boundary after them go through the scalar path
+        constexpr uint32_t b_first = (TAPS + 1 + R::kBlockFrames - 1) / R::kBlockFrames;
 #pragma unroll
-        for (uint32_t d = 0; d < kQuadAhead; d++) ring.request(q_first + d);
+        for (uint32_t d = 0; d < kQuadAhead; d++) ring.request(b_first + d);
         int32_t *col = &s_res[0][0][lane];
         // residual of sample-frame j0 + r: to the tile (two-warp form) or straight into the coder
         auto put = [&](uint32_t r, uint32_t j, int32_t err) {
@@ -908,27 +1000,23 @@ enc_final2_kernel(EncArgs A, JobLists Q, uint32_t ctas_per_list)
                     hist[TAPS - j] = x;
                     prev = x;
                 }
-                for (r = TAPS + 1; r < q_first * 4u && r < n; r++) put(r, r, predict_enc_step<TAPS, WRAP>(src.get(r), hist, a, chanshift));
-                r = q_first * 4u;
+#pragma unroll 1
+                for (r = TAPS + 1; r < b_first * R::kBlockFrames && r < n; r++) put(r, r, predict_enc_step<TAPS, WRAP>(src.get(r), hist, a, chanshift));
+                r = b_first * R::kBlockFrames;
             }
-            // whole quads of this tile
-            for (; r < kEncTileRows; r += 4) {
-                const uint32_t q = (j0 + r) >> 2;
-                if (q < nq) {
-                    ring.request(q + kQuadAhead);
-                    cp_async_wait<kQuadAhead>();            // quad q is in
-                    uint32_t wq[QuadRing<DEPTH, STEREO>::WQ];
-                    ring.read(q, wq);
-                    int32_t l[4], rr[4];
-                    unpack_quad<DEPTH, STEREO>(wq, l, rr);
-#pragma unroll
-                    for (int i = 0; i < 4; i++) {
-                        const int32_t x = STEREO ? ((src.cl * l[i] + src.cr * rr[i]) >> src.sh_mix) : l[i];
+            // whole blocks of this tile
+            for (; r < kEncTileRows; r += R::kBlockFrames) {
+                const uint32_t blk = (j0 + r) / R::kBlockFrames;
+                if (blk < nblk) {
+                    ring.request(blk + kQuadAhead);
+                    cp_async_wait<kQuadAhead>();            // block blk is in
+                    ring_block_samples<DEPTH, STEREO>(ring, blk, src.cl, src.cr, src.sh_mix, [&](uint32_t i, int32_t x) {
                         put(r + i, j0 + r + i, predict_enc_step<TAPS, WRAP>(x, hist, a, chanshift));
-                    }
+                    });
                 } else {
-                    // the odd frames after the last whole quad (and nothing at all past n)
-                    for (uint32_t i = 0; i < 4 && j0 + r + i < n; i++)
+                    // the odd frames after the last whole block (and nothing at all past n)
+#pragma unroll 1
+                    for (uint32_t i = 0; i < R::kBlockFrames && j0 + r + i < n; i++)
                         put(r + i, j0 + r + i, predict_enc_step<TAPS, WRAP>(src.get(j0 + r + i), hist, a, chanshift));
                 }
             }
@@ -1472,7 +1560,8 @@ static uint32_t enc_launch_search_v(cudaStream_t s, const EncArgs &A, uint32_t m
         if (split) {
             const uint32_t ctas = (uint32_t)((threads + 31) / 32);
             if (ev) cudaEventRecord(ev[0], s);
-            enc_search_split_kernel<DEPTH, true, PACKED, WRAP><<<ctas, 32, 0, s>>>(A, pairs, pair_mask, *split);
+            if (PACKED && DEPTH != 16 && dense) enc_search_split_kernel<DEPTH, true, PACKED && DEPTH != 16, WRAP, PACKED && DEPTH != 16><<<ctas, 32, 0, s>>>(A, pairs, pair_mask, *split);
+            else enc_search_split_kernel<DEPTH, true, PACKED, WRAP><<<ctas, 32, 0, s>>>(A, pairs, pair_mask, *split);
             if (ev) cudaEventRecord(ev[1], s);
             if (dense == 2) enc_final2_kernel<DEPTH, true, WRAP, true><<<2 * ctas, 64, 0, s>>>(A, *split, ctas);
             else if (dense) enc_final2_kernel<DEPTH, true, WRAP, false><<<2 * ctas, 32, 0, s>>>(A, *split, ctas);
@@ -1492,7 +1581,8 @@ static uint32_t enc_launch_search_v(cudaStream_t s, const EncArgs &A, uint32_t m
             JobLists Qm = *split;
             Qm.counts += 2;     // the mono launch has its own pair of counters
             if (ev) cudaEventRecord(ev[3], s);
-            enc_search_split_kernel<DEPTH, false, false, WRAP><<<ctas, 32, 0, s>>>(A, monos, mono_mask, Qm);
+            if (dense) enc_search_split_kernel<DEPTH, false, false, WRAP, true><<<ctas, 32, 0, s>>>(A, monos, mono_mask, Qm);
+            else enc_search_split_kernel<DEPTH, false, false, WRAP><<<ctas, 32, 0, s>>>(A, monos, mono_mask, Qm);
             if (ev) cudaEventRecord(ev[4], s);
             if (dense == 2) enc_final2_kernel<DEPTH, false, WRAP, true><<<2 * ctas, 64, 0, s>>>(A, Qm, ctas);
             else if (dense) enc_final2_kernel<DEPTH, false, WRAP, false><<<2 * ctas, 32, 0, s>>>(A, Qm, ctas);

@@ -629,10 +629,9 @@ static int32_t encode_core(alac_b200_engine *e, const alac_b200_enc_config *cfg,
     // starting from init_coefs (|a| <= 1216) the int16 range cannot be left within K frames if this holds
     const bool wrap = coef_state != nullptr || K == 0 || (uint64_t)K * 2u * F + 1216u > 32767u;
     const bool packed = cfg->channels == 2 && (reinterpret_cast<uintptr_t>(d_pcm) & 7u) == 0;
-    // dense: a mono or stereo stream whose packets all start on 4-byte boundaries (see enc_final2_kernel)
-    bool dense = cfg->channels <= 2 && (reinterpret_cast<uintptr_t>(d_pcm) & 3u) == 0 && (F == 1 || ((uint64_t)F * bpf) % 4 == 0 || P == n_streams);
-    for (uint64_t s = 0; s < n_streams && dense; s++) dense = (streams[s].first_sample_frame * bpf) % 4 == 0;
-    if (dense && ((uint64_t)F * bpf) % 4 != 0) for (uint32_t p = 0; p < P && dense; p++) dense = (h_pkt_frame[p] * bpf) % 4 == 0;
+    // dense: a mono or stereo stream whose packets all start on 16-byte boundaries (see QuadRing, enc_final2_kernel)
+    bool dense = cfg->channels <= 2 && (reinterpret_cast<uintptr_t>(d_pcm) & 15u) == 0 && (((uint64_t)F * bpf) % 16 == 0 || P == n_streams);
+    for (uint64_t s = 0; s < n_streams && dense; s++) dense = (streams[s].first_sample_frame * bpf) % 16 == 0;
     // developer override: 0 = the generic final pass, 1 = dense one-warp form, 2 = dense two-warp form, default = by job count
     static const int final2_mode = [] { const char *v = getenv("ALAC_B200_FINAL2"); return v ? atoi(v) : -1; }();
     if (final2_mode == 0) dense = false;

@@ -1531,7 +1531,7 @@ __global__ void __launch_bounds__(kAsmWarps * 32) enc_assemble_kernel(AsmArgs A)
         const uint32_t word = gather(0, nb);
         for (uint32_t b = 0; b < nb; b++) dst[b] = (uint8_t)(word >> (24 - 8 * b));
     }
-    for (uint32_t g = lane; g < words_total; g += 32) {
+    auto put_word = [&](uint32_t g) {
         const uint32_t byte0 = lead_bytes + 4u * g;
         const uint32_t nbytes = min(4u, size - byte0);
         const uint32_t word = gather(byte0, nbytes);
@@ -1540,7 +1540,71 @@ __global__ void __launch_bounds__(kAsmWarps * 32) enc_assemble_kernel(AsmArgs A)
         } else {
             for (uint32_t b = 0; b < nbytes; b++) dst[byte0 + b] = (uint8_t)(word >> (24 - 8 * b));
         }
+    };
+    // Almost every output word lies wholly inside ONE long region -- a Golomb stream in the slab or the shift bytes of
+    // the PCM -- and is then a funnel shift of two consecutive source words (or two or three fixed-width PCM entries):
+    // those words take the short path below, region by region.  The few words in between (headers, region
+    // boundaries, the tail of the packet) go through the general gather.
+    const uint32_t lead_bits = lead_bytes * 8u;
+    const uint32_t full_words = size > lead_bytes ? (size - lead_bytes) / 4u : 0u;      // output words that are whole
+    uint32_t done_to = 0;                                                               // words [0, done_to) are written
+    for (uint32_t ri = 0; ri < nreg; ri++) {
+        const Region r = R[ri];
+        if (r.nbits < 96u || r.kind == REG_RAW || (r.kind == REG_WORDS && r.dst + r.nbits <= lead_bits)) continue;
+        // whole output words inside the region: word g = packet bits [lead_bits + 32 g, + 32)
+        const uint32_t g_lo = r.dst > lead_bits ? (r.dst - lead_bits + 31u) / 32u : 0u;
+        const uint32_t g_hi = min(full_words, (r.dst + r.nbits - lead_bits) / 32u);
+        if (g_hi <= g_lo || g_lo < done_to) continue;
+        for (uint32_t g = done_to + lane; g < g_lo; g += 32) put_word(g);                    // the words before it
+        // four words per lane and trip: all their loads are issued before the first store (the kernel is otherwise
+        // bound by the latency of loads that are used at once)
+        constexpr uint32_t kU = 4;
+        if (r.kind == REG_WORDS) {
+            for (uint32_t g0 = g_lo + lane; g0 < g_hi; g0 += 32u * kU) {
+                uint32_t whi[kU], wlo[kU];
+#pragma unroll
+                for (uint32_t u = 0; u < kU; u++) {
+                    const uint32_t g = min(g0 + 32u * u, g_hi - 1u);
+                    const uint32_t i = (lead_bits + 32u * g - r.dst) >> 5;
+                    whi[u] = r.words[i];
+                    wlo[u] = r.words[i + 1];        // (the slab has spare words past every stream)
+                }
+#pragma unroll
+                for (uint32_t u = 0; u < kU; u++) {
+                    const uint32_t g = g0 + 32u * u;
+                    if (g < g_hi) *reinterpret_cast<uint32_t *>(dst + lead_bytes + 4u * g) = bswap32(__funnelshift_l(wlo[u], whi[u], (lead_bits - r.dst) & 31u));
+                }
+            }
+        } else {
+            constexpr uint32_t sh = shift ? shift : 8u;
+            constexpr uint32_t mask = (1u << sh) - 1u;
+            const bool stereo = (A.lay.elem_tag[r.elem] == ID_CPE);
+            const uint8_t *eb = frame_base + (size_t)A.lay.elem_chan[r.elem] * bps;
+            for (uint32_t g0 = g_lo + lane; g0 < g_hi; g0 += 32u * kU) {
+                uint32_t word[kU];
+#pragma unroll
+                for (uint32_t u = 0; u < kU; u++) {
+                    const uint32_t g = min(g0 + 32u * u, g_hi - 1u);
+                    const uint32_t off = lead_bits + 32u * g - r.dst;
+                    if (stereo) {
+                        word[u] = bits_from_entries(2 * sh, off, 32u, [&](uint32_t i) -> uint32_t {
+                            const uint8_t *p = eb + (size_t)i * stride;
+                            return ((load_raw_bits<DEPTH>(p) & mask) << sh) | (load_raw_bits<DEPTH>(p + bps) & mask);
+                        });
+                    } else {
+                        word[u] = bits_from_entries(sh, off, 32u, [&](uint32_t i) -> uint32_t { return load_raw_bits<DEPTH>(eb + (size_t)i * stride) & mask; });
+                    }
+                }
+#pragma unroll
+                for (uint32_t u = 0; u < kU; u++) {
+                    const uint32_t g = g0 + 32u * u;
+                    if (g < g_hi) *reinterpret_cast<uint32_t *>(dst + lead_bytes + 4u * g) = bswap32(word[u]);
+                }
+            }
+        }
+        done_to = g_hi;
     }
+    for (uint32_t g = done_to + lane; g < words_total; g += 32) put_word(g);
 }
 
 

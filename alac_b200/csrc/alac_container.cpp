@@ -124,6 +124,13 @@ int32_t alac_b200_caf_write(const char *path, uint32_t sample_rate, uint32_t cha
     if (channels < 1 || channels > 8) return kParamError;
     const uint32_t flags = bit_depth == 16 ? 1u : bit_depth == 20 ? 2u : bit_depth == 24 ? 3u : bit_depth == 32 ? 4u : 0u;
     if (!flags) return kParamError;
+    // the 'desc' and 'pakt' arithmetic below is the reference's: 4096 frames per packet (kALACDefaultFramesPerPacket,
+    // convert-utility/main.cu:286, CAFFileALAC.cpp:260-286).  A cookie that says otherwise would give a file whose chunks disagree.
+    if (cookie_size < 24) return kParamError;
+    {
+        const uint8_t *c = static_cast<const uint8_t *>(cookie);
+        if (((uint32_t)c[0] << 24 | (uint32_t)c[1] << 16 | (uint32_t)c[2] << 8 | c[3]) != 4096u) return kParamError;
+    }
     File out(path, "wb");
     if (!out.f) return kFileNotFound;
 
@@ -194,6 +201,9 @@ int32_t alac_b200_caf_probe(const char *path, alac_b200_caf_info *info)
         if (fread(ch, 1, 12, in.f) != 12) break;
         uint64_t size = be64(ch + 4);
         const uint64_t body = (uint64_t)ftell(in.f);
+        // chunk sizes come from the file: every chunk but a to-end-of-file 'data' must lie inside it (a negative or
+        // huge size would otherwise seek backwards and walk the same chunks forever)
+        if (memcmp(ch, "data", 4) && (size > file_size || body + size > file_size)) return kParamError;
         if (!memcmp(ch, "desc", 4)) {
             uint8_t d[32];
             if (size < 32 || fread(d, 1, 32, in.f) != 32) return kParamError;
@@ -237,6 +247,9 @@ uint64_t alac_b200_caf_read_table(const char *path, const alac_b200_caf_info *in
     if (!path || !info || !sizes) return 0;
     File in(path, "rb");
     if (!in.f) return 0;
+    fseek(in.f, 0, SEEK_END);
+    const uint64_t file_size = (uint64_t)ftell(in.f);
+    if (info->table_offset > file_size || info->table_bytes > file_size - info->table_offset) return 0;     // (a caller-made info)
     std::vector<uint8_t> t((size_t)info->table_bytes);
     fseek(in.f, (long)info->table_offset, SEEK_SET);
     if (fread(t.data(), 1, t.size(), in.f) != t.size()) return 0;

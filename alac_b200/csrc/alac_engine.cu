@@ -643,6 +643,7 @@ static int32_t encode_core(alac_b200_engine *e, const alac_b200_enc_config *cfg,
     uint64_t *d_job_total = e->xwords.as<uint64_t>() + 1;   // placed, home rank: bytes of the whole job
     uint32_t *d_xerr = reinterpret_cast<uint32_t *>(e->xwords.as<uint64_t>() + 2);
     std::vector<cudaEvent_t> comp_done, scan_done;
+    int last_dense_form = 0;
     const bool trace = getenv("ALAC_B200_TRACE") != nullptr;
     const auto host_t0 = std::chrono::steady_clock::now();
     size_t tile_at = 0;
@@ -705,6 +706,7 @@ static int32_t encode_core(alac_b200_engine *e, const alac_b200_enc_config *cfg,
         // two-warp final pass while the launch's jobs do not fill the GPU (about one wave of one-warp CTAs: 148 SMs x 24 x 32 jobs)
         const uint64_t jobs_in_launch = (uint64_t)c.cnt * L.chains_per_packet;
         const int dense_form = !dense ? 0 : final2_mode > 0 ? final2_mode : (jobs_in_launch <= 148ull * 24 * 32 ? 2 : 1);
+        last_dense_form = split ? dense_form : 0;
         t_search.push_back(e->timer());
         // (before, between search and final, after) events of the pair launch and of the mono launch (split form)
         cudaEvent_t mid[6];
@@ -854,6 +856,8 @@ static int32_t encode_core(alac_b200_engine *e, const alac_b200_enc_config *cfg,
         for (size_t i = 0; i + 1 < t_asm.size(); i += 2) { float ms = 0; cudaEventElapsedTime(&ms, t_asm[i], t_asm[i + 1]); stats->ms_assemble += ms; }
         for (size_t i = 0; i + 2 < e->t_mid.size(); i += 3) { float ms = 0; cudaEventElapsedTime(&ms, e->t_mid[i + 1], e->t_mid[i + 2]); stats->ms_final += ms; }
         stats->ms_search -= stats->ms_final;
+        stats->final_form = (uint32_t)last_dense_form;
+        stats->search_dense = (last_dense_form && ((pair_mask && packed && cfg->bit_depth != 16) || (!pair_mask && mono_mask))) ? 1u : 0u;
         if (pl) stats->payload_bytes = total;
     }
     return ALAC_B200_OK;

@@ -52,7 +52,8 @@ class Stats(C.Structure):
                 ("max_packet_bytes", C.c_uint32), ("kernel_launches", C.c_uint32),
                 ("ms_h2d", C.c_float), ("ms_kernels", C.c_float), ("ms_d2h", C.c_float),
                 ("ms_search", C.c_float), ("ms_assemble", C.c_float), ("ms_decode", C.c_float),
-                ("ms_final", C.c_float), ("ms_entropy", C.c_float), ("ms_finish", C.c_float), ("ms_fused", C.c_float)]
+                ("ms_final", C.c_float), ("ms_entropy", C.c_float), ("ms_finish", C.c_float), ("ms_fused", C.c_float),
+                ("final_form", C.c_uint32), ("search_dense", C.c_uint32)]
 
     def as_dict(self) -> dict:
         return {n: getattr(self, n) for n, _ in self._fields_}

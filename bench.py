@@ -225,9 +225,14 @@ def run_reference(args):
 
 # ------------------------------------------------------------------------------------------------
 # ncu symbols of the kernels a step launches, by the name the engine's per-kernel timers use
-def kernel_symbols(depth: int) -> dict:
-    return {"enc_search_split": f"alacb::enc_search_split_kernel<{depth}, true, true, false>",
-            "enc_final": f"alacb::enc_final_kernel<{depth}, true, true, false>",
+def kernel_symbols(depth: int, final_form: int = 2, search_dense: int = 0) -> dict:
+    """final_form / search_dense: which kernels the engine picked (alac_b200_stats): the final pass is enc_final2_kernel
+    <depth, stereo, wrap, two-warp> for dense streams, the search kernel carries a fifth `dense` argument for the
+    block-ring form (20/24/32-bit and mono)."""
+    final = (f"alacb::enc_final_kernel<{depth}, true, true, false>" if not final_form
+             else f"alacb::enc_final2_kernel<{depth}, true, false, {'true' if final_form == 2 else 'false'}>")
+    return {"enc_search_split": f"alacb::enc_search_split_kernel<{depth}, true, true, false, {'true' if search_dense else 'false'}>",
+            "enc_final": final,
             "enc_assemble": f"alacb::enc_assemble_kernel<{depth}>",
             "dec_fused": f"alacb::dec_fused_kernel<{depth}>",
             "dec_entropy": f"alacb::dec_entropy_kernel<{depth}>",
@@ -404,7 +409,9 @@ def measure_device(W: Work, ctx, steps: int, warmup: int, sampler=None):
             acc[k] = enc.stats[k] * steps
         for k in ("ms_entropy", "ms_finish", "ms_fused"):
             acc[k] = dd.stats[k] * steps
+        es = enc.stats
         del pk_l
+    m.final_form, m.search_dense = int(es["final_form"]), int(es["search_dense"])
     m.kernels = {"enc_search_split": acc["ms_search"] / steps, "enc_final": acc["ms_final"] / steps,
                  "enc_assemble": acc["ms_assemble"] / steps, "dec_fused": acc["ms_fused"] / steps,
                  "dec_entropy": acc["ms_entropy"] / steps, "dec_finish": acc["ms_finish"] / steps}
@@ -460,14 +467,20 @@ def run_cuda(args):
     n_slices = (m.frames_rank + slice_frames - 1) // slice_frames
     slice_pk = (slice_frames + FRAME - 1) // FRAME
     pcm_h = torch.empty(slice_frames * W.bpf, dtype=torch.uint8).pin_memory()
-    pk_hs = [torch.empty(alac_b200.encode_bound(cfg, slice_frames), dtype=torch.uint8).pin_memory() for _ in range(3)]
-    sz_hs = [torch.empty(slice_pk, dtype=torch.int32).pin_memory() for _ in range(3)]
-    out_h = torch.empty(slice_frames * W.bpf, dtype=torch.uint8).pin_memory()
-    pcm_np, out_np = pcm_h.numpy(), out_h.numpy()
+    # engines per direction in the pipelined leg.  One each is the measured optimum: a second pair gains 2 % on the 1-hour
+    # 16-bit slices (28.1 against 28.7 ms) and loses 14 % on the 2 GB slices of the 24/96 corpus (903 against 790 ms)
+    D = max(1, int(os.environ.get("ALAC_BENCH_E2E_DEPTH", "1")))
+    nbuf = 2 * D + 1
+    pk_hs = [torch.empty(alac_b200.encode_bound(cfg, slice_frames), dtype=torch.uint8).pin_memory() for _ in range(nbuf)]
+    sz_hs = [torch.empty(slice_pk, dtype=torch.int32).pin_memory() for _ in range(nbuf)]
+    out_hs = [torch.empty(slice_frames * W.bpf, dtype=torch.uint8).pin_memory() for _ in range(D)]
+    pcm_np, out_nps = pcm_h.numpy(), [t.numpy() for t in out_hs]
+    out_np = out_nps[0]
     pk_np = [t.numpy() for t in pk_hs]
     sz_np = [t.numpy().view(np.uint32) for t in sz_hs]
     pcm_h.copy_(pcm_d[:slice_frames * W.bpf])
-    eng_dec = alac_b200.Engine(local)       # second engine on the same GPU: the decode leg of the pipeline
+    enc_engs = [eng] + [alac_b200.Engine(local) for _ in range(D - 1)]
+    dec_engs = [alac_b200.Engine(local) for _ in range(D)]      # further engines on the same GPU: the decode leg of the pipeline
 
     def step_host():
         """one slice, strictly alternating synchronous calls: host PCM -> host packets -> host PCM"""
@@ -476,31 +489,37 @@ def run_cuda(args):
         return e_, d_
 
     def pipeline_host(n):
-        """n slices through two engines, both kept busy: the encode engine starts slice i+1 as soon as it has finished slice i
-        (alac_b200_encode_submit), the decode engine takes slice i as soon as it has finished slice i-1
-        (alac_b200_decode_submit); three packet buffers rotate between them.  PCM going up for the next encode and PCM coming
-        down from the previous decode share the full-duplex link.  Every slice still goes host -> device -> host (packets)
-        -> device -> host (PCM), all inside the timed region."""
-        wait_enc = eng.encode_submit(pcm_np, cfg, out=pk_np[0], out_sizes=sz_np[0])
-        wait_dec = None
+        """n slices through D encode engines and D decode engines, all kept busy with the asynchronous forms of the C ABI
+        (alac_b200_encode_submit / alac_b200_decode_submit, one call in flight per engine): slice i is encoded by engine
+        i mod D and decoded by decode engine i mod D; 2 D + 1 packet buffers rotate between them.  The tail of one call (its
+        last kernels, its last bytes coming down) overlaps the head of the next, so both directions of the link stay
+        busy.  Every slice still goes host -> device -> host (packets) -> device -> host (PCM), all inside the timed
+        region."""
+        enc_wait, dec_wait = {}, {}
+        for j in range(min(D, n)):
+            enc_wait[j] = enc_engs[j % D].encode_submit(pcm_np, cfg, out=pk_np[j % nbuf], out_sizes=sz_np[j % nbuf])
         d_ = None
         for i in range(n):
-            e_ = wait_enc()
-            if i + 1 < n:
-                wait_enc = eng.encode_submit(pcm_np, cfg, out=pk_np[(i + 1) % 3], out_sizes=sz_np[(i + 1) % 3])
-            if wait_dec is not None:
-                d_ = wait_dec()
-            wait_dec = eng_dec.decode_submit(e_.cookie, e_.packets, e_.sizes, out=out_np)
-        d_ = wait_dec()
+            e_ = enc_wait.pop(i)()
+            j = i + D                               # (its packet buffer was last read by the decode of slice i - D - 1: done)
+            if j < n:
+                enc_wait[j] = enc_engs[j % D].encode_submit(pcm_np, cfg, out=pk_np[j % nbuf], out_sizes=sz_np[j % nbuf])
+            if (i - D) in dec_wait:                 # decode engine i mod D is free after this
+                d_ = dec_wait.pop(i - D)()
+            dec_wait[i] = dec_engs[i % D].decode_submit(e_.cookie, e_.packets, e_.sizes, out=out_nps[i % D])
+        for i in sorted(dec_wait):
+            d_ = dec_wait[i]()
         return e_, d_
 
     e_, d_ = step_host()
     assert np.array_equal(d_.pcm, pcm_np), "host-buffer round trip is not the identity"
     out_np[:] = 0
-    e_, d_ = pipeline_host(2)
-    assert np.array_equal(d_.pcm, pcm_np), "pipelined host-buffer round trip is not the identity"
+    for o in out_nps:
+        o[:] = 0
+    e_, d_ = pipeline_host(2 * D)
+    assert all(np.array_equal(o, pcm_np) for o in out_nps), "pipelined host-buffer round trip is not the identity"
     slice_payload = e_.nbytes
-    e2e_steps = max(1, min(args.steps, 10 if n_slices == 1 else 1))
+    e2e_steps = max(1, min(args.steps, 20 if n_slices == 1 else 1))
 
     def timed(fn):
         barrier()
@@ -525,8 +544,9 @@ def run_cuda(args):
     floor_ms = n_slices * pcie_floor_ms(torch, dev, pcm_np.nbytes + slice_payload, pcm_np.nbytes + slice_payload, 0, 0, world, dist)
     if full_mask:
         os.sched_setaffinity(0, full_mask)
-    eng_dec.close()
-    del pcm_h, out_h, pk_hs
+    for x in enc_engs[1:] + dec_engs:
+        x.close()
+    del pcm_h, out_hs, pk_hs
 
     # ---- CPU baseline on this box's host cores (bounded sample of the same workload), rank 0 ----------------
     line = None
@@ -558,11 +578,11 @@ def run_cuda(args):
         dom_ms = kernels[dominant]
         alg_bytes = pcm_bytes + payload
         achieved = alg_bytes / (dom_ms / 1e3) / 1e9
-        symbols = kernel_symbols(W.depth)
+        symbols = kernel_symbols(W.depth, m.final_form, m.search_dense)
         traffic = issue_frac = warp_inst = None
         if W.seconds == CONFIGS[W.name][2] and world == 1:
             for k in load_ncu_profile(W.name):
-                if dominant in k["kernel"]:
+                if dominant + "_kernel" in k["kernel"] or dominant.replace("enc_final", "enc_final2") + "_kernel" in k["kernel"]:
                     traffic = int(k["dram_read_bytes"] + k["dram_write_bytes"])
                     warp_inst = k.get("inst_executed")
         sm_clock = (m.clocks.get("sm_mhz") or 1965.0) * 1e6
@@ -585,7 +605,8 @@ def run_cuda(args):
             "clocks": m.clocks,
             "e2e": {"value": e2e_value / 1e6, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "ms_per_step": e2e_s * 1e3, "steps": e2e_steps, "slices_per_step": n_slices,
-                    "how": "two engines on the GPU, alac_b200_encode_submit of step i+1 overlaps the decode of step i (full-duplex PCIe)",
+                    "how": f"{D} encode + {D} decode engines on the GPU driven through alac_b200_encode_submit / alac_b200_decode_submit: the "
+                           "calls of neighbouring steps overlap (full-duplex PCIe), every step still host -> device -> host -> device -> host",
                     "pcie_floor_ms": floor_ms, "e2e_over_floor": e2e_s * 1e3 / floor_ms if floor_ms else None,
                     "alternating_calls_ms_per_step": e2e_serial_s * 1e3, "alternating_calls_pcie_floor_ms": floor_serial_ms},
             "gpu_launches": int(m.job_launches),
@@ -627,7 +648,7 @@ def run_cuda(args):
                                "steps": 3, "warmup": 2, "x_realtime": m3.value / W3.rate, "encode_msamples_s": m3.enc_rate / 1e6,
                                "decode_msamples_s": m3.dec_rate / 1e6, "compression_ratio": round(m3.ratio, 4),
                                "sample_frames_per_job": m3.job_frames, "packets_this_gpu": m3.npk,
-                               "kernel_ms_per_step": {kernel_symbols(24)[k]: round(v, 4) for k, v in m3.kernels.items()},
+                               "kernel_ms_per_step": {kernel_symbols(24, m3.final_form, m3.search_dense)[k]: round(v, 4) for k, v in m3.kernels.items()},
                                "cpu_baseline": {"value": rtN3 / 1e6, "unit": UNIT, "cores": threads, "kind": kind3,
                                                 "sample": f"{threads} threads x {fptN3} packets of the same corpus"},
                                "x_all_host_cores": m3.value / rtN3, "bit_exact": True}

@@ -78,6 +78,8 @@ typedef struct alac_b200_stats {
     float    ms_entropy;          /* decode: sum over launches of dec_entropy_kernel (groups the fused kernel does not take) */
     float    ms_finish;           /* decode: sum over launches of dec_finish_kernel (same) */
     float    ms_fused;            /* decode: sum over launches of dec_fused_kernel (regular mono / stereo groups) */
+    uint32_t final_form;          /* encode, split form: 0 = enc_final_kernel, 1 = enc_final2_kernel one-warp, 2 = two-warp (last launch) */
+    uint32_t search_dense;        /* encode, split form: 1 = the search passes streamed PCM through the block ring */
 } alac_b200_stats;
 
 /* ---- engine ------------------------------------------------------------------------------ */

@@ -105,3 +105,35 @@ def test_probe_errors(lib, tmp_path):
     assert lib.alac_b200_wav_probe(str(p).encode(), C.byref(PcmInfo())) == -50
     assert lib.alac_b200_caf_probe(str(p).encode(), C.byref(CafInfo())) == -50
     assert lib.alac_b200_wav_probe(str(tmp_path / "missing.wav").encode(), C.byref(PcmInfo())) == -43
+
+
+def test_damaged_caf_is_rejected_not_walked_forever(lib, tmp_path):
+    """Chunk sizes come from the file: a negative or huge size must end the walk with a parameter error (it used to
+    seek backwards and loop), and a packet table that claims more bytes than the file holds reads nothing."""
+    import struct
+    d = np.load(GOLDEN[0])
+    cookie = np.ascontiguousarray(d["cookie"]).astype(np.uint8)
+    packets = np.ascontiguousarray(d["packets"]).astype(np.uint8)
+    sizes = np.ascontiguousarray(d["sizes"]).astype(np.uint32)
+    ch, depth = int(cookie[9]), int(cookie[5])
+    good = str(tmp_path / "good.caf").encode()
+    assert lib.alac_b200_caf_write(good, 44100, ch, depth, cookie.ctypes.data, cookie.size, 4096 * len(sizes) * ch * 2,
+                                   packets.ctypes.data, sizes.ctypes.data, len(sizes)) == 0
+    raw = bytearray(open(good, "rb").read())
+    info = CafInfo()
+    assert lib.alac_b200_caf_probe(good, C.byref(info)) == 0
+    kuki = raw.index(b"kuki")
+    for bad_size in (0xFFFFFFFFFFFFFFF0, 1 << 40, len(raw)):
+        bad = bytearray(raw)
+        bad[kuki + 4:kuki + 12] = struct.pack(">Q", bad_size)
+        path = str(tmp_path / "bad.caf").encode()
+        open(path, "wb").write(bad)
+        assert lib.alac_b200_caf_probe(path, C.byref(CafInfo())) != 0
+    lying = CafInfo.from_buffer_copy(bytes(info))
+    lying.table_bytes = 1 << 40
+    out = np.zeros(16, np.uint32)
+    assert lib.alac_b200_caf_read_table(good, C.byref(lying), out.ctypes.data, out.size) == 0
+    # a cookie whose frame length is not the 4096 that 'desc' and 'pakt' are written with
+    c2 = cookie.copy()
+    c2[0:4] = [0, 0, 8, 0]
+    assert lib.alac_b200_caf_write(str(tmp_path / "x.caf").encode(), 44100, ch, depth, c2.ctypes.data, c2.size, 0, None, None, 0) != 0

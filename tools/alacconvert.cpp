@@ -4,6 +4,8 @@
 // Options (extensions): -k N   encoder-reset schedule, frames per segment (default 0 = byte-identical to
 //                              the reference CLI; N >= 1 encodes segments in parallel)
 //                       -f     fast mode (SetFastMode)
+//                       -g N   shard the call by frame range over the first N GPUs of the box
+//                              (alac_b200_engine_create_multi; same bytes as one GPU)
 // The whole file goes through ONE batched call of libalac_b200; no per-frame loop, no CPU codec.
 #include <cstdio>
 #include <cstdlib>
@@ -21,26 +23,35 @@ static bool ends_with(const std::string &s, const char *suf)
 
 static int usage()
 {
-    printf("Usage: alacconvert [-k frames_per_segment] [-f] <input file> <output file>\n"
+    printf("Usage: alacconvert [-k frames_per_segment] [-f] [-g gpus] <input file> <output file>\n"
            "       WAV -> CAF encodes, CAF -> WAV decodes (16/20/24/32-bit PCM, 1-8 channels)\n");
     return 1;
 }
 
 int main(int argc, char **argv)
 {
-    uint32_t K = 0, fast = 0;
+    uint32_t K = 0, fast = 0, gpus = 1;
     std::vector<std::string> files;
     for (int i = 1; i < argc; i++) {
         if (!strcmp(argv[i], "-h")) return usage();
         else if (!strcmp(argv[i], "-k") && i + 1 < argc) K = (uint32_t)atoi(argv[++i]);
         else if (!strcmp(argv[i], "-f")) fast = 1;
+        else if (!strcmp(argv[i], "-g") && i + 1 < argc) gpus = (uint32_t)atoi(argv[++i]);
         else files.push_back(argv[i]);
     }
     if (files.size() != 2) return usage();
     printf("Input file: %s\nOutput file: %s\n", files[0].c_str(), files[1].c_str());   // main.cu:122-123
 
     alac_b200_engine *eng = nullptr;
-    if (alac_b200_engine_create(-1, &eng) != ALAC_B200_OK) { fprintf(stderr, "no usable CUDA device\n"); return 1; }
+    int32_t est;
+    if (gpus > 1) {
+        std::vector<int32_t> devs;
+        for (uint32_t d = 0; d < gpus; d++) devs.push_back((int32_t)d);
+        est = alac_b200_engine_create_multi(devs.data(), gpus, &eng);
+    } else {
+        est = alac_b200_engine_create(-1, &eng);
+    }
+    if (est != ALAC_B200_OK) { fprintf(stderr, "no usable CUDA device%s\n", gpus > 1 ? "s (or no peer access between them)" : ""); return 1; }
     int rc = 1;
     alac_b200_pcm_info wav;
     alac_b200_caf_info caf;
@@ -48,6 +59,7 @@ int main(int argc, char **argv)
         // ---- encode (EncodeALAC, main.cu:391-632)
         std::vector<uint8_t> pcm((size_t)wav.data_bytes);
         FILE *f = fopen(files[0].c_str(), "rb");
+        if (!f) { fprintf(stderr, "cannot open %s\n", files[0].c_str()); alac_b200_engine_destroy(eng); return 1; }
         fseek(f, (long)wav.data_offset, SEEK_SET);
         const size_t got = fread(pcm.data(), 1, pcm.size(), f);
         fclose(f);
@@ -75,6 +87,7 @@ int main(int argc, char **argv)
         for (uint64_t i = 0; i < np; i++) nbytes += sizes[i];
         std::vector<uint8_t> packets((size_t)nbytes);
         FILE *f = fopen(files[0].c_str(), "rb");
+        if (!f) { fprintf(stderr, "cannot open %s\n", files[0].c_str()); alac_b200_engine_destroy(eng); return 1; }
         fseek(f, (long)caf.data_offset, SEEK_SET);
         const size_t got = fread(packets.data(), 1, packets.size(), f);
         fclose(f);

@@ -53,7 +53,9 @@ struct alac_b200_engine {
     cudaStream_t own_stream = nullptr;
     cudaStream_t copy_in = nullptr, copy_out = nullptr;     // transfer streams of the host-buffer pipeline
     cudaStream_t side = nullptr;                            // staged placement, home rank: wait-for-all + compaction
-    bool finish_pending = false;
+    bool finish_pending = false;                            // a deferred finish: home rank = side stream, other ranks = copy-out stream
+    bool finish_far = false;
+    uint64_t finish_total = 0, finish_capacity = 0, last_base = 0;
     cudaStream_t lanes[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   // compute streams of the host-buffer pipeline
     cudaStream_t cur = nullptr;                             // stream the launch helpers / timers use right now
     uint64_t *h_totals = nullptr;                           // pinned: running byte / frame totals per chunk
@@ -265,7 +267,12 @@ int32_t alac_b200_engine_create(int32_t device, alac_b200_engine **out_engine)
     for (auto &ln : e->lanes) lanes_ok = lanes_ok && cudaStreamCreateWithFlags(&ln, cudaStreamNonBlocking) == cudaSuccess;
     if (!lanes_ok || cudaStreamCreateWithFlags(&e->copy_in, cudaStreamNonBlocking) != cudaSuccess ||
         cudaStreamCreateWithFlags(&e->copy_out, cudaStreamNonBlocking) != cudaSuccess ||
-        cudaStreamCreateWithFlags(&e->side, cudaStreamNonBlocking) != cudaSuccess ||
+        [&] {   // the side stream closes the gaps of a staged job while this GPU already decodes: highest priority, so its CTAs
+                // are placed as soon as slots free up instead of after the decode kernels' queued CTAs
+            int lo = 0, hi = 0;
+            cudaDeviceGetStreamPriorityRange(&lo, &hi);
+            return cudaStreamCreateWithPriority(&e->side, cudaStreamNonBlocking, hi);
+        }() != cudaSuccess ||
         cudaHostAlloc(&e->h_totals, kMaxChunks * sizeof(uint64_t), cudaHostAllocDefault) != cudaSuccess) {
         delete e;
         return ALAC_B200_CUDA_ERROR;
@@ -439,7 +446,11 @@ static int32_t encode_core(alac_b200_engine *e, const alac_b200_enc_config *cfg,
     if (out_base) *out_base = 0;
     if (stats) memset(stats, 0, sizeof(*stats));
     CU_CHECK(e, cudaSetDevice(e->device));
-    if (e->finish_pending) { CU_CHECK(e, cudaStreamSynchronize(e->side)); e->finish_pending = false; }     // (an unfinished deferred job)
+    if (e->finish_pending) {        // (an unfinished deferred job)
+        CU_CHECK(e, cudaStreamSynchronize(e->side));
+        CU_CHECK(e, cudaStreamSynchronize(e->copy_out));
+        e->finish_pending = false;
+    }
     e->launches = 0;
     e->timers_used = 0;
     e->t_mid.clear();
@@ -514,8 +525,16 @@ static int32_t encode_core(alac_b200_engine *e, const alac_b200_enc_config *cfg,
     uint64_t chunk_target = scratch_chunk_packets();
     if (!chunk_target) chunk_target = std::max<uint64_t>(4096, (8ull << 30) / ((uint64_t)L.chains_per_packet * cap_words * 4));
     const bool multi = in_host || out_host || staged;   // host buffers / staged placement: chunks run on several compute streams
-    if (multi) chunk_target /= 8;
-    const bool taper = multi && P >= 4096;
+    if (staged) {
+        // Staged placement: a chunk's packets leave for the home GPU when the chunk is done, and whatever has not left
+        // when the call's kernels end travels while the caller decodes (defer_finish) -- so few, large chunks (the
+        // kernels run at single-stream efficiency: 10-hour 24/96 on two GPUs, 47.9 ms with 13 chunks, 40.4 ms with 4)
+        // as long as some bytes start early: four chunks per call, none smaller than 16 k packets.
+        chunk_target = std::min<uint64_t>(chunk_target, std::max<uint64_t>(16384, ((uint64_t)P + 3) / 4));
+    } else if (multi) {
+        chunk_target /= 8;
+    }
+    const bool taper = multi && !staged && P >= 4096;
     struct Chunk { uint32_t s0, s1, p0, cnt; uint64_t f_lo, f_hi; };
     std::vector<Chunk> chunks;
     uint64_t max_chunk = 0, span_lo = ~0ull, span_hi = 0;
@@ -704,7 +723,8 @@ static int32_t encode_core(alac_b200_engine *e, const alac_b200_enc_config *cfg,
         Q.jobs = split ? e->jobs.as<FinalJob>() + 2 * jobs_per_slot * slot : nullptr;
         Q.counts = split ? e->job_counts.as<uint32_t>() + 4 * ci : nullptr;
         // two-warp final pass while the launch's jobs do not fill the GPU (about one wave of one-warp CTAs: 148 SMs x 24 x 32 jobs)
-        const uint64_t jobs_in_launch = (uint64_t)c.cnt * L.chains_per_packet;
+        // (chunks of a host-buffer / staged call run side by side on the lanes: what counts is what is on the GPU at once)
+        const uint64_t jobs_in_launch = std::min<uint64_t>(P, (uint64_t)c.cnt * nstreams_used) * L.chains_per_packet;
         const int dense_form = !dense ? 0 : final2_mode > 0 ? final2_mode : (jobs_in_launch <= 148ull * 24 * 32 ? 2 : 1);
         last_dense_form = split ? dense_form : 0;
         t_search.push_back(e->timer());
@@ -812,17 +832,30 @@ static int32_t encode_core(alac_b200_engine *e, const alac_b200_enc_config *cfg,
             }
         }
     }
-    if (P) CU_CHECK(e, cudaMemcpyAsync(packet_sizes, e->sizes.p, (size_t)P * 4, sizes_host ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice, e->copy_out));
-    CU_CHECK(e, cudaMemcpyAsync(h_counters, e->counters.p, 16, cudaMemcpyDeviceToHost, e->copy_out));
-    if (pl) CU_CHECK(e, cudaMemcpyAsync(h_place, d_base, 24, cudaMemcpyDeviceToHost, e->copy_out));
+    // staged form, a rank other than the home rank, defer_finish: the call ends with this rank's kernels.  Its chunks keep
+    // travelling to the home GPU on the copy-out stream (and the exchange words follow them) while the caller already uses
+    // the GPU for something else -- decoding its own block; alac_b200_placed_finish() ends the job on this rank too.
+    const bool defer_far = to_slot && pl->defer_finish != 0;
+    cudaStream_t rs = defer_far ? st : e->copy_out;        // stream of the result copies
+    if (P) CU_CHECK(e, cudaMemcpyAsync(packet_sizes, e->sizes.p, (size_t)P * 4, sizes_host ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice, rs));
+    CU_CHECK(e, cudaMemcpyAsync(h_counters, e->counters.p, 16, cudaMemcpyDeviceToHost, rs));
+    if (pl && !defer_far) CU_CHECK(e, cudaMemcpyAsync(h_place, d_base, 24, cudaMemcpyDeviceToHost, e->copy_out));
     if (coef_state) {
         CU_CHECK(e, cudaMemcpyAsync(coef_state, e->state.p, (size_t)n_streams * ALAC_B200_STATE_INT16S * 2, cudaMemcpyDeviceToHost, e->copy_out));
     }
-    CU_CHECK(e, cudaEventRecord(e->ev[3], e->copy_out));
-    CU_CHECK(e, cudaStreamSynchronize(e->copy_out));
+    CU_CHECK(e, cudaEventRecord(e->ev[3], rs));
+    if (!defer_far) CU_CHECK(e, cudaStreamSynchronize(e->copy_out));
     CU_CHECK(e, cudaStreamSynchronize(st));
     guard.armed = false;
-    if (pl) {
+    if (defer_far) {
+        e->finish_pending = true;
+        e->finish_far = true;
+        e->finish_total = total;
+        e->finish_capacity = pl->dst_capacity;
+        if (out_local) *out_local = static_cast<void *>(d_out);
+    } else if (pl) {
+        e->finish_far = false;
+        e->last_base = h_place[0];
         if (h_place[2] & 0xffffffffull) { e->err = "cross-GPU exchange timed out (a rank of the job did not arrive)"; return ALAC_B200_CUDA_ERROR; }
         if (h_place[0] + total > pl->dst_capacity) { e->err = "dst_packets capacity exceeded"; return ALAC_B200_PARAM_ERROR; }
         if (out_base) *out_base = h_place[0];
@@ -1027,7 +1060,7 @@ extern "C" int32_t alac_b200_placed_finish(alac_b200_engine *e, uint64_t *out_jo
     if (out_job_bytes) *out_job_bytes = 0;
     if (!e->finish_pending) return ALAC_B200_OK;
     CU_CHECK(e, cudaSetDevice(e->device));
-    CU_CHECK(e, cudaStreamSynchronize(e->side));
+    CU_CHECK(e, cudaStreamSynchronize(e->finish_far ? e->copy_out : e->side));
     e->finish_pending = false;
     unsigned long long h[3] = {0, 0, 0};
     CU_CHECK(e, cudaMemcpy(h, e->xwords.p, 24, cudaMemcpyDeviceToHost));
@@ -1035,7 +1068,19 @@ extern "C" int32_t alac_b200_placed_finish(alac_b200_engine *e, uint64_t *out_jo
         e->err = (h[2] & 0xffffffffull) == 3 ? "dst_packets capacity exceeded" : "cross-GPU exchange timed out (a rank of the job did not arrive)";
         return (h[2] & 0xffffffffull) == 3 ? ALAC_B200_PARAM_ERROR : ALAC_B200_CUDA_ERROR;
     }
-    if (out_job_bytes) *out_job_bytes = h[1];
+    if (e->finish_far) {
+        e->last_base = h[0];
+        if (h[0] + e->finish_total > e->finish_capacity) { e->err = "dst_packets capacity exceeded"; return ALAC_B200_PARAM_ERROR; }
+    } else if (out_job_bytes) {
+        *out_job_bytes = h[1];
+    }
+    return ALAC_B200_OK;
+}
+
+extern "C" int32_t alac_b200_placed_base(alac_b200_engine *e, uint64_t *out_base)
+{
+    if (!e || !out_base || e->finish_pending) return ALAC_B200_PARAM_ERROR;
+    *out_base = e->last_base;
     return ALAC_B200_OK;
 }
 

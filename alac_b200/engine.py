@@ -121,6 +121,8 @@ def load_library():
     lib.alac_b200_encode_placed.restype = i32
     lib.alac_b200_placed_finish.argtypes = [vp, C.POINTER(u64)]
     lib.alac_b200_placed_finish.restype = i32
+    lib.alac_b200_placed_base.argtypes = [vp, C.POINTER(u64)]
+    lib.alac_b200_placed_base.restype = i32
     lib.alac_b200_device_alloc.argtypes = [vp, u64, C.POINTER(vp)]
     lib.alac_b200_device_alloc.restype = i32
     lib.alac_b200_device_free.argtypes = [vp, vp]
@@ -290,6 +292,14 @@ class Engine:
         if st:
             raise AlacError(st, self._err())
         return nb.value
+
+    def placed_base(self) -> int:
+        """Byte offset of this rank's block inside the job's buffer (alac_b200_placed_base; after placed_finish)."""
+        b = C.c_uint64(0)
+        st = self.lib.alac_b200_placed_base(self.h, C.byref(b))
+        if st:
+            raise AlacError(st, "a deferred placed call is still pending")
+        return b.value
 
     def encode_placed(self, pcm, cfg: EncoderConfig, placement: Placement, streams=None, out_sizes=None):
         """This rank's share of a job several GPUs encode together (alac_b200_encode_placed): the packets go straight

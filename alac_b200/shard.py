@@ -213,8 +213,9 @@ class SharedJob:
                          self.slot_offsets if staged else None, 1 if (defer_finish and staged) else 0)
 
     def finish(self) -> int:
-        """Home rank: wait until the job's buffer is complete (no-op elsewhere / when nothing is pending)."""
-        return self.engine.placed_finish() if self.rank == self.home else 0
+        """Ends a step whose placement asked for defer_finish: the home rank waits until the job's buffer is complete
+        (returns the job's bytes), every other rank until its block has arrived on the home GPU.  A no-op otherwise."""
+        return self.engine.placed_finish()
 
     def close(self):
         if getattr(self, "_ptrs", None) is None:

@@ -321,6 +321,7 @@ def measure_device(W: Work, ctx, steps: int, warmup: int, sampler=None):
     m.sz_d = torch.empty(max(m.npk, 1), dtype=torch.int32, device=dev)
     out_d = torch.empty(m.pcm_d.numel(), dtype=torch.uint8, device=dev)
     m.job = m.pk_d = None
+    m.phase_wall = [0.0, 0.0, 0.0, 0]
     if world > 1:
         # staged placement (ALAC_B200_PLACE=direct selects the in-kernel peer-store form for comparison)
         slots = None
@@ -340,12 +341,17 @@ def measure_device(W: Work, ctx, steps: int, warmup: int, sampler=None):
             enc = eng.encode(m.pcm_d, cfg, out=m.pk_d, out_sizes=m.sz_d)
             dec = eng.decode(cookie, enc.packets, enc.sizes, out=out_d)
             return enc.stats, dec, enc.nbytes
+        t0 = time.perf_counter()
         sizes, _, nb, base, mine, st = eng.encode_placed(m.pcm_d, cfg, m.job.placement(first_packet, defer_finish=os.environ.get('ALAC_B200_DEFER', '1') != '0'), out_sizes=m.sz_d)
+        t1 = time.perf_counter()
         # every rank decodes its own packet range (its own copy of the block: the concatenation on GPU 0 is the job's
         # only cross-GPU step, BASELINE.json north_star).  On GPU 0 "wait for every rank, close the gaps" runs on the
         # device meanwhile; the step ends when the job's buffer is complete.
         dec = eng.decode(cookie, mine, sizes, out=out_d)
+        t2 = time.perf_counter()
         m.job.finish()
+        t3 = time.perf_counter()
+        m.phase_wall = [m.phase_wall[0] + t1 - t0, m.phase_wall[1] + t2 - t1, m.phase_wall[2] + t3 - t2, m.phase_wall[3] + 1]
         return st, dec, nb
 
     # ---- parity in the same run: round-trip identity on this rank's whole range
@@ -371,6 +377,7 @@ def measure_device(W: Work, ctx, steps: int, warmup: int, sampler=None):
     launches = 0
     acc = {k: 0.0 for k in ("ms_search", "ms_final", "ms_assemble", "ms_entropy", "ms_finish", "ms_fused")}
     ms_enc_k = ms_dec_k = 0.0
+    m.phase_wall = [0.0, 0.0, 0.0, 0]
     ev0.record()
     for _ in range(steps):
         es, d_, _ = step_device()
@@ -396,6 +403,13 @@ def measure_device(W: Work, ctx, steps: int, warmup: int, sampler=None):
     if world > 1:
         dist.all_reduce(tot)
     m.job_payload, m.job_launches = int(tot[0].item()), int(tot[1].item())
+    m.phases = None
+    if world > 1:
+        # host wall time per step of the three calls of a step, per rank: [encode_placed, decode, placed_finish] in ms
+        ph = torch.tensor([x / max(m.phase_wall[3], 1) * 1e3 for x in m.phase_wall[:3]], dtype=torch.float64, device=dev)
+        allph = [torch.zeros_like(ph) for _ in range(world)]
+        dist.all_gather(allph, ph)
+        m.phases = [[round(float(v), 2) for v in t.tolist()] for t in allph]
     if m.job is not None:
         # the placed call runs its chunks on several streams, so its per-kernel timers overlap; the per-kernel figures (and the
         # roofline) of a multi-GPU run come from one plain single-stream pass over the same shard, outside the timed region
@@ -610,6 +624,7 @@ def run_cuda(args):
                     "pcie_floor_ms": floor_ms, "e2e_over_floor": e2e_s * 1e3 / floor_ms if floor_ms else None,
                     "alternating_calls_ms_per_step": e2e_serial_s * 1e3, "alternating_calls_pcie_floor_ms": floor_serial_ms},
             "gpu_launches": int(m.job_launches),
+            **({"call_ms_per_rank": {"order": ["alac_b200_encode_placed", "alac_b200_decode", "alac_b200_placed_finish"], "ranks": m.phases}} if m.phases else {}),
             "roofline": {"bound": "hbm", "kernel": symbols[dominant], "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
                          "frac": achieved / hbm_peak, "traffic": traffic, "peak_source": peak_kind,
                          "algorithmic_bytes_per_launch": int(alg_bytes), "ms_per_launch": dom_ms,
@@ -648,6 +663,7 @@ def run_cuda(args):
                                "steps": 3, "warmup": 2, "x_realtime": m3.value / W3.rate, "encode_msamples_s": m3.enc_rate / 1e6,
                                "decode_msamples_s": m3.dec_rate / 1e6, "compression_ratio": round(m3.ratio, 4),
                                "sample_frames_per_job": m3.job_frames, "packets_this_gpu": m3.npk,
+                               "call_ms_per_rank": {"order": ["alac_b200_encode_placed", "alac_b200_decode", "alac_b200_placed_finish"], "ranks": m3.phases},
                                "kernel_ms_per_step": {kernel_symbols(24, m3.final_form, m3.search_dense)[k]: round(v, 4) for k, v in m3.kernels.items()},
                                "cpu_baseline": {"value": rtN3 / 1e6, "unit": UNIT, "cores": threads, "kind": kind3,
                                                 "sample": f"{threads} threads x {fptN3} packets of the same corpus"},

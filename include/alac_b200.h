@@ -160,9 +160,11 @@ typedef struct alac_b200_placement {
        bound; the staging area extends at least 32 bytes past the last slot. */
     void           *staging;        /* device pointer in the home GPU's memory (local or peer), or NULL = direct form */
     const uint64_t *slot_offsets;
-    /* staged form, home rank: 0 = the call returns when the job's buffer is complete; 1 = it returns when the home
-       rank's own block is in place and leaves "wait for every rank, close the gaps" running on the device -- the caller
-       does other work on this GPU (decoding its own shard) and ends the job with alac_b200_placed_finish(). */
+    /* staged form: 0 = the home rank's call returns when the job's buffer is complete, another rank's call when its
+       block has arrived in its slot; 1 = the call returns with this rank's own kernels.  On the home rank "wait for
+       every rank, close the gaps" then keeps running on the device, on the other ranks the block keeps travelling over
+       NVLink (*out_base is not known yet and reads 0) -- the caller does other work on this GPU (decoding its own
+       shard out of *out_local_block) and ends the job with alac_b200_placed_finish() on EVERY rank. */
     uint32_t        defer_finish;
 } alac_b200_placement;
 /* Same arguments as alac_b200_encode for this rank's PCM; packet_sizes[] (the rank's own entries) stays local
@@ -177,9 +179,13 @@ int32_t alac_b200_encode_placed(alac_b200_engine *engine, const alac_b200_enc_co
                                 uint64_t *out_num_packets, uint64_t *out_bytes, uint64_t *out_base,
                                 void **out_local_block, alac_b200_stats *stats);
 
-/* ends a staged job whose home-rank call was made with defer_finish = 1: returns when every rank's block is at its final
-   offset of dst_packets; *out_job_bytes (optional) = the job's total packet bytes.  A no-op (status 0) otherwise. */
+/* ends a staged job whose call was made with defer_finish = 1.  Home rank: returns when every rank's block is at its final
+   offset of dst_packets; *out_job_bytes (optional) = the job's total packet bytes.  Other ranks: returns when this rank's
+   block has arrived on the home GPU.  A no-op (status 0) when nothing is pending.
+   alac_b200_placed_base: the byte offset of this rank's block inside dst_packets of the engine's latest placed call
+   (what *out_base of a non-deferred call returns); valid once nothing is pending. */
 int32_t alac_b200_placed_finish(alac_b200_engine *engine, uint64_t *out_job_bytes);
+int32_t alac_b200_placed_base(alac_b200_engine *engine, uint64_t *out_base);
 
 /* device memory that can be shared with other processes (plain cudaMalloc on the engine's device) and the
    cudaIpc* wrappers a one-process-per-GPU launcher needs; handle = 64 bytes (cudaIpcMemHandle_t) */

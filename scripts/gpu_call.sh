@@ -1,7 +1,11 @@
-python -m pytest tests -m gpu -x -q > gpurun_out/r02_pytest.log 2>&1; echo pytest rc=$?; tail -2 gpurun_out/r02_pytest.log
-python bench.py > gpurun_out/r02_bench_c2.json 2> gpurun_out/r02_bench_c2.err; echo bench c2 rc=$?
-python bench.py --config c3 --steps 3 --warmup 3 > gpurun_out/r02_bench_c3.json 2> gpurun_out/r02_bench_c3.err; echo bench c3 rc=$?
-python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/r02_bench_ref.json 2> gpurun_out/r02_bench_ref.err; echo bench ref rc=$?
-TAG=c2 ARGS="3600 16 44100" bash scripts/profile_r02.sh
-TAG=c3_1h ARGS="3600 24 96000" bash scripts/profile_r02.sh
-TAG=c3 LIGHT=1 ARGS="36000 24 96000" bash scripts/profile_r02.sh
+python -m pytest tests/test_gpu_multi.py -x -q 2>&1 | tail -2
+python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 8 --steps 10 --warmup 3 > gpurun_out/r02_bench_n8.json 2> gpurun_out/r02_bench_n8.err; echo n8 rc=$?
+python - <<PY
+import json
+d=json.loads(open("gpurun_out/r02_bench_n8.json").read().strip().splitlines()[-1])
+print(d["value"], d["ms_per_step"], d["encode_msamples_s"], d["decode_msamples_s"], d["x_all_host_cores"], d["e2e"]["value"], d["e2e"]["ms_per_step"], d["e2e"]["e2e_over_floor"])
+print(d["call_ms_per_rank"])
+c=d["config3"]
+print("c3", c["value"], c["ms_per_step"], c["encode_msamples_s"], c["decode_msamples_s"], c["x_all_host_cores"], c["cpu_baseline"]["value"], c["kernel_ms_per_step"])
+print(c["call_ms_per_rank"])
+PY

@@ -43,6 +43,7 @@ for it in range(3):                                  # several epochs through th
     dec = eng.decode(alac_b200.magic_cookie(cfg), mine, sizes)
     ok = ok and dec.status == 0 and torch.equal(dec.pcm, pcm)
     job.finish()
+    base = eng.placed_base()        # (a deferred call of a rank other than the home rank learns its offset at finish())
     dist.barrier()          # (the shared buffer is complete once the home rank's call -- or its finish() -- has returned)
     dec = eng.decode(alac_b200.magic_cookie(cfg), job.packets_region[base:base + nb], sizes)
     ok = ok and dec.status == 0 and torch.equal(dec.pcm, pcm)

@@ -357,10 +357,16 @@ __device__ __forceinline__ void predict_pass(const Src &src, uint32_t num, int32
 #pragma unroll
             for (uint32_t d = 0; d < kQuadAhead; d++) ring.request(b_first + d);
         }
+        // (head and tail share ONE copy of the scalar loop -- two trips of the phase loop: the body is long, there are
+        //  five instantiations of this pass in the search kernel, and the kernel feels instruction-cache pressure)
         uint32_t j = TAPS + 1;
+        uint32_t stop = min(num, b_first * R::kBlockFrames);
 #pragma unroll 1
-        for (; j < b_first * R::kBlockFrames && j < num; j++) sink(j, predict_enc_step<TAPS, WRAP>(src.get(j), hist, a, chanshift));
-        if (nb > b_first) {
+        for (int phase = 0; phase < 2; phase++) {
+#pragma unroll 1
+            for (; j < stop; j++) sink(j, predict_enc_step<TAPS, WRAP>(src.get(j), hist, a, chanshift));
+            stop = num;
+            if (phase || nb <= b_first) continue;
             for (uint32_t b = b_first; b < nb; b++, j += R::kBlockFrames) {
                 ring.request(b + kQuadAhead);
                 cp_async_wait<kQuadAhead>();            // block b is in
@@ -369,8 +375,6 @@ __device__ __forceinline__ void predict_pass(const Src &src, uint32_t num, int32
             }
             cp_async_wait<0>();
         }
-#pragma unroll 1
-        for (; j < num; j++) sink(j, predict_enc_step<TAPS, WRAP>(src.get(j), hist, a, chanshift));
         return;
     }
     if constexpr (Src::kWide) {
@@ -754,8 +758,14 @@ struct JobLists {
 
 // DENSE: a dense element (see DenseElem) -- the passes stream their PCM through the lane's word ring instead of
 // per-sample loads (20/24/32-bit and mono streams; 16-bit packed stereo has its own 16-byte ring, MixSrc::kWide).
+#ifndef ALAC_SEARCH_MINB
+#define ALAC_SEARCH_MINB 20
+#endif
+#ifndef ALAC_FINAL1_MINB
+#define ALAC_FINAL1_MINB 24
+#endif
 template <int DEPTH, bool STEREO, bool PACKED, bool WRAP, bool DENSE = false>
-__global__ void __launch_bounds__(32, 20)
+__global__ void __launch_bounds__(32, ALAC_SEARCH_MINB)
 enc_search_split_kernel(EncArgs A, uint32_t elems_of_kind, uint32_t kind_elem0, JobLists Q)
 {
     constexpr uint32_t kLanesPerJob = STEREO ? 2 : 1;
@@ -901,7 +911,7 @@ enc_final_kernel(EncArgs A, JobLists Q, uint32_t ctas_per_list)
 // throughput-bound, the coder warp's idle half only costs occupancy, and the one-warp form is the faster one
 // (10-hour 24/96 corpus: 44 ms against 52 ms; 1-hour 16/44.1: 2.9 ms against 2.6 ms).  The engine picks by job count.
 template <int DEPTH, bool STEREO, bool WRAP, bool SPLIT>
-__global__ void __launch_bounds__(SPLIT ? 64 : 32, SPLIT ? 12 : 24)
+__global__ void __launch_bounds__(SPLIT ? 64 : 32, SPLIT ? 12 : ALAC_FINAL1_MINB)
 enc_final2_kernel(EncArgs A, JobLists Q, uint32_t ctas_per_list)
 {
     __shared__ uint4 s_ring[QuadRing<DEPTH, STEREO>::kRows][32];
@@ -1000,24 +1010,23 @@ enc_final2_kernel(EncArgs A, JobLists Q, uint32_t ctas_per_list)
                     hist[TAPS - j] = x;
                     prev = x;
                 }
-#pragma unroll 1
-                for (r = TAPS + 1; r < b_first * R::kBlockFrames && r < n; r++) put(r, r, predict_enc_step<TAPS, WRAP>(src.get(r), hist, a, chanshift));
-                r = b_first * R::kBlockFrames;
+                r = TAPS + 1;
             }
-            // whole blocks of this tile
-            for (; r < kEncTileRows; r += R::kBlockFrames) {
-                const uint32_t blk = (j0 + r) / R::kBlockFrames;
-                if (blk < nblk) {
+            // whole blocks of this tile through the ring; the frames between the warm-up and the first block boundary and
+            // the odd frames after the last whole block one by one (ONE copy of the scalar step: instruction cache)
+#pragma unroll 1
+            while (r < kEncTileRows) {
+                const uint32_t j = j0 + r, blk = j / R::kBlockFrames;
+                if (j >= b_first * R::kBlockFrames && blk < nblk) {     // (j is on a block boundary here)
                     ring.request(blk + kQuadAhead);
                     cp_async_wait<kQuadAhead>();            // block blk is in
                     ring_block_samples<DEPTH, STEREO>(ring, blk, src.cl, src.cr, src.sh_mix, [&](uint32_t i, int32_t x) {
-                        put(r + i, j0 + r + i, predict_enc_step<TAPS, WRAP>(x, hist, a, chanshift));
+                        put(r + i, j + i, predict_enc_step<TAPS, WRAP>(x, hist, a, chanshift));
                     });
+                    r += R::kBlockFrames;
                 } else {
-                    // the odd frames after the last whole block (and nothing at all past n)
-#pragma unroll 1
-                    for (uint32_t i = 0; i < R::kBlockFrames && j0 + r + i < n; i++)
-                        put(r + i, j0 + r + i, predict_enc_step<TAPS, WRAP>(src.get(j0 + r + i), hist, a, chanshift));
+                    if (j < n) put(r, j, predict_enc_step<TAPS, WRAP>(src.get(j), hist, a, chanshift));
+                    r++;
                 }
             }
             if (SPLIT) {

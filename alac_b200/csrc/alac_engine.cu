@@ -294,8 +294,13 @@ void alac_b200_engine_destroy(alac_b200_engine *e)
     for (size_t i = 1; i < e->subs.size(); i++) alac_b200_engine_destroy(e->subs[i]);
     e->subs.clear();
     cudaSetDevice(e->device);
-    e->xchg.release(); e->m_out.release(); e->m_sizes.release(); e->m_aux.release(); e->xwords.release();
+    // nothing may still be in flight on the engine's buffers (a deferred placed call keeps copying / compacting)
     cudaStreamSynchronize(e->stream);
+    if (e->copy_in) cudaStreamSynchronize(e->copy_in);
+    if (e->copy_out) cudaStreamSynchronize(e->copy_out);
+    if (e->side) cudaStreamSynchronize(e->side);
+    for (auto &ln : e->lanes) if (ln) cudaStreamSynchronize(ln);
+    e->xchg.release(); e->m_out.release(); e->m_sizes.release(); e->m_aux.release(); e->xwords.release();
     DevBuf *bufs[] = {&e->pcm, &e->pkt_frame, &e->pkt_samples, &e->seg_first, &e->seg_count, &e->seg_stream, &e->recs,
                       &e->scratch, &e->sizes, &e->offsets, &e->out, &e->state, &e->counters, &e->scan_tiles, &e->d_packets, &e->d_sizes,
                       &e->d_pkt_off, &e->d_pkt_samples, &e->d_out_frame, &e->d_status, &e->d_pcm, &e->d_class, &e->d_rank, &e->d_perm, &e->d_chan, &e->d_meta, &e->d_hdr, &e->jobs, &e->job_counts};

@@ -289,13 +289,75 @@ struct QuadRing {
     }
 };
 
+#ifdef ALAC_RING_BULK
+// EXPERIMENT: the same ring filled by per-lane bulk copies (cp.async.bulk, SASS UBLKCP) that complete on an
+// mbarrier per slot instead of 16-byte cp.async groups.  A lane's slots are contiguous (a bulk copy writes one run of
+// shared memory): row = kSlots blocks + 16 bytes of padding, which keeps the 128-bit reads of a quarter-warp on
+// different banks.  Every lane arrives once per block index on the slot's barrier (count 32), with its byte count when
+// it has a block to fetch and without when it has not, so all lanes of the warp must walk the same block indices.
+template <int DEPTH, bool STEREO>
+struct BulkRing {
+    static constexpr uint32_t WQ = DenseElem<DEPTH, STEREO>::kQuadWords;
+    static constexpr uint32_t QB = (WQ % 4u == 0) ? 1u : (WQ % 2u == 0) ? 2u : 4u;
+    static constexpr uint32_t G = WQ * QB / 4u;
+    static constexpr uint32_t kBlockFrames = 4u * QB;
+    static constexpr uint32_t kSlots = kQuadAhead + 1u;
+    static constexpr uint32_t kRowBytes = kSlots * G * 16u + 16u;
+    const uint8_t *base;
+    uint32_t row, bars, blocks, first;
+    __device__ __forceinline__ void start(const uint8_t *packet, uint32_t n, uint8_t *row_ptr, uint64_t *bar_ptr, uint32_t first_block, uint32_t lane)
+    {
+        base = packet;
+        row = (uint32_t)__cvta_generic_to_shared(row_ptr);
+        bars = (uint32_t)__cvta_generic_to_shared(bar_ptr);
+        blocks = n / kBlockFrames;
+        first = first_block;
+        if (lane == 0) {
+#pragma unroll
+            for (uint32_t i = 0; i < kSlots; i++) asm volatile("mbarrier.init.shared::cta.b64 [%0], 32;" ::"r"(bars + 8u * i) : "memory");
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncwarp();
+    }
+    __device__ __forceinline__ void request(uint32_t b) const
+    {
+        const uint32_t bar = bars + 8u * (b & (kSlots - 1u));
+        if (b < blocks) {
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(G * 16u) : "memory");
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                         ::"r"(row + (b & (kSlots - 1u)) * (G * 16u)), "l"(base + (size_t)b * (G * 16u)), "r"(G * 16u), "r"(bar) : "memory");
+        } else {
+            asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+        }
+    }
+    __device__ __forceinline__ void acquire(uint32_t b) const
+    {
+        const uint32_t bar = bars + 8u * (b & (kSlots - 1u)), parity = ((b - first) / kSlots) & 1u;
+        uint32_t done = 0;
+        for (uint32_t spin = 0; !done; spin++) {
+            asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                         : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+            if (spin > (1u << 24)) __trap();        // (an experiment must not hang the box)
+        }
+    }
+    __device__ __forceinline__ void read(uint32_t b, uint32_t (&w)[WQ * QB]) const
+    {
+        const uint32_t src = row + (b & (kSlots - 1u)) * (G * 16u);
+#pragma unroll
+        for (uint32_t i = 0; i < G; i++) {
+            const uint4 v = lds_u128(src + i * 16u);
+            w[4 * i] = v.x; w[4 * i + 1] = v.y; w[4 * i + 2] = v.z; w[4 * i + 3] = v.w;
+        }
+    }
+};
+#endif
+
 // The lane's (mixed) samples of block b, in order: f(i, x) for i = 0 .. kBlockFrames - 1.  The quads of a block run
 // through ONE copy of the caller's four-step body (the words of the later quads move down in registers): the bodies --
 // predictor step plus Golomb step -- are long and these kernels feel instruction-cache pressure.
-template <int DEPTH, bool STEREO, class F>
-__device__ __forceinline__ void ring_block_samples(const QuadRing<DEPTH, STEREO> &ring, uint32_t b, int32_t cl, int32_t cr, uint32_t sh_mix, F &&f)
+template <int DEPTH, bool STEREO, class R, class F>
+__device__ __forceinline__ void ring_block_samples(const R &ring, uint32_t b, int32_t cl, int32_t cr, uint32_t sh_mix, F &&f)
 {
-    using R = QuadRing<DEPTH, STEREO>;
     uint32_t w[R::WQ * R::QB];
     ring.read(b, w);
 #pragma unroll 1
@@ -966,9 +1028,17 @@ enc_final2_kernel(EncArgs A, JobLists Q, uint32_t ctas_per_list)
     src.base = J.base; src.stride = DenseElem<DEPTH, STEREO>::kFrameBytes;
     src.set_mix((int32_t)(J.flags >> 1), (J.flags & 1u) != 0);
     src.valid = n;
+#ifdef ALAC_RING_BULK
+    using R = BulkRing<DEPTH, STEREO>;
+    __shared__ __align__(16) uint8_t s_bulk[32][R::kRowBytes];
+    __shared__ __align__(8) uint64_t s_bar[R::kSlots];
+    R ring;
+    ring.start(have ? J.base : reinterpret_cast<const uint8_t *>(s_ring), n, &s_bulk[lane][0], &s_bar[0], ((list ? 8u : 4u) + 1u + R::kBlockFrames - 1u) / R::kBlockFrames, lane);
+#else
     QuadRing<DEPTH, STEREO> ring;
     ring.start(have ? J.base : reinterpret_cast<const uint8_t *>(s_ring), n, &s_ring[0][lane]);
     using R = QuadRing<DEPTH, STEREO>;
+#endif
     static_assert(kEncTileRows % R::kBlockFrames == 0, "a tile is a whole number of blocks");
     const uint32_t nblk = ring.blocks;      // whole blocks of the packet
     auto run = [&](auto taps_tag) {
@@ -1019,12 +1089,20 @@ enc_final2_kernel(EncArgs A, JobLists Q, uint32_t ctas_per_list)
                 const uint32_t j = j0 + r, blk = j / R::kBlockFrames;
                 if (j >= b_first * R::kBlockFrames && blk < nblk) {     // (j is on a block boundary here)
                     ring.request(blk + kQuadAhead);
+#ifdef ALAC_RING_BULK
+                    ring.acquire(blk);
+#else
                     cp_async_wait<kQuadAhead>();            // block blk is in
+#endif
                     ring_block_samples<DEPTH, STEREO>(ring, blk, src.cl, src.cr, src.sh_mix, [&](uint32_t i, int32_t x) {
                         put(r + i, j + i, predict_enc_step<TAPS, WRAP>(x, hist, a, chanshift));
                     });
                     r += R::kBlockFrames;
                 } else {
+#ifdef ALAC_RING_BULK
+                    // (a lane past its last whole block still arrives once per block index: the barrier counts all 32 lanes)
+                    if (j >= b_first * R::kBlockFrames && j % R::kBlockFrames == 0) ring.request(blk + kQuadAhead);
+#endif
                     if (j < n) put(r, j, predict_enc_step<TAPS, WRAP>(src.get(j), hist, a, chanshift));
                     r++;
                 }

@@ -1474,6 +1474,7 @@ struct AsmArgs {
 };
 
 constexpr int kAsmWarps = 4;
+constexpr uint32_t kAsmStageBytes = 3136;   // PCM span of 128 output words of a shift region: 24-bit stereo 1.5 KB, 24-bit mono in a stereo-wide frame 3.1 KB
 constexpr int kHdrWords = 13;       // 7 + 16 + 32 + 16 + 2*(16+128) = 359 bits
 constexpr int kMaxRegions = 8 * 4 + 1;
 
@@ -1484,6 +1485,7 @@ __global__ void __launch_bounds__(kAsmWarps * 32) enc_assemble_kernel(AsmArgs A)
     __shared__ Region s_reg[kAsmWarps][kMaxRegions];
     __shared__ uint32_t s_nreg[kAsmWarps];
     __shared__ uint32_t s_end_word[kAsmWarps];
+    __shared__ __align__(16) uint8_t s_stage[DepthTraits<DEPTH>::kShift ? kAsmWarps : 1][DepthTraits<DEPTH>::kShift ? kAsmStageBytes : 16];
 
     const uint32_t lane = threadIdx.x & 31u, wid = threadIdx.x >> 5;
     const uint32_t rel = blockIdx.x * kAsmWarps + wid;      // chunk-relative packet
@@ -1667,7 +1669,53 @@ __global__ void __launch_bounds__(kAsmWarps * 32) enc_assemble_kernel(AsmArgs A)
             constexpr uint32_t mask = (1u << sh) - 1u;
             const bool stereo = (A.lay.elem_tag[r.elem] == ID_CPE);
             const uint8_t *eb = frame_base + (size_t)A.lay.elem_chan[r.elem] * bps;
-            for (uint32_t g0 = g_lo + lane; g0 < g_hi; g0 += 32u * kU) {
+            // The shift bytes sit at a stride of one sample-frame in the PCM (6 bytes for 24-bit stereo): fetched straight
+            // from global memory that is two to six byte loads per output word.  When the element is (nearly) the whole
+            // frame, the warp instead copies the PCM span of 128 output words into shared memory with aligned 16-byte
+            // loads (an aligned vector that holds one valid byte lies inside a mapped granule) and picks the bytes there.
+            const uint32_t Wb = stereo ? 2u * sh : sh;
+            const uint32_t elem_bytes = (stereo ? 2u : 1u) * bps;
+            uint32_t g_from = g_lo;
+            if (shift != 0 && ((128u * 32u) / Wb + 2u) * stride + elem_bytes + 32u <= kAsmStageBytes) {
+                uint8_t *stage = s_stage[wid];
+                for (uint32_t t0 = g_lo; t0 < g_hi; t0 += 32u * kU) {
+                    const uint32_t gw = min(32u * kU, g_hi - t0);
+                    const uint32_t e_lo = (lead_bits + 32u * t0 - r.dst) / Wb;
+                    const uint32_t e_hi = (lead_bits + 32u * (t0 + gw) - r.dst - 1u) / Wb;
+                    const uint8_t *p0 = eb + (size_t)e_lo * stride;
+                    const uint32_t lead = (uint32_t)(reinterpret_cast<uintptr_t>(p0) & 15u);
+                    const uint4 *a0 = reinterpret_cast<const uint4 *>(p0 - lead);
+                    const uint32_t nvec = (lead + (e_hi - e_lo) * stride + elem_bytes + 15u) >> 4;
+                    __syncwarp();
+                    for (uint32_t v = lane; v < nvec; v += 32) reinterpret_cast<uint4 *>(stage)[v] = __ldg(a0 + v);
+                    __syncwarp();
+                    const uint8_t *sb = stage + lead;
+                    uint32_t word[kU];
+#pragma unroll
+                    for (uint32_t u = 0; u < kU; u++) {
+                        const uint32_t g = min(t0 + lane + 32u * u, g_hi - 1u);
+                        const uint32_t off = lead_bits + 32u * g - r.dst;
+                        auto low = [&](const uint8_t *q) -> uint32_t {      // the sample's low `sh` bits (little-endian container)
+                            return sh == 8 ? (uint32_t)q[0] : ((uint32_t)q[0] | ((uint32_t)q[1] << 8));
+                        };
+                        if (stereo) {
+                            word[u] = bits_from_entries(2 * sh, off, 32u, [&](uint32_t i) -> uint32_t {
+                                const uint8_t *q = sb + (i - e_lo) * stride;
+                                return (low(q) << sh) | low(q + bps);
+                            });
+                        } else {
+                            word[u] = bits_from_entries(sh, off, 32u, [&](uint32_t i) -> uint32_t { return low(sb + (i - e_lo) * stride); });
+                        }
+                    }
+#pragma unroll
+                    for (uint32_t u = 0; u < kU; u++) {
+                        const uint32_t g = t0 + lane + 32u * u;
+                        if (g < g_hi) *reinterpret_cast<uint32_t *>(dst + lead_bytes + 4u * g) = bswap32(word[u]);
+                    }
+                }
+                g_from = g_hi;
+            }
+            for (uint32_t g0 = g_from + lane; g0 < g_hi; g0 += 32u * kU) {
                 uint32_t word[kU];
 #pragma unroll
                 for (uint32_t u = 0; u < kU; u++) {

@@ -59,7 +59,10 @@ struct alac_b200_engine {
     cudaStream_t lanes[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   // compute streams of the host-buffer pipeline
     cudaStream_t cur = nullptr;                             // stream the launch helpers / timers use right now
     uint64_t *h_totals = nullptr;                           // pinned: running byte / frame totals per chunk
+    int32_t *h_status = nullptr;                            // pinned: per-packet status of the latest decode call
+    size_t h_status_cap = 0;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t ev_far = nullptr, ev_far0 = nullptr;        // staged placement (trace): start of the placed call, this rank's last cross-GPU work
     std::string err;
     // encode
     DevBuf pcm, pkt_frame, pkt_samples, seg_first, seg_count, seg_stream, recs, scratch, sizes, offsets, out, state, counters, scan_tiles;
@@ -283,6 +286,7 @@ int32_t alac_b200_engine_create(int32_t device, alac_b200_engine **out_engine)
             return ALAC_B200_CUDA_ERROR;
         }
     }
+    if (cudaEventCreate(&e->ev_far) != cudaSuccess || cudaEventCreate(&e->ev_far0) != cudaSuccess) { delete e; return ALAC_B200_CUDA_ERROR; }
     *out_engine = e;
     return ALAC_B200_OK;
 }
@@ -307,6 +311,8 @@ void alac_b200_engine_destroy(alac_b200_engine *e)
     for (DevBuf *b : bufs) b->release();
     for (auto &ev : e->ev)
         if (ev) cudaEventDestroy(ev);
+    if (e->ev_far) cudaEventDestroy(e->ev_far);
+    if (e->ev_far0) cudaEventDestroy(e->ev_far0);
     for (auto &ev : e->timers) cudaEventDestroy(ev);
     if (e->own_stream) cudaStreamDestroy(e->own_stream);
     if (e->copy_in) cudaStreamDestroy(e->copy_in);
@@ -314,6 +320,7 @@ void alac_b200_engine_destroy(alac_b200_engine *e)
     if (e->copy_out) cudaStreamDestroy(e->copy_out);
     if (e->side) cudaStreamDestroy(e->side);
     if (e->h_totals) cudaFreeHost(e->h_totals);
+    if (e->h_status) cudaFreeHost(e->h_status);
     delete e;
 }
 
@@ -616,6 +623,7 @@ static int32_t encode_core(alac_b200_engine *e, const alac_b200_enc_config *cfg,
     unsigned long long h_place[3] = {0, 0, 0};
     DrainGuard guard(e);
     CU_CHECK(e, cudaEventRecord(e->ev[0], st));
+    if (staged) CU_CHECK(e, cudaEventRecord(e->ev_far0, st));
     // small tables first: they share the H2D copy engine with the PCM chunks and must not queue behind them
     if (!same_tables && P) {
         CU_CHECK(e, cudaMemcpyAsync(e->pkt_frame.p, h_pkt_frame.data(), (size_t)P * 8, cudaMemcpyHostToDevice, st));
@@ -815,6 +823,7 @@ static int32_t encode_core(alac_b200_engine *e, const alac_b200_enc_config *cfg,
         xchg_publish_resolve_kernel<<<1, 32, 0, xs>>>(x, pl->rank, pl->epoch, e->offsets.as<uint64_t>() + P, d_base, d_xerr);
         xchg_done_kernel<<<1, 1, 0, xs>>>(x, pl->rank, pl->epoch);
         e->launches += 2;
+        if (!is_home) cudaEventRecord(e->ev_far, xs);
         if (is_home) {
             // wait for every rank, close the gaps between the slots, release the slots -- all on the device, on a side
             // stream, so that with defer_finish the host returns as soon as this rank's own block is placed
@@ -828,6 +837,7 @@ static int32_t encode_core(alac_b200_engine *e, const alac_b200_enc_config *cfg,
             xchg_compact_kernel<<<compact_ctas, 256, 0, e->side>>>(x, pl->n_ranks, pl->epoch, so, static_cast<const uint8_t *>(pl->staging),
                                                              static_cast<uint8_t *>(pl->dst_packets), pl->dst_capacity, d_xerr);
             xchg_release_kernel<<<1, 1, 0, e->side>>>(x, pl->epoch);
+            cudaEventRecord(e->ev_far, e->side);
             e->launches += 3;
             e->finish_pending = true;
             if (!pl->defer_finish) {
@@ -1067,6 +1077,12 @@ extern "C" int32_t alac_b200_placed_finish(alac_b200_engine *e, uint64_t *out_jo
     CU_CHECK(e, cudaSetDevice(e->device));
     CU_CHECK(e, cudaStreamSynchronize(e->finish_far ? e->copy_out : e->side));
     e->finish_pending = false;
+    if (getenv("ALAC_B200_TRACE")) {        // developer aid: when the cross-GPU work of the job ended, in ms since the encode call started
+        float ms = 0;
+        cudaEventElapsedTime(&ms, e->ev_far0, e->ev_far);
+        fprintf(stderr, "[alac_b200] dev %d: %s at %.2f ms after the placed call started\n", e->device,
+                e->finish_far ? "last block byte handed to the home GPU" : "gaps closed, job buffer complete", ms);
+    }
     unsigned long long h[3] = {0, 0, 0};
     CU_CHECK(e, cudaMemcpy(h, e->xwords.p, 24, cudaMemcpyDeviceToHost));
     if (h[2] & 0xffffffffull) {
@@ -1249,8 +1265,21 @@ static int32_t decode_core(alac_b200_engine *e, const void *cookie, uint32_t coo
     CU_CHECK(e, e->counters.reserve(64 * chunks.size()));
     CU_CHECK(e, e->scan_tiles.reserve((2 * scan_tiles_for(P) + chunks.size() + 2) * 8));
 
-    std::vector<int32_t> h_status(P);                   // (written by the copy-out stream: declared before the guard)
+    // per-packet status on the host: pinned (a copy into pageable memory blocks the caller until everything queued before
+    // it on its stream has run -- on a rank of a staged job that is the block still travelling to the home GPU)
+    if (e->h_status_cap < P) {
+        if (e->h_status) cudaFreeHost(e->h_status);
+        e->h_status = nullptr; e->h_status_cap = 0;
+        const size_t want = (size_t)P + P / 8 + 64;
+        CU_CHECK(e, cudaHostAlloc(&e->h_status, want * sizeof(int32_t), cudaHostAllocDefault));
+        e->h_status_cap = want;
+    }
+    int32_t *h_status = e->h_status;
     DrainGuard guard(e);
+    const bool trace_host = getenv("ALAC_B200_TRACE") != nullptr;
+    const auto host_t0 = std::chrono::steady_clock::now();
+    auto host_ms = [&] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - host_t0).count(); };
+    double hp[5] = {0, 0, 0, 0, 0};
     CU_CHECK(e, cudaEventRecord(e->ev[0], st));
     const uint32_t *d_sizes;
     const uint8_t *d_packets;
@@ -1358,6 +1387,7 @@ static int32_t decode_core(alac_b200_engine *e, const void *cookie, uint32_t coo
     CU_CHECK(e, cudaGetLastError());
     if (multi) for (cudaEvent_t ev : comp_done) CU_CHECK(e, cudaStreamWaitEvent(st, ev, 0));     // join the lanes
     CU_CHECK(e, cudaEventRecord(e->ev[2], st));
+    hp[0] = host_ms();
 
     // ---- results (copy-out stream) ----
     uint64_t copied = 0;
@@ -1375,14 +1405,23 @@ static int32_t decode_core(alac_b200_engine *e, const void *cookie, uint32_t coo
             }
         }
     }
-    CU_CHECK(e, cudaMemcpyAsync(h_status.data(), A.pkt_status, (size_t)P * 4, cudaMemcpyDeviceToHost, e->copy_out));
+    hp[1] = host_ms();
+    // device-resident output: the small result copies follow the kernels on the call's own stream (the copy-out stream
+    // may still be moving a deferred placed block: nothing of this call has to wait for that)
+    cudaStream_t rs = out_host ? e->copy_out : st;
+    CU_CHECK(e, cudaMemcpyAsync(h_status, A.pkt_status, (size_t)P * 4, cudaMemcpyDeviceToHost, rs));
+    hp[2] = host_ms();
     const cudaMemcpyKind to_user = out_host ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice;
-    if (packet_samples) CU_CHECK(e, cudaMemcpyAsync(packet_samples, A.pkt_samples, (size_t)P * 4, to_user, e->copy_out));
-    if (packet_status) CU_CHECK(e, cudaMemcpyAsync(packet_status, A.pkt_status, (size_t)P * 4, to_user, e->copy_out));
-    CU_CHECK(e, cudaEventRecord(e->ev[3], e->copy_out));
-    CU_CHECK(e, cudaStreamSynchronize(e->copy_out));
+    if (packet_samples) CU_CHECK(e, cudaMemcpyAsync(packet_samples, A.pkt_samples, (size_t)P * 4, to_user, rs));
+    if (packet_status) CU_CHECK(e, cudaMemcpyAsync(packet_status, A.pkt_status, (size_t)P * 4, to_user, rs));
+    CU_CHECK(e, cudaEventRecord(e->ev[3], rs));
+    if (out_host) CU_CHECK(e, cudaStreamSynchronize(e->copy_out));
+    hp[3] = host_ms();
     CU_CHECK(e, cudaStreamSynchronize(st));
+    hp[4] = host_ms();
     guard.armed = false;
+    if (trace_host) fprintf(stderr, "[alac_b200] dev %d decode host: queued %.2f, kernels done %.2f, status copy issued %.2f, copy-out drained %.2f, end %.2f ms\n",
+                            e->device, hp[0], hp[1], hp[2], hp[3], hp[4]);
     if (overflow) { e->err = "pcm capacity exceeded"; return ALAC_B200_PARAM_ERROR; }
 
     if (getenv("ALAC_B200_TRACE")) {        // developer aid: per-chunk timeline in ms since the call started

@@ -86,3 +86,42 @@ def test_placed_encode_two_ranks(form):
     rc, out = _run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
                     "--master-port", "29533" if form == "staged" else "29534", "scripts/placed_check.py", "24", form])
     assert rc == 0, out
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs")
+def test_alacconvert_cli_on_two_gpus(tmp_path):
+    """`alacconvert -g 2` (alac_b200_engine_create_multi inside the CLI): the same file as on one GPU, and it decodes back."""
+    from tests import caf_ref
+    exe = os.path.join(os.path.dirname(alac_b200.library_path()), "alacconvert")
+    ch, depth, sr = 2, 24, 96000
+    pcm = synth.make("music", 4096 * 700 + 123, ch, depth, seed=11)
+    wav = str(tmp_path / "in.wav")
+    open(wav, "wb").write(caf_ref.wav_bytes(sr, ch, depth, pcm.tobytes()))
+    outs = []
+    for g in ("1", "2"):
+        caf, back = str(tmp_path / f"g{g}.caf"), str(tmp_path / f"g{g}.wav")
+        subprocess.run([exe, "-k", "1", "-g", g, wav, caf], check=True, stdout=subprocess.DEVNULL)
+        subprocess.run([exe, "-g", g, caf, back], check=True, stdout=subprocess.DEVNULL)
+        assert open(back, "rb").read() == open(wav, "rb").read()
+        outs.append(open(caf, "rb").read())
+    assert outs[0] == outs[1]
+
+
+def test_stats_name_the_kernel_forms(engine):
+    """alac_b200_stats.final_form / search_dense: a dense stereo stream takes the block-ring kernels (two-warp final pass for
+    a launch that does not fill the GPU), a stream at an odd byte offset takes the generic ones -- with the same bytes."""
+    dev = torch.device("cuda", torch.cuda.current_device())
+    ch, depth = 2, 24
+    cfg = alac_b200.EncoderConfig(channels=ch, bit_depth=depth, frames_per_segment=1)
+    frames = 4096 * 64 + 100
+    buf = torch.zeros(frames * 6 + 16, dtype=torch.uint8, device=dev)
+    pcm = synth.corpus_torch(0, frames, ch, depth, dev, seed=5)
+    buf[:pcm.numel()] = pcm
+    dense = engine.encode(buf[:pcm.numel()], cfg)
+    assert dense.stats["final_form"] == 2 and dense.stats["search_dense"] == 1
+    buf[6:6 + pcm.numel()] = pcm.clone()                    # one sample-frame (6 bytes) further: packets off the 16-byte grid
+    odd = engine.encode(buf[6:6 + pcm.numel()], cfg)
+    assert odd.stats["final_form"] == 0 and odd.stats["search_dense"] == 0
+    assert odd.nbytes == dense.nbytes and torch.equal(odd.packets, dense.packets)
+    dec = engine.decode(odd.cookie, odd.packets, odd.sizes)
+    assert dec.status == 0 and torch.equal(dec.pcm, pcm)

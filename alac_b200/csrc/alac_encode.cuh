@@ -1,19 +1,27 @@
 // alac_encode.cuh -- encode kernels.
 //
-//   enc_search_split_kernel + enc_final_kernel   (frames_per_segment = 1: every frame is its own chain)
+//   enc_search_split_kernel + enc_final2_kernel / enc_final_kernel   (frames_per_segment = 1: every frame is its own chain)
 //                       one lane per (frame, channel), one-warp CTAs.  The search kernel runs stages A and B of
 //                       EncodeStereo / EncodeMono (codec/ALACEncoder.cu:290-558, :812-963) -- mixRes search,
 //                       numU/numV search, escape estimate; U and V of a pair sit on adjacent lanes and exchange
 //                       bit counts by shuffle -- and files each channel's final-pass job under its tap count; the
 //                       final kernel runs stage C (final predictor + Golomb emission) with full, uniform warps.
+//                       Dense streams (mono / stereo, packets on 16-byte boundaries) stream their PCM through the
+//                       block ring (QuadRing: 16-byte cp.async, three blocks ahead): enc_search_split_kernel<.., DENSE>
+//                       and enc_final2_kernel -- the latter as a one-warp form, or as a two-warp form (predictor warp ->
+//                       residual tiles in shared memory -> Golomb warp) for launches that do not fill the GPU.
+//                       Everything else goes through enc_final_kernel (per-sample loads).
 //   enc_search_kernel   chained frames (frames_per_segment != 1 or a coefficient-state hand-off): one lane per
 //                       (segment, channel) walks the frames of its segment; stages A, B, C in one kernel, the
 //                       final-pass jobs regrouped by tap count inside the CTA.
-//                       Both forms emit each channel's Golomb stream into a private scratch slab and one
+//                       All forms emit each channel's Golomb stream into a private scratch slab and one
 //                       ElemRec per element.
 //   enc_size_kernel     packet byte sizes from the element records.
+//   scan_*_kernel       exclusive scan of the sizes (two launches, chained across chunks).
+//   xchg_*_kernel       the cross-GPU packet-offset exchange and the gap compaction of staged placement.
 //   enc_assemble_kernel one warp per packet: gathers header / shift bytes / Golomb streams /
-//                       escape samples into the packet at its scanned offset (32-bit stores).
+//                       escape samples into the packet at its scanned offset (32-bit stores); words inside one long
+//                       region take a short path (funnel shift of two slab words, PCM span staged in shared memory).
 #pragma once
 #include "alac_device.cuh"
 #include <type_traits>

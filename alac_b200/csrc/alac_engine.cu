@@ -1367,8 +1367,8 @@ static int32_t decode_core(alac_b200_engine *e, const void *cookie, uint32_t coo
         }
         t_dec.push_back(e->timer());
         // regular mono / stereo groups go to the fused kernel (entropy and finish warps side by side).  Not for the depths with
-        // shift bytes (24 / 32 bit): there the parallel phase re-reads the packet for every sample, which the single
-        // finish warp of the fused kernel cannot hide (24-bit: 4.2 ms either way; 32-bit: 5.3 ms fused against 4.8 ms)
+        // shift bytes (24 / 32 bit): there the output phase merges bytes re-read from the packet, too much for the single
+        // finish warp of the fused kernel (one hour of 24/96: 6.8 ms either way; ten hours: 59.6 ms fused against 54.3 ms)
         static const int fused_mode = [] { const char *v = getenv("ALAC_B200_FUSED"); return v ? atoi(v) : -1; }();   // developer override: 0 never, 1 always
         A.fused = (nch <= 2 && (fused_mode < 0 ? (depth == 16 || depth == 20) : fused_mode != 0)) ? 1u : 0u;
         cudaEvent_t mid[2] = {e->new_event(), e->new_event()};

@@ -208,7 +208,7 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": rt / 1e6, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * sf / rt, "higher_is_better": True,
         "scaling": W.scaling, "vs_baseline": None, "dtype": "int32", "data": "synthetic",
-        "config": {"workload": W.label(), "sample": f"{sf} sample-frames per step "
+        "config": {"workload": W.label(), "name": W.name, "sample": f"{sf} sample-frames per step "
                    f"({sf / W.rate / 60:.1f} min of audio), {threads} host threads x {frames_per_thread} packets"},
         "x_realtime": rt / W.rate,
         "encode_msamples_s": float(np.mean([r[1] for r in rates])) / 1e6,

@@ -197,3 +197,56 @@ def test_round_trip_identity(oracle, ch, depth):
         es = oracle.Encoder(ch, depth).encode_stream(pcm, 0)
         back, st = oracle.Decoder(es.cookie).decode_stream(es.packets, es.sizes)
         assert not st.any() and np.array_equal(back, pcm)
+
+
+def _one_walk_pc_block(x, coefs, taps, chanbits, denshift=9):
+    """The kernels' formulation of pc_block's 4 / 8-tap paths (alac_device.cuh lms_adapt / predict_enc_step), restated in
+    Python: both error signs are ONE walk on left = |err| with left -= w * ((|b| + c) >> denshift), c = 0 or 2^denshift - 1,
+    a tap is updated while left > 0, and the update adds sign(b) * (+1 for err < 0, -1 otherwise)."""
+    def sext(v, bits):
+        v &= (1 << bits) - 1
+        return v - (1 << bits) if v >> (bits - 1) else v
+    a = [int(c) for c in coefs[:taps]]
+    n = len(x)
+    res = [0] * n
+    res[0] = int(x[0])
+    for j in range(1, min(taps + 1, n)):
+        res[j] = sext(int(x[j]) - int(x[j - 1]), chanbits)
+    for j in range(taps + 1, n):
+        top = int(x[j - taps - 1])
+        b = [top - int(x[j - 1 - k]) for k in range(taps)]
+        acc = sext((1 << (denshift - 1)) - sum(a[k] * b[k] for k in range(taps)), 32)     # (int32 arithmetic, as in C and on the GPU)
+        err = sext(int(x[j]) - top - (acc >> denshift), chanbits)
+        res[j] = err
+        m = -1 if err < 0 else 0
+        nsg, c, left = -2 * m - 1, m & ((1 << denshift) - 1), abs(err)
+        for k in range(taps - 1, -1, -1):
+            sb = (b[k] > 0) - (b[k] < 0)
+            if left > 0:
+                a[k] = sext(a[k] + sb * nsg, 16)
+            left -= (taps - k) * ((sb * b[k] + c) >> denshift)
+    coefs[:taps] = np.array(a, np.int16)
+    return np.array(res, np.int32)
+
+
+@pytest.mark.parametrize("taps", [4, 8])
+@pytest.mark.parametrize("chanbits", [16, 17, 21, 25])
+def test_one_walk_ladder_equals_the_reference_pc_block(oracle, taps, chanbits):
+    """The sign-LMS ladder as the CUDA kernels compute it (one walk on |err|, predicated update: DESIGN.md section 4) against
+    the reference's own pc_block object (codec/dp_enc.c:236-329), residuals and adapted coefficients, on signals that make
+    the walk stop early, run through, hit err = 0 and hit history differences of 0 and +-1."""
+    use_ref = oracle.have_reference()
+    rng = np.random.default_rng(taps * 31 + chanbits)
+    amp = 1 << (chanbits - 2)
+    signals = [
+        (rng.integers(-amp, amp, 1500) // rng.integers(1, 64)).astype(np.int32),                        # noise of one scale
+        (np.cumsum(rng.integers(-3, 4, 1500)) + (amp // 4 * np.sin(np.arange(1500) / 17.0))).astype(np.int32),   # smooth: small errors, walk stops early
+        np.repeat(rng.integers(-amp, amp, 150), 10).astype(np.int32),                                   # plateaus: b = 0, err = 0
+        (rng.integers(-1, 2, 1500)).astype(np.int32),                                                   # |b| <= 2
+    ]
+    for x in signals:
+        ca, cb_ = oracle.init_coefs(32), oracle.init_coefs(32)
+        want = oracle.pc_block(x, ca, taps, chanbits, reference=use_ref)
+        got = _one_walk_pc_block(x, cb_, taps, chanbits)
+        assert np.array_equal(got, want[:len(x)])
+        assert np.array_equal(ca[:taps], cb_[:taps])

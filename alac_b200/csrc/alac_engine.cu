@@ -917,7 +917,7 @@ struct Shard {
     uint64_t first_packet = 0, packets = 0, first_stream = 0;
     int32_t rc = 0;
     uint64_t np = 0, bytes = 0, base = 0, frames = 0;
-    alac_b200_stats st;
+    alac_b200_stats st = {};
 };
 
 // Contiguous frame ranges, cut at multiples of frames_per_segment packets (whole streams when a stream is one chain)
